@@ -1,0 +1,372 @@
+"""Dihedral-group tables that parameterise the orbit-tying kernels (host side, numpy).
+
+Host-side mirror of the reference's ``design_opt/models/group_action.py``: the dihedral group
+D_n acting on the n legs, its subgroups ``H_d`` (cyclic), ``K_i`` (one reflection) and ``H_k_l``
+(dihedral), their leg orbits, the closest-sub/super-group lattice, and ``LearnedGroup`` with the
+alpha-interpolated subgroup name ``"<sub>><alpha>><super>><n>"``.
+
+It is written from the group's closed form rather than from permutation matrices: element
+``rho_k`` sends leg i to (k+i) mod n, ``pi_k`` sends i to (k-i) mod n
+(reference ``group_action.py:19-41``).  Only the tables the device kernels consume are on the
+hot path (``get_cur_orbits`` :322-325, ``get_cur_subgroup_embeds`` :443-458,
+``get_cur_subgroup_symmetrizer`` :426-441); the epsilon-greedy lattice walk is once-per-epoch
+host bookkeeping kept API-compatible (:461-473).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict, defaultdict
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+
+class DihedralGroupElement:
+    """One element of D_n: a leg permutation plus its 2x2 action on xy offsets."""
+
+    def __init__(self, name: str, n: int, k: int, type: str, x_axis_index: int = 0):
+        self.name, self.n, self.k, self.type, self.x_axis_index = name, n, k, type, x_axis_index
+        legs = np.arange(n)
+        unit = 2.0 * np.pi / n
+        if type == 'rho':
+            self.map_to = (k + legs) % n
+            c, s = np.cos(unit * k), np.sin(unit * k)
+            self.matrix = np.array([[c, -s], [s, c]])
+            self.trans_angle = lambda phi, _a=unit * k: (_a + phi) % (2 * np.pi)
+        elif type == 'pi':
+            self.map_to = (k - legs) % n
+            a = unit * (k - x_axis_index)
+            c, s = np.cos(a), np.sin(a)
+            self.matrix = np.array([[c, s], [s, -c]])
+            self.trans_angle = lambda phi, _a=a: (_a - phi) % (2 * np.pi)
+        else:
+            raise NotImplementedError(type)
+        self.map_to = self.map_to.astype(np.int64)
+        self.permutation = np.zeros((n, n), dtype=np.int64)
+        self.permutation[self.map_to, legs] = 1
+        # a permutation matrix is orthogonal: inverse == transpose
+        self.permutation_inv = self.permutation.T.copy()
+
+
+def _subgroup_element_names(n: int, type: int, a: int, b: int) -> List[str]:
+    names: List[str] = []
+
+    def add(nm):
+        if nm not in names:
+            names.append(nm)
+
+    if type == 1:
+        for i in range(n // a):
+            add(f'rho_{a * i}')
+    elif type == 2:
+        add('rho_0'); add(f'pi_{a}')
+    elif type == 3:
+        for i in range(n // a):
+            add(f'rho_{a * i}'); add(f'pi_{b + a * i}'); add(f'pi_{(b - a * i) % n}')
+    else:
+        raise NotImplementedError(type)
+    return names
+
+
+class DihedralSubgroup:
+    """A subgroup of D_n with its leg orbits (1-based legs; representative = smallest leg)."""
+
+    def __init__(self, name, n, type, group_elements, group_elements_idx, multi_table=None,
+                 a=0, b=0, x_axis_index=0):
+        self.name, self.n, self.type, self.x_axis_index = name, n, type, x_axis_index
+        self.group_elements, self.group_elements_idx, self.multi_table = group_elements, group_elements_idx, multi_table
+        self.elements = OrderedDict((nm, group_elements[nm]) for nm in _subgroup_element_names(n, type, a, b))
+        self.elements_set = set(self.elements)
+        self.size = len(self.elements_set)
+        self.elements_idx = [group_elements_idx[nm] for nm in group_elements if nm in self.elements]
+        self.elements_indicator = torch.tensor([[1.0 if nm in self.elements else 0.0 for nm in group_elements]])
+
+        # who maps leg i onto leg j (last element in insertion order wins, like the reference)
+        self.adj_matrix = np.zeros((n, n), dtype=np.int64)
+        self.trans_matrix_name = [[None] * n for _ in range(n)]
+        self.trans_matrix = [[None] * n for _ in range(n)]
+        self.trans_matrix_name_all = [[[] for _ in range(n)] for _ in range(n)]
+        self.trans_matrix_all = [[[] for _ in range(n)] for _ in range(n)]
+        for g_name, g in self.elements.items():
+            for i in range(n):
+                j = int(g.map_to[i])
+                self.adj_matrix[i, j] = 1
+                self.trans_matrix_name[i][j] = g_name
+                self.trans_matrix[i][j] = g.matrix
+                self.trans_matrix_name_all[i][j].append(g_name)
+                self.trans_matrix_all[i][j].append(g.matrix)
+
+        self.orbits = OrderedDict()
+        self.orbits_trans_matrix = OrderedDict()
+        self.reprentative_set_defaults = OrderedDict()
+        seen = np.zeros(n, dtype=bool)
+        for i in range(n):
+            if seen[i]:
+                continue
+            members = np.flatnonzero(self.adj_matrix[i]) + 1
+            rep = int(members[0])
+            seen[members - 1] = True
+            self.orbits[rep] = members
+            self.orbits_trans_matrix[rep] = np.stack([self.trans_matrix[rep - 1][o - 1] for o in members], axis=0)
+            # orientation is ambiguous iff two elements carry rep onto the same leg with different matrices
+            unique = all(np.allclose(m, self.trans_matrix[rep - 1][o - 1], atol=1e-6)
+                         for o in members for m in self.trans_matrix_all[rep - 1][o - 1])
+            if unique:
+                self.reprentative_set_defaults[rep] = (False, None)
+            else:
+                ang = 2 * np.pi / n * (rep - 1 - x_axis_index / 2)
+                self.reprentative_set_defaults[rep] = (True, np.array([np.cos(ang), np.sin(ang)]))
+
+
+class DihedralGroup:
+    def __init__(self, n: int, x_axis_index: int = 0):
+        self.n = n
+        self.group_elements = OrderedDict()
+        self.group_elements_idx = OrderedDict()
+        for t in ('rho', 'pi'):
+            for k in range(n):
+                nm = f'{t}_{k}'
+                self.group_elements_idx[nm] = len(self.group_elements)
+                self.group_elements[nm] = DihedralGroupElement(nm, n, k, t, x_axis_index)
+
+        # multiplication table by closed form: (perm, matrix) of g1*g2 identifies g3
+        self.multi_table = OrderedDict()
+        for n1, g1 in self.group_elements.items():
+            row = OrderedDict()
+            for n2, g2 in self.group_elements.items():
+                perm = g1.map_to[g2.map_to]
+                mat = g1.matrix @ g2.matrix
+                row[n2] = None
+                for n3, g3 in self.group_elements.items():
+                    if np.array_equal(g3.map_to, perm) and np.abs(mat - g3.matrix).sum() < 1e-6:
+                        row[n2] = n3
+            self.multi_table[n1] = row
+
+        mk = lambda nm, t, **kw: DihedralSubgroup(nm, n, t, self.group_elements, self.group_elements_idx,
+                                                  self.multi_table, x_axis_index=x_axis_index, **kw)
+        self.subgroups = OrderedDict()
+        for d in range(1, n + 1):
+            if n % d == 0:
+                self.subgroups[f'H_{d}'] = mk(f'H_{d}', 1, a=d)
+        for i in range(n):
+            self.subgroups[f'K_{i}'] = mk(f'K_{i}', 2, a=i)
+        for k in range(1, n):
+            if n % k == 0:
+                for l in range(k):
+                    self.subgroups[f'H_{k}_{l}'] = mk(f'H_{k}_{l}', 3, a=k, b=l)
+
+        self.subgroups_idx = OrderedDict((nm, i) for i, nm in enumerate(self.subgroups))
+        self.subgroups_element_num = OrderedDict((nm, sg.size) for nm, sg in self.subgroups.items())
+
+        # Hasse diagram: keep only covering relations (plus the reflexive pair, like the reference)
+        self.subgroup_struct = OrderedDict((nm, OrderedDict(sub=set(), super=set())) for nm in self.subgroups)
+        items = list(self.subgroups.items())
+        for n1, s1 in items:
+            for n2, s2 in items:
+                if not s1.elements_set <= s2.elements_set:
+                    continue
+                between = any(n3 not in (n1, n2) and s1.elements_set <= s3.elements_set <= s2.elements_set
+                              for n3, s3 in items)
+                if not between:
+                    self.subgroup_struct[n1]['super'].add(n2)
+                    self.subgroup_struct[n2]['sub'].add(n1)
+
+
+class LearnedGroup(torch.nn.Module):
+    """Current design subgroup and its tables; drop-in for the reference's ``LearnedGroup``."""
+
+    def __init__(self, ns, x_axis_index=0, struct_subgroup=True, updating_subgroup=True,
+                 init_subgroup_name=None, subgroup_alpha_gap=3):
+        super().__init__()
+        self.ns = ns
+        self.is_struct_subgroup = struct_subgroup
+        self.Gs = OrderedDict((i, DihedralGroup(i, x_axis_index=x_axis_index)) for i in ns)
+
+        # subgroups of D_i and D_j that act by the same set of 2x2 matrices
+        self.Gs_sub_structure = {}
+        for i in ns:
+            self.Gs_sub_structure[i] = {}
+            for ni, si in self.Gs[i].subgroups.items():
+                self.Gs_sub_structure[i][ni] = {}
+                for j in ns:
+                    if j == i:
+                        continue
+                    twins = set()
+                    for nj, sj in self.Gs[j].subgroups.items():
+                        if si.size != sj.size:
+                            continue
+                        if all(any(np.allclose(gi.matrix, gj.matrix) for gj in sj.elements.values())
+                               for gi in si.elements.values()):
+                            twins.add(nj)
+                    self.Gs_sub_structure[i][ni][j] = twins
+
+        self.cur_subgroup_name = init_subgroup_name
+        self.is_updating_subgroup = updating_subgroup
+        self.backup_subgroup_name = self.cur_subgroup_name
+        self.subgroup_alpha_gap = subgroup_alpha_gap
+        self.random_prob_init = 0.0
+        self.random_prob_end = 0.0
+        self.random_prob_epoch = 1
+        self.random_prob = self.random_prob_init
+        self.value_subgroup = defaultdict(float)
+        self.count_subgroup = defaultdict(lambda: 1e-6)
+        self.count = 1
+        self.info_update_subgroup = {}
+        self.subgroup_embeds = dict()
+        self.num_all_elements = 2 * sum(ns)
+        self.element_indicator_slice = {}
+        at = 0
+        for i in ns:
+            self.element_indicator_slice[i] = slice(at, at + 2 * i)
+            at += 2 * i
+        self.get_cur_subgroup_embeds()
+
+    # ---- name parsing -------------------------------------------------------------------
+    def _get_parsed_names(self, inpt_name=None):
+        sub, alpha, supr, num = (inpt_name if inpt_name is not None else self.cur_subgroup_name).split('>')
+        alpha, num = int(alpha), int(num)
+        n_sub = self.Gs[num].subgroups_element_num[sub]
+        n_super = self.Gs[num].subgroups_element_num[supr]
+        frac = n_sub / n_super
+        return {
+            'sub': sub, 'alpha': alpha, 'super': supr, 'num': num,
+            'alpha_ratio': (1 - frac) / self.subgroup_alpha_gap * alpha + frac,
+            'close_to': sub if alpha > self.subgroup_alpha_gap / 2 else supr,
+            'sub_size': n_sub, 'super_size': n_super,
+        }
+
+    def _close_subgroup(self) -> DihedralSubgroup:
+        p = self._get_parsed_names()
+        return self.Gs[p['num']].subgroups[p['close_to']]
+
+    def get_cur_num(self):
+        return self._get_parsed_names()['num']
+
+    def get_cur_orbits(self):
+        return self._close_subgroup().orbits
+
+    def get_cur_orbits_matrix(self, representative):
+        return self._close_subgroup().orbits_trans_matrix[representative]
+
+    def get_cur_reprentative_set_defaults(self, representative):
+        return self._close_subgroup().reprentative_set_defaults[representative]
+
+    # ---- tables consumed by the kernels -------------------------------------------------
+    def get_cur_subgroup_symmetrizer(self):
+        p = self._get_parsed_names()
+        sub = self.Gs[p['num']].subgroups[p['sub']].elements
+        sup = self.Gs[p['num']].subgroups[p['super']].elements
+        a = p['alpha_ratio']
+        out = []
+        for nm, g in sup.items():
+            ratio = a / len(sub) if nm in sub else (1 - a) / (len(sup) - len(sub))
+            out.append({'matrix': g.matrix, 'permutation_inv': g.permutation_inv, 'ratio': ratio})
+        return out
+
+    def _update_cur_subgroup_embeds(self):
+        p = self._get_parsed_names()
+        ind_sub = self.Gs[p['num']].subgroups[p['sub']].elements_indicator
+        ind_super = self.Gs[p['num']].subgroups[p['super']].elements_indicator
+        beta = (1 - p['alpha_ratio']) / (p['super_size'] - p['sub_size'] + 1e-6)
+        embed = torch.zeros(self.num_all_elements)
+        embed[self.element_indicator_slice[p['num']]] = ind_sub * (p['alpha_ratio'] / p['sub_size'] - beta) + ind_super * beta
+        self.subgroup_embeds[self.cur_subgroup_name] = embed
+
+    def get_cur_subgroup_embeds(self):
+        if self.cur_subgroup_name not in self.subgroup_embeds:
+            self._update_cur_subgroup_embeds()
+        return self.subgroup_embeds[self.cur_subgroup_name]
+
+    def leg_representatives(self, index_base: int) -> np.ndarray:
+        """``rep[leg]`` for legs 0..index_base-1 (leg 0 = root digit, maps to itself)."""
+        rep = np.arange(index_base, dtype=np.int32)
+        for r, members in self.get_cur_orbits().items():
+            for m in members:
+                rep[int(m)] = int(r)
+        return rep
+
+    # ---- lattice walk (host bookkeeping) ------------------------------------------------
+    def _update_random_porb(self):
+        slope = (self.random_prob_end - self.random_prob_init) / self.random_prob_epoch
+        self.random_prob = max(self.random_prob_end, slope * self.count + self.random_prob_init)
+
+    def _update_count(self):
+        self.count_subgroup[self.cur_subgroup_name] += 1
+        self.count += 1
+
+    def store_cur_subgroup_name(self):
+        self.backup_subgroup_name = self.cur_subgroup_name
+
+    def restore_cur_subgroup_name(self):
+        self.cur_subgroup_name = self.backup_subgroup_name
+
+    def set_cur_subgroup_name(self, name):
+        self.cur_subgroup_name = name
+
+    def _get_in_group_neibor_subgroup_name(self, inpt_name):
+        p = self._get_parsed_names(inpt_name)
+        num, gap = p['num'], self.subgroup_alpha_gap
+        out = []
+        coarse = gap == 1 or not np.allclose(self.random_prob, self.random_prob_end) or self.count < 20
+        if coarse or p['alpha'] == 0:
+            assert p['sub'] == p['super']
+            s = self.Gs[num].subgroup_struct[p['sub']]
+        if coarse:
+            out = [f'{g}>0>{g}>{num}' for g in s['sub'] | s['super']]
+        elif p['alpha'] == 0:
+            out += [f"{a}>1>{p['super']}>{num}" for a in s['sub'] if a != p['super']]
+            out += [f"{p['sub']}>{gap - 1}>{a}>{num}" for a in s['super'] if a != p['sub']]
+        else:
+            down = f"{p['super']}>0>{p['super']}>{num}" if p['alpha'] == 1 else f"{p['sub']}>{p['alpha'] - 1}>{p['super']}>{num}"
+            up = f"{p['sub']}>0>{p['sub']}>{num}" if p['alpha'] == gap - 1 else f"{p['sub']}>{p['alpha'] + 1}>{p['super']}>{num}"
+            out = [down, up]
+        return list(set(out))
+
+    def get_neibor_subgroup_name(self):
+        if not self.is_struct_subgroup:
+            return list({f'{sg}>0>{sg}>{n}' for n, g in self.Gs.items() for sg in g.subgroups})
+        p = self._get_parsed_names()
+        inside = self._get_in_group_neibor_subgroup_name(self.cur_subgroup_name) + [self.cur_subgroup_name]
+        outside = []
+        if p['alpha'] == 0:
+            for j, twins in self.Gs_sub_structure[p['num']][p['sub']].items():
+                for sg in twins:
+                    nm = f'{sg}>0>{sg}>{j}'
+                    outside.append(nm)
+                    outside.extend(self._get_in_group_neibor_subgroup_name(nm))
+        for nm in inside:
+            q = self._get_parsed_names(nm)
+            if q['alpha'] == 0:
+                for j, twins in self.Gs_sub_structure[q['num']][q['sub']].items():
+                    outside.extend(f'{sg}>0>{sg}>{j}' for sg in twins)
+        return list(set(inside + outside))
+
+    def _set_value_subgroup(self, name, v, beta=0.2):
+        self.value_subgroup[name] = v * beta + self.value_subgroup[name] * (1 - beta)
+
+    def _get_value_subgroup(self, name):
+        return self.value_subgroup[name]
+
+    def update_all_values(self, value_dict):
+        for k, v in value_dict.items():
+            self._set_value_subgroup(k, v)
+
+    def update_subgroup(self, episode_reward):
+        self._update_count()
+        self._update_random_porb()
+        cand = self.get_neibor_subgroup_name()
+        if self.is_updating_subgroup:
+            vals = np.array([self._get_value_subgroup(k) for k in cand])
+            if np.random.uniform() < self.random_prob:
+                self.cur_subgroup_name = cand[np.argsort(vals)[-2]]
+            else:
+                self.cur_subgroup_name = cand[vals.argmax()]
+
+    def get_info(self):
+        info = {
+            'subgroup_freq': {k: v / self.count for k, v in self.count_subgroup.items()},
+            'subgroup_value': dict(self.value_subgroup),
+            'random_prob': self.random_prob,
+        }
+        info.update(self.info_update_subgroup)
+        return info
