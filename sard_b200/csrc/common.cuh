@@ -1,0 +1,75 @@
+// Shared helpers for the sard_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/sard_b200.h"
+
+int sard_set_error(const char* fmt, ...);
+
+#define SARD_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return sard_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define SARD_LAUNCH_OK(name)                                                                 \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess)                                                                  \
+      return sard_set_error("launch %s failed: %s", name, cudaGetErrorString(e__));          \
+  } while (0)
+
+#define SARD_REQUIRE(cond, msg)                                                              \
+  do {                                                                                       \
+    if (!(cond)) return sard_set_error("%s:%d requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+  } while (0)
+
+#define SARD_TRY(call)                                                                       \
+  do {                                                                                       \
+    int r__ = (call);                                                                        \
+    if (r__ != 0) return r__;                                                                \
+  } while (0)
+
+static inline cudaStream_t as_stream(sard_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid sizing: a multiple of the SM count for grid-stride kernels (148 SMs on B200).
+static inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  long long cap = 148LL * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case SARD_ACT_RELU: return v > 0.f ? v : 0.f;
+    case SARD_ACT_TANH: return tanhf(v);
+    case SARD_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  switch (act) {
+    case SARD_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case SARD_ACT_TANH: return 1.f - y * y;
+    case SARD_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}

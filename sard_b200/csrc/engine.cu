@@ -1,0 +1,509 @@
+// Network schedules: one host call launches the whole forward(+loss+backward) of a net over one run.
+// The schedules mirror the reference modules layer by layer:
+//   tower   = RunningNorm -> in_fc -> L x (GraphConv -> act)          (running_norm.py, gnn.py:54-68)
+//   critic  = tower -> MLP(tanh) on root rows -> cat ext -> value_head  (transform2act_critic.py:78-108)
+//   stage   = tower -> cat ext -> JSMLP by body index -> [sin] -> [orbit tie] -> loss
+//                                                                      (transform2act_policy.py:233-335)
+// All buffers come from a caller-provided workspace carved deterministically (bump allocation), so
+// the GATHER and COMPUTE phases of a data-parallel step can be separate calls.
+#include "common.cuh"
+#include <string.h>
+
+thread_local char g_sard_err[1024] = "";
+int sard_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_sard_err, sizeof(g_sard_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+extern "C" const char* sard_last_error_string(void) { return g_sard_err; }
+extern "C" int sard_abi_version(void) { return SARD_ABI_VERSION; }
+extern "C" int sard_struct_sizes(int* out, int capacity) {
+  const int sizes[] = {(int)sizeof(SardArena), (int)sizeof(SardSel), (int)sizeof(SardGatherOut), (int)sizeof(SardGemm),
+                       (int)sizeof(SardWGrad), (int)sizeof(SardPolicyLoss), (int)sizeof(SardAdamSeg), (int)sizeof(SardDense),
+                       (int)sizeof(SardTower), (int)sizeof(SardValueNet), (int)sizeof(SardIndexLinear),
+                       (int)sizeof(SardPolicyStage), (int)sizeof(SardPolicyNet)};
+  const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
+  for (int i = 0; i < n && i < capacity; ++i) out[i] = sizes[i];
+  return n;
+}
+
+namespace {
+
+struct Bump {
+  float* base; long long off;
+  float* f(long long n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~3LL; return p; }
+  int* i(long long n) { return reinterpret_cast<int*>(f(n)); }
+};
+
+inline int r4(int v) { return (v + 3) & ~3; }
+inline long long wg_partials(int M, int N1, int N2, int chunk_rows) {
+  return (long long)ceil_div(M, chunk_rows) * N1 * (N2 + 1);
+}
+
+constexpr int WG_CHUNK = 256;     // rows per weight-gradient chunk
+constexpr int IL_TILE = 128;      // rows per grouped-GEMM tile (= BM of gemm_kernel)
+
+struct TowerBufs {
+  float* x; int ldx;
+  int *nd_graph, *nd_arena, *body, *root_row;
+  float* partials;
+  float* xa[SARD_MAX_LAYERS];
+  float* hout;
+  float *dz[2], *dxa;
+  int maxh;
+};
+
+void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBufs& t) {
+  t.ldx = r4(tw.D);
+  t.x = b.f((long long)n * t.ldx);
+  t.nd_graph = b.i(n); t.nd_arena = b.i(n); t.body = b.i(n); t.root_row = b.i(B);
+  t.partials = b.f(2LL * tw.D * ceil_div(n > 0 ? n : 1, 128));
+  t.maxh = 0;
+  for (int l = 0; l <= tw.L; ++l) t.maxh = tw.h[l] > t.maxh ? tw.h[l] : t.maxh;
+  for (int l = 0; l < tw.L; ++l) t.xa[l] = b.f((long long)n * 2 * tw.h[l]);
+  t.hout = b.f((long long)n * tw.h[tw.L]);
+  if (train) {
+    t.dz[0] = b.f((long long)n * t.maxh);
+    t.dz[1] = b.f((long long)n * t.maxh);
+    t.dxa = b.f((long long)n * 2 * t.maxh);
+  } else {
+    t.dz[0] = t.dz[1] = t.dxa = nullptr;
+  }
+}
+
+long long tower_wg_need(const SardTower& tw, int n) {
+  long long need = wg_partials(n, tw.h[0], tw.D, WG_CHUNK);
+  for (int l = 1; l <= tw.L; ++l) {
+    long long v = wg_partials(n, tw.h[l], 2 * tw.h[l - 1], WG_CHUNK);
+    need = v > need ? v : need;
+  }
+  return need;
+}
+
+SardGemm gemm0() { SardGemm g; memset(&g, 0, sizeof(g)); return g; }
+SardWGrad wgrad0() { SardWGrad w; memset(&w, 0, sizeof(w)); w.chunk_rows = WG_CHUNK; return w; }
+
+int tower_gather(const SardTower& tw, const SardArena* arena, const SardSel* sel, int lead, int tail, int nconst,
+                 const float* consts, int onehot, TowerBufs& t, sard_stream_t st) {
+  SardGatherOut o;
+  o.lead = lead; o.tail = tail; o.nconst = nconst; o.onehot = onehot; o.consts = consts;
+  o.x = t.x; o.ldx = t.ldx; o.nd_graph = t.nd_graph; o.nd_arena = t.nd_arena; o.body = t.body; o.root_row = t.root_row;
+  SARD_REQUIRE(lead + tail + nconst + (onehot ? 3 : 0) == tw.D, "tower input width != column program");
+  return sard_gather_nodes(arena, sel, &o, st);
+}
+
+// normalise + in_fc + GraphConv layers
+int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, const SardSel* sel, TowerBufs& t,
+                  sard_stream_t st) {
+  const int n = sel->n;
+  SARD_TRY(sard_norm_apply(t.x, t.ldx, n, tw.D, tw.mean, tw.inv, tw.count, 5.0f, st));
+  {
+    SardGemm g = gemm0();
+    g.A = t.x; g.lda = t.ldx; g.B0 = P + tw.in_w; g.ldb0 = tw.D; g.b_split = tw.D; g.bias = P + tw.in_b;
+    g.M = n; g.N = tw.h[0]; g.R = tw.D; g.act = SARD_ACT_NONE;
+    if (tw.L > 0) { g.Y = t.xa[0] + tw.h[0]; g.ldy = 2 * tw.h[0]; } else { g.Y = t.hout; g.ldy = tw.h[0]; }
+    SARD_TRY(sard_linear_fwd(&g, st));
+  }
+  for (int l = 1; l <= tw.L; ++l) {
+    const int hi = tw.h[l - 1], ho = tw.h[l];
+    float* xin = t.xa[l - 1];
+    SARD_TRY(sard_csr_aggregate(xin + hi, 2 * hi, xin, 2 * hi, nullptr, 0, nullptr, 0, 0, n, hi, t.nd_graph, t.nd_arena,
+                                sel->cum, sel->node_base, arena->in_ptr, arena->in_nbr, st));
+    SardGemm g = gemm0();
+    g.A = xin; g.lda = 2 * hi; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
+    g.bias = tw.has_bias ? P + tw.bl[l - 1] : nullptr;
+    g.M = n; g.N = ho; g.R = 2 * hi; g.act = tw.act;
+    if (l < tw.L) { g.Y = t.xa[l] + ho; g.ldy = 2 * ho; } else { g.Y = t.hout; g.ldy = ho; }
+    SARD_TRY(sard_linear_fwd(&g, st));
+  }
+  return 0;
+}
+
+// dz_top: [n, h[L]] gradient w.r.t. the pre-activation of the last layer (act' already applied), in t.dz[0]
+int tower_backward(const SardTower& tw, const float* P, float* G, const SardArena* arena, const SardSel* sel,
+                   TowerBufs& t, float* wg_scratch, sard_stream_t st) {
+  const int n = sel->n;
+  int cur = 0;
+  for (int l = tw.L; l >= 1; --l) {
+    const int hi = tw.h[l - 1], ho = tw.h[l];
+    float* dz = t.dz[cur];
+    float* xin = t.xa[l - 1];
+    SardWGrad w = wgrad0();
+    w.P = dz; w.ldp = ho; w.Q = xin; w.ldq = 2 * hi; w.M = n; w.N1 = ho; w.N2 = 2 * hi;
+    w.dW0 = G + tw.wl[l - 1]; w.ldw0 = hi; w.dW1 = G + tw.wr[l - 1]; w.ldw1 = hi; w.w_split = hi;
+    w.db = tw.has_bias ? G + tw.bl[l - 1] : nullptr; w.partials = wg_scratch;
+    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SardGemm g = gemm0();
+    g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
+    g.M = n; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
+    SARD_TRY(sard_linear_bwd_data(&g, st));
+    // dz_{l-1} = (dxa[:, hi:2hi] + A^T dxa[:, 0:hi]) * act'(y_{l-1});  layer 0 (in_fc) has no activation
+    const float* yprev = (l - 1 >= 1) ? xin + hi : nullptr;
+    SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[cur ^ 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
+                                t.nd_graph, t.nd_arena, sel->cum, sel->node_base, arena->out_ptr, arena->out_nbr, st));
+    cur ^= 1;
+  }
+  SardWGrad w = wgrad0();
+  w.P = t.dz[cur]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;
+  w.dW0 = G + tw.in_w; w.ldw0 = tw.D; w.w_split = tw.D; w.db = G + tw.in_b; w.partials = wg_scratch;
+  return sard_linear_bwd_weight(&w, st);
+}
+
+// ext[B, 3*64] written at `ext` with leading dimension ld_ext; e1[k]: [B,64] hidden activations
+int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena* arena, const SardSel* sel,
+                     float* const e1[3], float* ext, int ld_ext, sard_stream_t st) {
+  for (int k = 0; k < 3; ++k) {
+    SardGemm g = gemm0();
+    g.A = arena->ext[k]; g.lda = arena->ext_dim[k]; g.a_rows = sel->ids;
+    g.B0 = P + enc[k][0].w; g.ldb0 = enc[k][0].in; g.b_split = enc[k][0].in; g.bias = P + enc[k][0].b;
+    g.M = sel->B; g.N = enc[k][0].out; g.R = enc[k][0].in; g.act = SARD_ACT_RELU; g.Y = e1[k]; g.ldy = enc[k][0].out;
+    SARD_REQUIRE(enc[k][0].in == arena->ext_dim[k], "encoder input dim != arena ext dim");
+    SARD_TRY(sard_linear_fwd(&g, st));
+    SardGemm h = gemm0();
+    h.A = e1[k]; h.lda = enc[k][0].out; h.B0 = P + enc[k][1].w; h.ldb0 = enc[k][1].in; h.b_split = enc[k][1].in;
+    h.bias = P + enc[k][1].b; h.M = sel->B; h.N = enc[k][1].out; h.R = enc[k][1].in; h.act = SARD_ACT_RELU;
+    h.Y = ext + k * SARD_EXT_DIM; h.ldy = ld_ext;
+    SARD_TRY(sard_linear_fwd(&h, st));
+  }
+  return 0;
+}
+
+// dext: [B, 3*64] gradient w.r.t. the pre-activation of the encoders' second layer (relu' applied)
+int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const SardArena* arena, const SardSel* sel,
+                      float* const e1[3], const float* dext, int ld_dext, float* de1, float* wg_scratch,
+                      sard_stream_t st) {
+  for (int k = 0; k < 3; ++k) {
+    const float* dz2 = dext + k * SARD_EXT_DIM;
+    SardWGrad w = wgrad0();
+    w.P = dz2; w.ldp = ld_dext; w.Q = e1[k]; w.ldq = enc[k][0].out; w.M = sel->B; w.N1 = enc[k][1].out; w.N2 = enc[k][1].in;
+    w.dW0 = G + enc[k][1].w; w.ldw0 = enc[k][1].in; w.w_split = enc[k][1].in; w.db = G + enc[k][1].b; w.partials = wg_scratch;
+    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SardGemm g = gemm0();
+    g.A = dz2; g.lda = ld_dext; g.B0 = P + enc[k][1].w; g.ldb0 = enc[k][1].in; g.b_split = enc[k][1].in;
+    g.M = sel->B; g.N = enc[k][1].in; g.R = enc[k][1].out; g.Y = de1; g.ldy = enc[k][1].in;
+    g.Dact = e1[k]; g.ldd = enc[k][0].out; g.dact0 = SARD_ACT_RELU; g.dact1 = SARD_ACT_RELU; g.dsplit = g.N;
+    SARD_TRY(sard_linear_bwd_data(&g, st));
+    SardWGrad w1 = wgrad0();
+    w1.P = de1; w1.ldp = enc[k][0].out; w1.Q = arena->ext[k]; w1.ldq = arena->ext_dim[k]; w1.q_rows = sel->ids;
+    w1.M = sel->B; w1.N1 = enc[k][0].out; w1.N2 = enc[k][0].in;
+    w1.dW0 = G + enc[k][0].w; w1.ldw0 = enc[k][0].in; w1.w_split = enc[k][0].in; w1.db = G + enc[k][0].b; w1.partials = wg_scratch;
+    SARD_TRY(sard_linear_bwd_weight(&w1, st));
+  }
+  return 0;
+}
+
+long long enc_wg_need(const SardDense enc[3][2], int B) {
+  long long need = 0;
+  for (int k = 0; k < 3; ++k)
+    for (int j = 0; j < 2; ++j) {
+      long long v = wg_partials(B, enc[k][j].out, enc[k][j].in, WG_CHUNK);
+      need = v > need ? v : need;
+    }
+  return need;
+}
+
+// ------------------------------------------------------------------------------------------ critic
+struct ValueBufs {
+  TowerBufs t;
+  double* rec;
+  float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
+  float* dcat; float* dm[2]; float* de1; float* wg;
+};
+
+void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
+  carve_tower(b, net.tower, n, B, train, vb.t);
+  vb.rec = reinterpret_cast<double*>(b.f(2 * (1 + 2 * net.tower.D) + 2));
+  for (int k = 0; k < 3; ++k) vb.e1[k] = b.f((long long)B * net.enc[k][0].out);
+  const int m_last = net.n_mlp > 0 ? net.mlp[net.n_mlp - 1].out : net.tower.h[net.tower.L];
+  vb.ldcat = m_last + 3 * SARD_EXT_DIM;
+  vb.cat = b.f((long long)B * vb.ldcat);
+  int maxm = 0;
+  for (int j = 0; j < net.n_mlp; ++j) {
+    vb.m[j] = (j < net.n_mlp - 1) ? b.f((long long)B * net.mlp[j].out) : vb.cat;
+    maxm = net.mlp[j].out > maxm ? net.mlp[j].out : maxm;
+  }
+  vb.v = b.f(B); vb.dv = b.f(B); vb.sq = b.f(B);
+  if (train) {
+    vb.dcat = b.f((long long)B * vb.ldcat);
+    vb.dm[0] = b.f((long long)B * (maxm > 0 ? maxm : 4)); vb.dm[1] = b.f((long long)B * (maxm > 0 ? maxm : 4));
+    vb.de1 = b.f((long long)B * SARD_EXT_DIM);
+    long long need = tower_wg_need(net.tower, n);
+    long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
+    for (int j = 0; j < net.n_mlp; ++j) { v = wg_partials(B, net.mlp[j].out, net.mlp[j].in, WG_CHUNK); need = v > need ? v : need; }
+    v = wg_partials(B, 1, vb.ldcat, WG_CHUNK); need = v > need ? v : need;
+    vb.wg = b.f(need);
+  } else {
+    vb.dcat = vb.dm[0] = vb.dm[1] = vb.de1 = vb.wg = nullptr;
+  }
+}
+
+}  // namespace
+
+extern "C" long long sard_value_workspace(const SardValueNet* net, int n, int B) {
+  Bump b{nullptr, 0};
+  ValueBufs vb;
+  carve_value(b, *net, n, B, true, vb);
+  return b.off + 64;
+}
+
+extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, const SardSel* sel, int train, int phase,
+                              float inv_B_global, double* moments_local, const double* moments_all, int n_records,
+                              float* sq_err_sum, float* ws, long long ws_floats, sard_stream_t st) {
+  if (sel->B <= 0 || sel->n <= 0) return 0;
+  const SardTower& tw = net->tower;
+  SARD_REQUIRE(tw.L >= 0 && tw.L <= SARD_MAX_LAYERS && net->n_mlp <= SARD_MAX_MLP, "layer counts");
+  // train: 0 = eval, 1 = RunningNorm update + loss + backward, 2 = RunningNorm update + forward only
+  const bool upd = train != 0, bwd = train == 1;
+  Bump b{ws, 0};
+  ValueBufs vb;
+  carve_value(b, *net, sel->n, sel->B, bwd, vb);
+  SARD_REQUIRE(b.off <= ws_floats, "value workspace too small");
+  const float* P = net->P;
+  float* G = net->G;
+  const int n = sel->n, B = sel->B;
+  if (phase & SARD_PHASE_GATHER) {
+    SARD_TRY(tower_gather(tw, arena, sel, arena->d_obs, 0, net->nconst, net->consts, net->onehot, vb.t, st));
+    if (upd) {
+      double* rec = moments_local ? moments_local : vb.rec;
+      SARD_TRY(sard_norm_moments(vb.t.x, vb.t.ldx, n, tw.D, vb.t.partials, rec, st));
+    }
+  }
+  if (!(phase & SARD_PHASE_COMPUTE)) return 0;
+  if (upd) {
+    const double* recs = moments_all ? moments_all : (moments_local ? moments_local : vb.rec);
+    SARD_TRY(sard_norm_update(recs, moments_all ? n_records : 1, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, st));
+  } else {
+    SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
+  }
+  SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat, st));
+  // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
+  const int hL = tw.h[tw.L];
+  for (int j = 0; j < net->n_mlp; ++j) {
+    SardGemm g = gemm0();
+    if (j == 0) { g.A = vb.t.hout; g.lda = hL; g.a_rows = vb.t.root_row; }
+    else { g.A = vb.m[j - 1]; g.lda = net->mlp[j - 1].out; }
+    g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in; g.bias = P + net->mlp[j].b;
+    g.M = B; g.N = net->mlp[j].out; g.R = net->mlp[j].in; g.act = net->mlp[j].act;
+    g.Y = vb.m[j]; g.ldy = (j < net->n_mlp - 1) ? net->mlp[j].out : vb.ldcat;
+    SARD_TRY(sard_linear_fwd(&g, st));
+  }
+  SARD_REQUIRE(net->n_mlp > 0, "critic without mlp is not supported");
+  {
+    SardGemm g = gemm0();
+    g.A = vb.cat; g.lda = vb.ldcat; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat; g.bias = P + net->head.b;
+    g.M = B; g.N = 1; g.R = vb.ldcat; g.Y = vb.v; g.ldy = 1;
+    SARD_REQUIRE(net->head.in == vb.ldcat, "value head width");
+    SARD_TRY(sard_linear_fwd(&g, st));
+  }
+  if (!bwd) return sard_value_loss(vb.v, sel->ids, B, nullptr, 0.f, nullptr, nullptr, arena->values, st);
+
+  SARD_TRY(sard_value_loss(vb.v, sel->ids, B, arena->returns, inv_B_global, vb.dv, vb.sq, nullptr, st));
+  if (sq_err_sum) SARD_TRY(sard_loss_reduce(vb.sq, B, 1, sq_err_sum, nullptr, 0, nullptr, st));
+  // head backward
+  {
+    SardWGrad w = wgrad0();
+    w.P = vb.dv; w.ldp = 1; w.Q = vb.cat; w.ldq = vb.ldcat; w.M = B; w.N1 = 1; w.N2 = vb.ldcat;
+    w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg;
+    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SardGemm g = gemm0();
+    g.A = vb.dv; g.lda = 1; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat;
+    g.M = B; g.N = vb.ldcat; g.R = 1; g.Y = vb.dcat; g.ldy = vb.ldcat;
+    g.Dact = vb.cat; g.ldd = vb.ldcat; g.dact0 = net->mlp[net->n_mlp - 1].act; g.dact1 = SARD_ACT_RELU;
+    g.dsplit = vb.ldcat - 3 * SARD_EXT_DIM;
+    SARD_TRY(sard_linear_bwd_data(&g, st));
+  }
+  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
+                             vb.de1, vb.wg, st));
+  // MLP backward (dz of layer j lives in dzj with leading dimension ldz)
+  const float* dzj = vb.dcat; int ldz = vb.ldcat; int cur = 0;
+  SARD_CUDA(cudaMemsetAsync(vb.t.dz[0], 0, sizeof(float) * (size_t)n * hL, as_stream(st)));
+  for (int j = net->n_mlp - 1; j >= 0; --j) {
+    SardWGrad w = wgrad0();
+    w.P = dzj; w.ldp = ldz; w.M = B; w.N1 = net->mlp[j].out; w.N2 = net->mlp[j].in;
+    if (j == 0) { w.Q = vb.t.hout; w.ldq = hL; w.q_rows = vb.t.root_row; } else { w.Q = vb.m[j - 1]; w.ldq = net->mlp[j - 1].out; }
+    w.dW0 = G + net->mlp[j].w; w.ldw0 = net->mlp[j].in; w.w_split = net->mlp[j].in; w.db = G + net->mlp[j].b; w.partials = vb.wg;
+    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SardGemm g = gemm0();
+    g.A = dzj; g.lda = ldz; g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in;
+    g.M = B; g.N = net->mlp[j].in; g.R = net->mlp[j].out; g.dsplit = g.N;
+    if (j == 0) {
+      // scatter into the root rows of the tower gradient; other rows stay zero
+      g.Y = vb.t.dz[0]; g.ldy = hL; g.y_rows = vb.t.root_row;
+      g.Dact = vb.t.hout; g.ldd = hL; g.dact0 = tw.L > 0 ? tw.act : SARD_ACT_NONE; g.dact1 = g.dact0;
+    } else {
+      g.Y = vb.dm[cur]; g.ldy = net->mlp[j - 1].out;
+      g.Dact = vb.m[j - 1]; g.ldd = net->mlp[j - 1].out; g.dact0 = net->mlp[j - 1].act; g.dact1 = g.dact0;
+    }
+    SARD_TRY(sard_linear_bwd_data(&g, st));
+    if (j > 0) { dzj = vb.dm[cur]; ldz = net->mlp[j - 1].out; cur ^= 1; }
+  }
+  return tower_backward(tw, P, G, arena, sel, vb.t, vb.wg, st);
+}
+
+// ------------------------------------------------------------------------------------------ policy stage
+namespace {
+struct StageBufs {
+  TowerBufs t;
+  double* rec;
+  float* e1[3]; float* ext;
+  int *srow, *spos, *grp_ptr, *tiles, *chunks, *grp_chunk_ptr, *counts, *sort_scratch;
+  float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
+  float* dout; float* gstat; float* dH[2]; float* dxs; float* dext; float* de1; float* wg;
+  int max_tiles, max_chunks;
+};
+
+void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, int n, int B, bool train, StageBufs& sb) {
+  carve_tower(b, s.tower, n, B, train, sb.t);
+  sb.rec = reinterpret_cast<double*>(b.f(2 * (1 + 2 * s.tower.D) + 2));
+  for (int k = 0; k < 3; ++k) sb.e1[k] = b.f((long long)B * net.enc[k][0].out);
+  sb.ext = b.f((long long)B * 3 * SARD_EXT_DIM);
+  sb.max_tiles = ceil_div(n, IL_TILE) + s.max_index;
+  sb.max_chunks = ceil_div(n, WG_CHUNK) + s.max_index;
+  sb.srow = b.i(n); sb.spos = b.i(n); sb.grp_ptr = b.i(s.max_index + 1);
+  sb.tiles = b.i(4LL * sb.max_tiles); sb.chunks = b.i(4LL * sb.max_chunks);
+  sb.grp_chunk_ptr = b.i(s.max_index + 1); sb.counts = b.i(4);
+  sb.sort_scratch = b.i((long long)(ceil_div(n > 0 ? n : 1, 256) + 2) * s.max_index);
+  const int hL = s.tower.h[s.tower.L];
+  sb.ldxs = hL + 3 * SARD_EXT_DIM;
+  sb.xs = b.f((long long)n * sb.ldxs);
+  int maxo = 4;
+  for (int j = 0; j < s.n_il - 1; ++j) { sb.H[j] = b.f((long long)n * s.il[j].out); maxo = s.il[j].out > maxo ? s.il[j].out : maxo; }
+  sb.ldo = r4(s.out_dim);
+  sb.out = b.f((long long)n * sb.ldo);
+  sb.pre = b.f((long long)n * sb.ldo);
+  if (train) {
+    sb.dout = b.f((long long)n * sb.ldo);
+    sb.gstat = b.f((long long)B * (4 + s.out_dim));
+    sb.dH[0] = b.f((long long)n * maxo); sb.dH[1] = b.f((long long)n * maxo);
+    sb.dxs = b.f((long long)n * sb.ldxs);
+    sb.dext = b.f((long long)B * 3 * SARD_EXT_DIM);
+    sb.de1 = b.f((long long)B * SARD_EXT_DIM);
+    long long need = tower_wg_need(s.tower, n);
+    long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
+    for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * (s.il[j].in + 1); need = v > need ? v : need; }
+    sb.wg = b.f(need);
+  } else {
+    sb.dout = sb.gstat = sb.dH[0] = sb.dH[1] = sb.dxs = sb.dext = sb.de1 = sb.wg = nullptr;
+  }
+}
+}  // namespace
+
+extern "C" long long sard_policy_workspace(const SardPolicyNet* net, int stage, int n, int B) {
+  Bump b{nullptr, 0};
+  StageBufs sb;
+  carve_stage(b, *net, net->stage[stage], n, B, true, sb);
+  return b.off + 64;
+}
+
+extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardArena* arena, const SardSel* sel, int train,
+                               int phase, float clip_eps, float inv_B_global, double* moments_local,
+                               const double* moments_all, int n_records, float* stats, float* outputs,
+                               float* log_prob_run, float* ws, long long ws_floats, sard_stream_t st) {
+  if (sel->B <= 0 || sel->n <= 0) return 0;
+  SARD_REQUIRE(stage >= 0 && stage < 3, "stage");
+  const SardPolicyStage& s = net->stage[stage];
+  const SardTower& tw = s.tower;
+  SARD_REQUIRE(s.n_il >= 1 && s.n_il <= SARD_MAX_IL, "index-linear layer count");
+  const bool upd = train != 0, bwd = train == 1;
+  Bump b{ws, 0};
+  StageBufs sb;
+  carve_stage(b, *net, s, sel->n, sel->B, bwd, sb);
+  SARD_REQUIRE(b.off <= ws_floats, "policy workspace too small");
+  const float* P = net->P;
+  float* G = net->G;
+  const int n = sel->n, B = sel->B;
+  if (phase & SARD_PHASE_GATHER) {
+    const int nconst = (stage == SARD_STAGE_CONTROL) ? 0 : net->nconst;
+    SARD_TRY(tower_gather(tw, arena, sel, s.lead, s.tail, nconst, net->consts, 0, sb.t, st));
+    if (upd) {
+      double* rec = moments_local ? moments_local : sb.rec;
+      SARD_TRY(sard_norm_moments(sb.t.x, sb.t.ldx, n, tw.D, sb.t.partials, rec, st));
+    }
+  }
+  if (!(phase & SARD_PHASE_COMPUTE)) return 0;
+  if (upd) {
+    const double* recs = moments_all ? moments_all : (moments_local ? moments_local : sb.rec);
+    SARD_TRY(sard_norm_update(recs, moments_all ? n_records : 1, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, st));
+  } else {
+    SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
+  }
+  SARD_TRY(tower_forward(tw, P, arena, sel, sb.t, st));
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, st));
+  SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
+                              sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, st));
+  const int hL = tw.h[tw.L];
+  SARD_TRY(sard_concat_sorted(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph, n,
+                              sb.xs, sb.ldxs, st));
+  SARD_REQUIRE(s.il[0].in == sb.ldxs, "first index-linear input width");
+  for (int j = 0; j < s.n_il; ++j) {
+    const bool last = j == s.n_il - 1;
+    SardGemm g = gemm0();
+    g.A = j == 0 ? sb.xs : sb.H[j - 1]; g.lda = j == 0 ? sb.ldxs : s.il[j - 1].out;
+    g.B0 = s.il[j].W; g.ldb0 = s.il[j].in; g.b_split = s.il[j].in; g.b_group_stride = (long long)s.il[j].out * s.il[j].in;
+    g.bias = s.il[j].b; g.bias_group_stride = s.il[j].out;
+    g.M = n; g.N = s.il[j].out; g.R = s.il[j].in;
+    g.tiles = sb.tiles; g.num_tiles = sb.counts; g.max_tiles = sb.max_tiles;
+    if (last) {
+      g.act = SARD_ACT_NONE; g.post = s.post; g.Y = sb.out; g.ldy = sb.ldo; g.y_rows = sb.srow;
+      g.Ypre = s.post != SARD_POST_NONE ? sb.pre : nullptr;
+      SARD_REQUIRE(s.il[j].out == s.out_dim, "last index-linear width");
+    } else {
+      g.act = s.il_act; g.Y = sb.H[j]; g.ldy = s.il[j].out;
+    }
+    SARD_TRY(sard_linear_fwd(&g, st));
+  }
+  // loss (eval: log-probs only)
+  SardPolicyLoss L;
+  memset(&L, 0, sizeof(L));
+  L.out = sb.out; L.ld_out = sb.ldo; L.pre = s.post != SARD_POST_NONE ? sb.pre : nullptr;
+  L.log_std = s.log_std >= 0 ? P + s.log_std : nullptr;
+  L.d = s.out_dim;
+  L.act_col = stage == SARD_STAGE_CONTROL ? 0 : (stage == SARD_STAGE_ATTR ? 1 : SARD_ACTION_DIM - 1);
+  L.tie_c0 = s.tie_c0; L.tie_c1 = s.tie_c1;
+  L.nd_arena = sb.t.nd_arena; L.cum = sel->cum; L.node_base = sel->node_base; L.ids = sel->ids; L.B = B;
+  L.actions = arena->actions; L.rep_local = (s.tie_c1 > s.tie_c0) ? arena->rep_local : nullptr;
+  L.clip_eps = clip_eps; L.inv_B = inv_B_global;
+  L.tied_out = outputs; L.log_prob_run = log_prob_run;
+  if (bwd) {
+    L.advantages = arena->advantages; L.fixed_log_probs = arena->fixed_log_probs;
+    L.dout = sb.dout; L.ld_dout = sb.ldo; L.gstat = sb.gstat;
+  } else if (!upd) {
+    L.log_prob_out = arena->fixed_log_probs;
+  }
+  if (outputs) SARD_REQUIRE(sb.ldo == s.out_dim || true, "outputs use the padded leading dimension");
+  SARD_TRY(stage == SARD_STAGE_SKEL ? sard_cat_loss(&L, st) : sard_gauss_loss(&L, st));
+  if (!bwd) return 0;
+  SARD_TRY(sard_loss_reduce(sb.gstat, B, 4 + s.out_dim, stats, s.log_std >= 0 ? G + s.log_std : nullptr, s.out_dim,
+                            s.log_std >= 0 ? P + s.log_std : nullptr, st));
+
+  // ---- backward through the JSMLP (sorted row space) ----
+  const float* dz = sb.dout; int ldz = sb.ldo; const int* dz_rows = sb.srow; int cur = 0;
+  for (int j = s.n_il - 1; j >= 0; --j) {
+    const float* Aj = j == 0 ? sb.xs : sb.H[j - 1];
+    const int lda = j == 0 ? sb.ldxs : s.il[j - 1].out;
+    SardWGrad w = wgrad0();
+    w.P = dz; w.ldp = ldz; w.p_rows = dz_rows; w.Q = Aj; w.ldq = lda; w.M = n; w.N1 = s.il[j].out; w.N2 = s.il[j].in;
+    w.chunks = sb.chunks; w.num_chunks = sb.counts + 1; w.max_chunks = sb.max_chunks;
+    w.grp_chunk_ptr = sb.grp_chunk_ptr; w.n_groups = s.max_index; w.slot_of_group = s.slot_of_index;
+    w.dW0 = s.GT + s.il[j].gW; w.ldw0 = s.il[j].in; w.w_split = s.il[j].in; w.w_slot_stride = (long long)s.il[j].out * s.il[j].in;
+    w.db = s.GT + s.il[j].gb; w.b_slot_stride = s.il[j].out; w.partials = sb.wg;
+    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SardGemm g = gemm0();
+    g.A = dz; g.lda = ldz; g.a_rows = dz_rows;
+    g.B0 = s.il[j].W; g.ldb0 = s.il[j].in; g.b_split = s.il[j].in; g.b_group_stride = (long long)s.il[j].out * s.il[j].in;
+    g.M = n; g.N = s.il[j].in; g.R = s.il[j].out; g.dsplit = g.N;
+    g.tiles = sb.tiles; g.num_tiles = sb.counts; g.max_tiles = sb.max_tiles;
+    if (j == 0) { g.Y = sb.dxs; g.ldy = sb.ldxs; }
+    else { g.Y = sb.dH[cur]; g.ldy = s.il[j - 1].out; g.Dact = sb.H[j - 1]; g.ldd = s.il[j - 1].out; g.dact0 = s.il_act; g.dact1 = s.il_act; }
+    SARD_TRY(sard_linear_bwd_data(&g, st));
+    if (j > 0) { dz = sb.dH[cur]; ldz = s.il[j - 1].out; dz_rows = nullptr; cur ^= 1; }
+  }
+  SARD_TRY(sard_unsort_grad(sb.dxs, sb.ldxs, sb.spos, sel->cum, sel->node_base, B, sb.t.hout, hL, hL,
+                            tw.L > 0 ? tw.act : SARD_ACT_NONE, sb.t.dz[0], hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM,
+                            sb.dext, 3 * SARD_EXT_DIM, st));
+  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg, st));
+  return tower_backward(tw, P, G, arena, sel, sb.t, sb.wg, st);
+}

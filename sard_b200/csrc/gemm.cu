@@ -1,0 +1,328 @@
+// Linear layers of the SARD nets: fp32 SIMT tiled GEMMs with fused prologues/epilogues.
+//
+//   forward        Y  = post(act(A W^T + b))        A [M,R] rows optionally gathered, W [N,R]
+//   backward-data  dA = (dY W) * act'(saved output)  same weight storage read transposed
+//   backward-weight dW += dY^T A, db += colsum(dY)   per-chunk partial products + ordered reduction
+//
+// Three things make these specific to the path rather than library GEMMs: (1) the weight operand can
+// be the concatenation [lin_l | lin_r] of a GraphConv layer without materialising it, (2) row tiles
+// can carry a body index selecting the weight slab of an IndexLinear (grouped GEMM over rows sorted
+// by index), (3) rows can be gathered/scattered through index vectors (root readout, un-sorting).
+// fp32 FFMA is used because the parity target is rtol 1e-4 against an fp64 oracle; see DESIGN.md
+// for the tcgen05 3xTF32 plan.
+#include "common.cuh"
+
+template <int BM, int BN, int BK, int TM, int TN, bool NT>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_kernel(const SardGemm g) {
+  constexpr int NTH = (BM / TM) * (BN / TN);
+  constexpr int EA = BM * BK / NTH;
+  constexpr int EB = BN * BK / NTH;
+  static_assert(BM * BK % NTH == 0 && BN * BK % NTH == 0, "tile/thread mismatch");
+  static_assert(TM % 4 == 0 || TM == 4, "TM");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  int row_start, row_end, group = 0;
+  if (g.tiles) {
+    if ((int)blockIdx.x >= *g.num_tiles) return;
+    const int4 t = reinterpret_cast<const int4*>(g.tiles)[blockIdx.x];
+    row_start = t.x; row_end = t.y; group = t.z;
+  } else {
+    row_start = blockIdx.x * BM;
+    row_end = min(g.M, row_start + BM);
+    if (row_start >= g.M) return;
+  }
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x;
+  const float* B0 = g.B0 + (size_t)group * g.b_group_stride;
+  const float* B1 = g.B1 ? g.B1 + (size_t)group * g.b_group_stride : nullptr;
+
+  // per-thread A rows are fixed across k-blocks: resolve the gather once
+  long long a_off[EA];
+#pragma unroll
+  for (int i = 0; i < EA; ++i) {
+    const int m = (tid + i * NTH) / BK;
+    const int grow = row_start + m;
+    if (grow < row_end) a_off[i] = (long long)(g.a_rows ? g.a_rows[grow] : grow) * g.lda;
+    else a_off[i] = -1;
+  }
+
+  float ra[EA], rb[EB];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      const int r = (tid + i * NTH) % BK;
+      const int kk = k0 + r;
+      ra[i] = (a_off[i] >= 0 && kk < g.R) ? __ldg(g.A + a_off[i] + kk) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int idx = tid + i * NTH;
+      int r, c;
+      if (NT) { r = idx % BK; c = idx / BK; } else { c = idx % BN; r = idx / BN; }
+      const int kk = k0 + r, gc = n0 + c;
+      float v = 0.f;
+      if (kk < g.R && gc < g.N) {
+        if (NT) v = kk < g.b_split ? __ldg(B0 + (size_t)gc * g.ldb0 + kk) : __ldg(B1 + (size_t)gc * g.ldb1 + (kk - g.b_split));
+        else    v = gc < g.b_split ? __ldg(B0 + (size_t)kk * g.ldb0 + gc) : __ldg(B1 + (size_t)kk * g.ldb1 + (gc - g.b_split));
+      }
+      rb[i] = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      const int idx = tid + i * NTH;
+      As[buf][idx % BK][idx / BK] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int idx = tid + i * NTH;
+      if (NT) Bs[buf][idx % BK][idx / BK] = rb[i];
+      else    Bs[buf][idx / BN][idx % BN] = rb[i];
+    }
+  };
+
+  const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nkb = (g.R + BK - 1) / BK;
+  int buf = 0;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (kb + 1 < nkb) load_tile((kb + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+      if constexpr (TN % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + j]);
+          b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[buf][k][tx * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kb + 1 < nkb) store_tile(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // epilogue
+  const float* bias = g.bias ? g.bias + (size_t)group * g.bias_group_stride : nullptr;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int grow = row_start + ty * TM + i;
+    if (grow >= row_end) continue;
+    const long long yrow = g.y_rows ? g.y_rows[grow] : grow;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gc = n0 + tx * TN + j;
+      if (gc >= g.N) continue;
+      float v = acc[i][j];
+      if (NT) {
+        if (bias) v += __ldg(bias + gc);
+        v = act_apply(v, g.act);
+        if (g.Ypre) g.Ypre[yrow * g.ldy + gc] = v;
+        if (g.post == SARD_POST_SIN_HALF_PI) v = sinf(v * 1.57079632679489662f);
+      } else if (g.Dact) {
+        const float y = g.Dact[yrow * g.ldd + gc];
+        v *= act_grad_from_output(y, gc < g.dsplit ? g.dact0 : g.dact1);
+      }
+      g.Y[yrow * g.ldy + gc] = v;
+    }
+  }
+}
+
+template <bool NT>
+static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
+  if (g->M <= 0 || g->N <= 0) return 0;
+  SARD_REQUIRE(g->R > 0, "gemm: empty reduction");
+  SARD_REQUIRE(g->B1 != nullptr || g->b_split >= (NT ? g->R : g->N), "gemm: b_split without second source");
+  cudaStream_t st = as_stream(stream);
+  if (g->N <= 16) {
+    constexpr int BM = 128, BN = 16;
+    const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
+    if (tiles <= 0) return 0;
+    dim3 grid(tiles, ceil_div(g->N, BN));
+    gemm_kernel<BM, BN, 16, 4, 2, NT><<<grid, 256, 0, st>>>(*g);
+  } else {
+    constexpr int BM = 128, BN = 64;
+    const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
+    if (tiles <= 0) return 0;
+    dim3 grid(tiles, ceil_div(g->N, BN));
+    gemm_kernel<BM, BN, 16, 8, 4, NT><<<grid, 256, 0, st>>>(*g);
+  }
+  SARD_LAUNCH_OK(NT ? "gemm_kernel<fwd>" : "gemm_kernel<bwd_data>");
+  return 0;
+}
+
+extern "C" int sard_linear_fwd(const SardGemm* g, sard_stream_t stream) { return launch_gemm<true>(g, stream); }
+extern "C" int sard_linear_bwd_data(const SardGemm* g, sard_stream_t stream) { return launch_gemm<false>(g, stream); }
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient: partial[chunk][c1][c2] = sum_{rows of chunk} P[row,c1] Q[row,c2]  (+ colsum(P) at c2==N2)
+// ------------------------------------------------------------------------------------------
+template <int B1, int B2, int BKM, int T1, int T2>
+__global__ void __launch_bounds__((B1 / T1) * (B2 / T2))
+wgrad_kernel(const SardWGrad w) {
+  constexpr int NTH = (B1 / T1) * (B2 / T2);
+  constexpr int EP = B1 * BKM / NTH, EQ = B2 * BKM / NTH;
+  __shared__ __align__(16) float Ps[2][BKM][B1 + 4];
+  __shared__ __align__(16) float Qs[2][BKM][B2 + 4];
+  int rs, re;
+  if (w.chunks) {
+    if ((int)blockIdx.x >= *w.num_chunks) return;
+    const int4 t = reinterpret_cast<const int4*>(w.chunks)[blockIdx.x];
+    rs = t.x; re = t.y;
+  } else {
+    rs = blockIdx.x * w.chunk_rows;
+    re = min(w.M, rs + w.chunk_rows);
+    if (rs >= w.M) return;
+  }
+  const int c10 = blockIdx.y * B1, c20 = blockIdx.z * B2;
+  const int tid = threadIdx.x;
+  const int t1 = tid / (B2 / T2), t2 = tid % (B2 / T2);
+  float acc[T1][T2], bsum[T1];
+#pragma unroll
+  for (int i = 0; i < T1; ++i) {
+    bsum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < T2; ++j) acc[i][j] = 0.f;
+  }
+  float rp[EP], rq[EQ];
+  auto load_tile = [&](int m0) {
+#pragma unroll
+    for (int i = 0; i < EP; ++i) {
+      const int idx = tid + i * NTH, c = idx % B1, r = idx / B1;
+      const int row = m0 + r, gc = c10 + c;
+      float v = 0.f;
+      if (row < re && gc < w.N1) v = __ldg(w.P + (size_t)(w.p_rows ? w.p_rows[row] : row) * w.ldp + gc);
+      rp[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < EQ; ++i) {
+      const int idx = tid + i * NTH, c = idx % B2, r = idx / B2;
+      const int row = m0 + r, gc = c20 + c;
+      float v = 0.f;
+      if (row < re && gc < w.N2) v = __ldg(w.Q + (size_t)(w.q_rows ? w.q_rows[row] : row) * w.ldq + gc);
+      rq[i] = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < EP; ++i) { const int idx = tid + i * NTH; Ps[buf][idx / B1][idx % B1] = rp[i]; }
+#pragma unroll
+    for (int i = 0; i < EQ; ++i) { const int idx = tid + i * NTH; Qs[buf][idx / B2][idx % B2] = rq[i]; }
+  };
+  const int nsteps = (re - rs + BKM - 1) / BKM;
+  int buf = 0;
+  load_tile(rs);
+  store_tile(0);
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + 1 < nsteps) load_tile(rs + (s + 1) * BKM);
+#pragma unroll
+    for (int k = 0; k < BKM; ++k) {
+      float p[T1], q[T2];
+#pragma unroll
+      for (int i = 0; i < T1; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&Ps[buf][k][t1 * T1 + i]);
+        p[i] = v.x; p[i + 1] = v.y; p[i + 2] = v.z; p[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < T2; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&Qs[buf][k][t2 * T2 + j]);
+        q[j] = v.x; q[j + 1] = v.y; q[j + 2] = v.z; q[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < T1; ++i) {
+        bsum[i] += p[i];
+#pragma unroll
+        for (int j = 0; j < T2; ++j) acc[i][j] = fmaf(p[i], q[j], acc[i][j]);
+      }
+    }
+    if (s + 1 < nsteps) store_tile(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int ldpart = w.N2 + 1;
+  float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
+#pragma unroll
+  for (int i = 0; i < T1; ++i) {
+    const int c1 = c10 + t1 * T1 + i;
+    if (c1 >= w.N1) continue;
+#pragma unroll
+    for (int j = 0; j < T2; ++j) {
+      const int c2 = c20 + t2 * T2 + j;
+      if (c2 < w.N2) part[(size_t)c1 * ldpart + c2] = acc[i][j];
+    }
+    if (blockIdx.z == 0 && t2 == 0) part[(size_t)c1 * ldpart + w.N2] = bsum[i];
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
+  const int ldpart = w.N2 + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= w.N1 * ldpart) return;
+  int k0, k1, slot = 0;
+  if (w.grp_chunk_ptr) {
+    const int u = blockIdx.y;
+    k0 = w.grp_chunk_ptr[u]; k1 = w.grp_chunk_ptr[u + 1];
+    if (k0 >= k1) return;
+    slot = w.slot_of_group ? w.slot_of_group[u] : u;
+    if (slot < 0) return;
+  } else {
+    k0 = 0; k1 = nchunks_plain;
+  }
+  float s = 0.f;
+  for (int k = k0; k < k1; ++k) s += w.partials[(size_t)k * w.N1 * ldpart + e];
+  const int c1 = e / ldpart, c2 = e - c1 * ldpart;
+  if (c2 == w.N2) {
+    if (w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
+  } else if (c2 < w.w_split) {
+    w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c2] += s;
+  } else {
+    w.dW1[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw1 + (c2 - w.w_split)] += s;
+  }
+}
+
+extern "C" int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream) {
+  if (w->M <= 0 || w->N1 <= 0 || w->N2 <= 0) return 0;
+  SARD_REQUIRE(w->dW1 != nullptr || w->w_split >= w->N2, "wgrad: w_split without second destination");
+  SARD_REQUIRE(w->partials != nullptr, "wgrad: partials scratch");
+  cudaStream_t st = as_stream(stream);
+  int nchunks;
+  if (w->chunks) {
+    nchunks = w->max_chunks;
+  } else {
+    SARD_REQUIRE(w->chunk_rows > 0, "wgrad: chunk_rows");
+    nchunks = ceil_div(w->M, w->chunk_rows);
+  }
+  if (nchunks <= 0) return 0;
+  dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
+  wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
+  SARD_LAUNCH_OK("wgrad_kernel");
+  dim3 rgrid(ceil_div((long long)w->N1 * (w->N2 + 1), 256), w->grp_chunk_ptr ? w->n_groups : 1);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(*w, w->chunks ? 0 : nchunks);
+  SARD_LAUNCH_OK("wgrad_reduce_kernel");
+  return 0;
+}

@@ -1,0 +1,161 @@
+// RunningNorm (khrylib/rl/core/running_norm.py:22-42): batch moments, running update, apply.
+//
+// Moments are accumulated as SHIFTED sums per 128-row chunk (shift = the chunk's first row), which
+// makes constant columns (the subgroup embedding, the all-zero sim columns of the design stages)
+// come out with variance exactly 0 like the reference's fp64 var_mean, and are merged with the
+// pairwise (Chan) formula in fp64 in a fixed order -> deterministic and rank-count independent.
+#include "common.cuh"
+
+#define NORM_CHUNK 128
+
+__global__ void norm_moments_kernel(const float* __restrict__ x, int ldx, int n, int D,
+                                    float* __restrict__ partials) {
+  const int chunk = blockIdx.x;
+  const int r0 = chunk * NORM_CHUNK, r1 = min(n, r0 + NORM_CHUNK);
+  const float cnt = (float)(r1 - r0);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float shift = x[(size_t)r0 * ldx + c];
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float d = x[(size_t)r * ldx + c] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+    const float m = s1 / cnt;
+    partials[((size_t)chunk * 2 + 0) * D + c] = shift + m;
+    partials[((size_t)chunk * 2 + 1) * D + c] = fmaxf(s2 - s1 * m, 0.f);
+  }
+}
+
+struct Mom { double n, mean, m2; };
+__device__ __forceinline__ Mom mom_merge(Mom a, Mom b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  const double n = a.n + b.n, d = b.mean - a.mean;
+  Mom r;
+  r.n = n;
+  r.mean = a.mean + d * (b.n / n);
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / n);
+  return r;
+}
+
+// one warp per column: lanes take chunks round-robin, then a fixed shuffle tree
+__global__ void norm_merge_chunks_kernel(const float* __restrict__ partials, int n, int D, int nchunks,
+                                         double* __restrict__ record) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (col >= D) return;
+  Mom acc = {0.0, 0.0, 0.0};
+  for (int k = lane; k < nchunks; k += 32) {
+    Mom b;
+    b.n = (double)(min(n, (k + 1) * NORM_CHUNK) - k * NORM_CHUNK);
+    b.mean = (double)partials[((size_t)k * 2 + 0) * D + col];
+    b.m2 = (double)partials[((size_t)k * 2 + 1) * D + col];
+    acc = mom_merge(acc, b);
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Mom other;
+    other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
+    other.mean = __shfl_xor_sync(0xffffffffu, acc.mean, o);
+    other.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, o);
+    // keep the merge order identical on both partners: lower lane's data is always "a"
+    acc = (lane & o) ? mom_merge(other, acc) : mom_merge(acc, other);
+  }
+  if (lane == 0) {
+    record[1 + col] = acc.mean;
+    record[1 + D + col] = acc.m2;
+    if (col == 0) record[0] = (double)n;
+  }
+}
+
+extern "C" int sard_norm_moments(const float* x, int ldx, int n, int D, float* partials, double* record,
+                                 sard_stream_t stream) {
+  SARD_REQUIRE(D > 0 && n >= 0, "norm dims");
+  cudaStream_t st = as_stream(stream);
+  const int nchunks = ceil_div(n, NORM_CHUNK);
+  if (n > 0) {
+    int threads = ((D + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    norm_moments_kernel<<<nchunks, threads, 0, st>>>(x, ldx, n, D, partials);
+    SARD_LAUNCH_OK("norm_moments_kernel");
+  }
+  norm_merge_chunks_kernel<<<ceil_div((long long)D * 32, 256), 256, 0, st>>>(partials, n, D, nchunks, record);
+  SARD_LAUNCH_OK("norm_merge_chunks_kernel");
+  return 0;
+}
+
+__global__ void norm_update_kernel(const double* __restrict__ records, int n_records, int D,
+                                   float* __restrict__ mean, float* __restrict__ var, float* __restrict__ std,
+                                   long long* __restrict__ count, float* __restrict__ inv) {
+  const long long n_old = *count;
+  const int stride = 1 + 2 * D;
+  double m_total = 0.0;
+  for (int k = 0; k < n_records; ++k) m_total += records[(size_t)k * stride];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    Mom acc = {0.0, 0.0, 0.0};
+    for (int k = 0; k < n_records; ++k) {
+      Mom b;
+      b.n = records[(size_t)k * stride];
+      b.mean = records[(size_t)k * stride + 1 + c];
+      b.m2 = records[(size_t)k * stride + 1 + D + c];
+      acc = mom_merge(acc, b);
+    }
+    if (acc.n > 0.0) {
+      const double mean_x = acc.mean, var_x = acc.m2 / acc.n;   // biased (unbiased=False)
+      const double w = (double)n_old / (acc.n + (double)n_old);
+      const double mu = (double)mean[c], v = (double)var[c];
+      const double dm = mean_x - mu;
+      const double v_new = w * v + (1.0 - w) * var_x + w * (1.0 - w) * dm * dm;
+      const double mu_new = w * mu + (1.0 - w) * mean_x;
+      const float sd = (float)sqrt(v_new);
+      var[c] = (float)v_new;
+      mean[c] = (float)mu_new;
+      std[c] = sd;
+      inv[c] = 1.0f / (sd + 1e-8f);
+    } else {
+      inv[c] = 1.0f / (std[c] + 1e-8f);
+    }
+  }
+  if (threadIdx.x == 0) *count = n_old + (long long)(m_total + 0.5);
+}
+
+extern "C" int sard_norm_update(const double* records, int n_records, int D, float* mean, float* var, float* std,
+                                long long* count, float* inv, sard_stream_t stream) {
+  SARD_REQUIRE(n_records >= 1, "n_records");
+  norm_update_kernel<<<1, 256, 0, as_stream(stream)>>>(records, n_records, D, mean, var, std, count, inv);
+  SARD_LAUNCH_OK("norm_update_kernel");
+  return 0;
+}
+
+__global__ void norm_prepare_eval_kernel(const float* __restrict__ std, int D, float* __restrict__ inv) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x)
+    inv[c] = 1.0f / (std[c] + 1e-8f);
+}
+
+extern "C" int sard_norm_prepare_eval(const float* std, int D, float* inv, sard_stream_t stream) {
+  norm_prepare_eval_kernel<<<ceil_div(D, 256), 256, 0, as_stream(stream)>>>(std, D, inv);
+  SARD_LAUNCH_OK("norm_prepare_eval_kernel");
+  return 0;
+}
+
+__global__ void norm_apply_kernel(float* __restrict__ x, int ldx, int n, int D, const float* __restrict__ mean,
+                                  const float* __restrict__ inv, const long long* __restrict__ count, float clip) {
+  if (*count <= 0) return;
+  const long long total = (long long)n * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / D), c = (int)(idx - (long long)r * D);
+    float* p = x + (size_t)r * ldx + c;
+    float v = (*p - __ldg(mean + c)) * __ldg(inv + c);
+    *p = fminf(fmaxf(v, -clip), clip);
+  }
+}
+
+extern "C" int sard_norm_apply(float* x, int ldx, int n, int D, const float* mean, const float* inv,
+                               const long long* count, float clip, sard_stream_t stream) {
+  if (n <= 0) return 0;
+  norm_apply_kernel<<<grid_for((long long)n * D, 256), 256, 0, as_stream(stream)>>>(x, ldx, n, D, mean, inv, count, clip);
+  SARD_LAUNCH_OK("norm_apply_kernel");
+  return 0;
+}

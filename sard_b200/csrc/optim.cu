@@ -1,0 +1,132 @@
+// Gradient-norm clip + Adam over live parameter segments, gated on device.
+// (clip_grad_norm_: khrylib/rl/agents/agent_ppo.py:53-56; torch.optim.Adam single-tensor update;
+//  KL / loss gate: design_opt/agents/transform2act_agent.py:404-407.)
+// The 38 M-parameter IndexLinear tables are never touched densely: segments cover the dense flat
+// parameter buffer plus only the table rows whose body index has ever been seen (rows that never
+// received a gradient keep m = v = 0 and are bit-unchanged by Adam, so skipping them is exact).
+#include "common.cuh"
+
+#define SQ_BLOCKS 1024
+
+__global__ void sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ scratch) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = g[i];
+    s = fmaf(v, v, s);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) scratch[blockIdx.x] = red[0];
+}
+
+__global__ void sqnorm_final_kernel(const float* __restrict__ scratch, int nb, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += (double)scratch[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)red[0];
+}
+
+extern "C" int sard_sqnorm(const float* g, long long n, float* scratch, float* out, sard_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  int nb = (int)((n + 1023) / 1024);
+  if (nb > SQ_BLOCKS) nb = SQ_BLOCKS;
+  if (nb < 1) nb = 1;
+  sqnorm_partial_kernel<<<nb, 256, 0, st>>>(g, n, scratch);
+  SARD_LAUNCH_OK("sqnorm_partial_kernel");
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(scratch, nb, out);
+  SARD_LAUNCH_OK("sqnorm_final_kernel");
+  return 0;
+}
+
+__global__ void adam_prepare_kernel(const float* stats, float inv_B, float inv_world, float inv_cat_nodes,
+                                    const float* sqnorm, float max_norm, int first_only, int use_gate,
+                                    int active_mask, double beta1, double beta2, float* ctl_f, int* ctl_i,
+                                    float* log_row) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float surr_loss = 0.f, kl = 0.f, entropy = 0.f, extra = 0.f;
+  if (stats) {
+    surr_loss = -stats[0] * inv_B;
+    kl = stats[1] * inv_B;
+    entropy = stats[4] * inv_world + stats[2] * inv_cat_nodes;
+    extra = stats[5] * inv_B;
+  }
+  int valid = 1;
+  if (use_gate && (kl > 0.1f || surr_loss > 10.f || !(kl == kl) || !(surr_loss == surr_loss))) valid = 0;
+  const float norm = sqnorm ? sqrtf(sqnorm[0]) : 0.f;
+  float scale = 1.f;
+  const int armed = ctl_i[1];
+  if (max_norm > 0.f && sqnorm && armed) {
+    scale = fminf(1.f, max_norm / (norm + 1e-6f));
+    if (valid && first_only) ctl_i[1] = 0;
+  }
+  ctl_f[0] = scale;
+  ctl_f[1] = (float)valid;
+  ctl_i[0] = valid;
+  for (int g = 0; g < SARD_MAX_GROUPS; ++g) {
+    if (!((active_mask >> g) & 1)) continue;
+    int step = ctl_i[8 + g];
+    if (valid) step += 1;
+    ctl_i[8 + g] = step;
+    const double s = (double)(step > 0 ? step : 1);
+    ctl_f[8 + g] = (float)(1.0 - pow(beta1, s));
+    ctl_f[16 + g] = (float)sqrt(1.0 - pow(beta2, s));
+  }
+  if (log_row) {
+    log_row[0] = surr_loss; log_row[1] = entropy; log_row[2] = kl; log_row[3] = (float)valid;
+    log_row[4] = norm; log_row[5] = extra;
+  }
+}
+
+extern "C" int sard_adam_prepare(const float* stats, float inv_B, float inv_world, float inv_cat_nodes,
+                                 const float* sqnorm, float max_norm, int first_only, int use_gate, int active_mask,
+                                 double beta1, double beta2, float* ctl_f, int* ctl_i, float* log_row,
+                                 sard_stream_t stream) {
+  adam_prepare_kernel<<<1, 32, 0, as_stream(stream)>>>(stats, inv_B, inv_world, inv_cat_nodes, sqnorm, max_norm,
+                                                      first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i,
+                                                      log_row);
+  SARD_LAUNCH_OK("adam_prepare_kernel");
+  return 0;
+}
+
+__global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr, float beta1, float beta2, float eps,
+                                  int active_mask, const float* __restrict__ ctl_f, const int* __restrict__ ctl_i) {
+  if (ctl_i[0] == 0) return;
+  const SardAdamSeg s = segs[blockIdx.y];
+  if (!((active_mask >> s.group) & 1)) return;
+  const float scale = ctl_f[0];
+  const float bc1 = ctl_f[8 + s.group], bc2s = ctl_f[16 + s.group];
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = s.g[i] * scale;
+    float m = s.m[i], v = s.v[i];
+    m = m + (g - m) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * beta2 + (1.f - beta2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / bc2s + eps;
+    s.p[i] = s.p[i] - step_size * (m / denom);
+    s.m[i] = m;
+    s.v[i] = v;
+  }
+}
+
+extern "C" int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max_seg_len, float lr, float beta1,
+                               float beta2, float eps, int active_mask, const float* ctl_f, const int* ctl_i,
+                               sard_stream_t stream) {
+  if (n_seg <= 0 || max_seg_len <= 0) return 0;
+  int gx = (int)((max_seg_len + 255) / 256);
+  if (gx > 256) gx = 256;
+  dim3 grid(gx, n_seg);
+  adam_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i);
+  SARD_LAUNCH_OK("adam_apply_kernel");
+  return 0;
+}

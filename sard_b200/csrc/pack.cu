@@ -1,0 +1,229 @@
+// Packing kernels: neighbour lists, orbit representatives, run gather, stable sort by body index.
+// All integer layouts here are bit-exact restatements of what the reference builds with numpy /
+// torch indexing (transform2act_policy.py:183-202, 421-436; jsmlp.py:33-39).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// Neighbour lists per graph.  One thread owns one graph and walks its edges in order, so each
+// node's list keeps the edge order (the order torch's CPU index_add_ sums in).
+// ------------------------------------------------------------------------------------------
+__global__ void csr_kernel(const int* __restrict__ node_ptr, const int* __restrict__ edge_ptr,
+                           const int* __restrict__ key, const int* __restrict__ val, int T,
+                           int* __restrict__ ptr, int* __restrict__ nbr) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= T) return;
+  const int gn = node_ptr[g], N = node_ptr[g + 1] - gn;
+  const int e0 = edge_ptr[g], E = edge_ptr[g + 1] - e0;
+  for (int v = 0; v < N; ++v) ptr[gn + v] = 0;
+  for (int e = 0; e < E; ++e) ptr[gn + key[e0 + e]] += 1;
+  int run = e0;
+  for (int v = 0; v < N; ++v) { int c = ptr[gn + v]; ptr[gn + v] = run; run += c; }
+  for (int e = 0; e < E; ++e) { int k = key[e0 + e]; nbr[ptr[gn + k]++] = val[e0 + e]; }
+  for (int v = N - 1; v >= 1; --v) ptr[gn + v] = ptr[gn + v - 1];
+  if (N > 0) ptr[gn] = e0;
+  if (g == T - 1) ptr[gn + N] = e0 + E;
+}
+
+extern "C" int sard_build_csr(const int* node_ptr, const int* edge_ptr, const int* esrc, const int* edst, int T,
+                              int* in_ptr, int* in_nbr, int* out_ptr, int* out_nbr, sard_stream_t stream) {
+  if (T <= 0) return 0;
+  const int threads = 128, blocks = ceil_div(T, threads);
+  csr_kernel<<<blocks, threads, 0, as_stream(stream)>>>(node_ptr, edge_ptr, edst, esrc, T, in_ptr, in_nbr);
+  SARD_LAUNCH_OK("csr_kernel(in)");
+  csr_kernel<<<blocks, threads, 0, as_stream(stream)>>>(node_ptr, edge_ptr, esrc, edst, T, out_ptr, out_nbr);
+  SARD_LAUNCH_OK("csr_kernel(out)");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Orbit representatives.
+// ------------------------------------------------------------------------------------------
+__global__ void orbit_rep_kernel(const int* __restrict__ node_ptr, const int* __restrict__ body, int T,
+                                 const int* __restrict__ leg_rep, int base, int* __restrict__ rep_local,
+                                 int* __restrict__ err_flag) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= T) return;
+  const int gn = node_ptr[g], N = node_ptr[g + 1] - gn;
+  for (int i = 0; i < N; ++i) {
+    const int b = body[gn + i];
+    int rep = i;
+    if (b > 0) {
+      const int leg = b % base;
+      const int target = b - leg + leg_rep[leg];
+      if (target != b) {
+        rep = -1;
+        for (int j = 0; j < N; ++j)
+          if (body[gn + j] == target) { rep = j; break; }
+        if (rep < 0) { rep = i; *err_flag = 1; }
+      }
+    }
+    rep_local[gn + i] = rep;
+  }
+}
+
+extern "C" int sard_orbit_rep(const int* node_ptr, const int* body_ind, int T, const int* leg_rep, int index_base,
+                              int* rep_local, int* err_flag, sard_stream_t stream) {
+  if (T <= 0) return 0;
+  SARD_REQUIRE(index_base >= 2, "index_base");
+  orbit_rep_kernel<<<ceil_div(T, 128), 128, 0, as_stream(stream)>>>(node_ptr, body_ind, T, leg_rep, index_base,
+                                                                   rep_local, err_flag);
+  SARD_LAUNCH_OK("orbit_rep_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Run gather: one warp per graph, lanes stream the graph's N x ldx output block.
+// ------------------------------------------------------------------------------------------
+struct GatherP {
+  const float* obs; int d_obs; const int* node_ptr; const int* stage; const int* body_ind;
+  const int* ids; const int* cum; int B; int node_base;
+  int lead, tail, nconst, onehot; const float* consts;
+  float* x; int ldx; int* nd_graph; int* nd_arena; int* body; int* root_row;
+};
+
+__global__ void gather_kernel(const GatherP p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B) return;
+  const int gid = p.ids[warp];
+  const int a0 = p.node_ptr[gid], N = p.node_ptr[gid + 1] - a0;
+  const int r0 = p.cum[warp] - p.node_base;
+  const int st = p.stage[gid];
+  const int c_tail = p.lead, c_const = p.lead + p.tail, c_hot = c_const + p.nconst;
+  const int c_end = c_hot + (p.onehot ? 3 : 0);
+  const int total = N * p.ldx;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int i = idx / p.ldx, c = idx - i * p.ldx;
+    float v;
+    if (c < c_tail) v = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + c);
+    else if (c < c_const) v = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + (p.d_obs - p.tail) + (c - c_tail));
+    else if (c < c_hot) v = __ldg(p.consts + (c - c_const));
+    else if (c < c_end) v = (c - c_hot) == st ? 1.f : 0.f;
+    else v = 0.f;
+    p.x[(size_t)(r0 + i) * p.ldx + c] = v;
+  }
+  for (int i = lane; i < N; i += 32) {
+    p.nd_graph[r0 + i] = warp;
+    p.nd_arena[r0 + i] = a0 + i;
+    p.body[r0 + i] = p.body_ind[a0 + i];
+  }
+  if (lane == 0 && p.root_row) p.root_row[warp] = r0;
+}
+
+extern "C" int sard_gather_nodes(const SardArena* arena, const SardSel* sel, const SardGatherOut* out,
+                                 sard_stream_t stream) {
+  if (sel->B <= 0) return 0;
+  const int width = out->lead + out->tail + out->nconst + (out->onehot ? 3 : 0);
+  SARD_REQUIRE(width <= out->ldx, "gather: ldx too small");
+  SARD_REQUIRE(out->lead + out->tail <= arena->d_obs, "gather: column program exceeds d_obs");
+  GatherP p;
+  p.obs = arena->obs; p.d_obs = arena->d_obs; p.node_ptr = arena->node_ptr; p.stage = arena->stage;
+  p.body_ind = arena->body_ind; p.ids = sel->ids; p.cum = sel->cum; p.B = sel->B; p.node_base = sel->node_base;
+  p.lead = out->lead; p.tail = out->tail; p.nconst = out->nconst; p.onehot = out->onehot; p.consts = out->consts;
+  p.x = out->x; p.ldx = out->ldx; p.nd_graph = out->nd_graph; p.nd_arena = out->nd_arena; p.body = out->body;
+  p.root_row = out->root_row;
+  const int threads = 256;
+  gather_kernel<<<ceil_div((long long)sel->B * 32, threads), threads, 0, as_stream(stream)>>>(p);
+  SARD_LAUNCH_OK("gather_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable counting sort by body index (3 kernels) + tile / chunk tables.
+// ------------------------------------------------------------------------------------------
+#define SORT_BLOCK 256
+
+__global__ void sort_hist_kernel(const int* __restrict__ body, int n, int max_index, int* __restrict__ blockhist,
+                                 int* __restrict__ counts) {
+  extern __shared__ int hist[];
+  for (int u = threadIdx.x; u < max_index; u += blockDim.x) hist[u] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * SORT_BLOCK + threadIdx.x;
+  if (r < n) {
+    int u = body[r];
+    if (u < 0 || u >= max_index) { counts[2] = 1; u = min(max(u, 0), max_index - 1); }
+    atomicAdd(&hist[u], 1);
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < max_index; u += blockDim.x) blockhist[(size_t)blockIdx.x * max_index + u] = hist[u];
+}
+
+__global__ void sort_scan_kernel(int nb, int n, int max_index, int tile_rows, int chunk_rows,
+                                 int* __restrict__ blockhist, int* __restrict__ cnt, int* __restrict__ grp_ptr,
+                                 int4* __restrict__ tiles, int4* __restrict__ chunks, int* __restrict__ grp_chunk_ptr,
+                                 int* __restrict__ counts) {
+  for (int u = threadIdx.x; u < max_index; u += blockDim.x) {
+    int total = 0;
+    for (int b = 0; b < nb; ++b) {
+      int t = blockhist[(size_t)b * max_index + u];
+      blockhist[(size_t)b * max_index + u] = total;
+      total += t;
+    }
+    cnt[u] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0, nt = 0, nc = 0;
+    for (int u = 0; u < max_index; ++u) {
+      const int c = cnt[u];
+      grp_ptr[u] = run;
+      grp_chunk_ptr[u] = nc;
+      for (int s = 0; s < c; s += tile_rows) tiles[nt++] = make_int4(run + s, run + min(s + tile_rows, c), u, 0);
+      for (int s = 0; s < c; s += chunk_rows) chunks[nc++] = make_int4(run + s, run + min(s + chunk_rows, c), u, 0);
+      run += c;
+    }
+    grp_ptr[max_index] = run;
+    grp_chunk_ptr[max_index] = nc;
+    counts[0] = nt;
+    counts[1] = nc;
+  }
+}
+
+__global__ void sort_scatter_kernel(const int* __restrict__ body, int n, int max_index,
+                                    const int* __restrict__ blockhist, const int* __restrict__ grp_ptr,
+                                    int* __restrict__ srow, int* __restrict__ spos) {
+  extern __shared__ int warp_cnt[];   // [SORT_BLOCK/32][max_index]
+  const int nwarp = SORT_BLOCK / 32;
+  for (int i = threadIdx.x; i < nwarp * max_index; i += blockDim.x) warp_cnt[i] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * SORT_BLOCK + threadIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int u = -1;
+  if (r < n) u = min(max(body[r], 0), max_index - 1);
+  const unsigned peers = __match_any_sync(0xffffffffu, u);
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  if (u >= 0 && rank == 0) warp_cnt[w * max_index + u] = __popc(peers);
+  __syncthreads();
+  if (u >= 0) {
+    int off = 0;
+    for (int ww = 0; ww < w; ++ww) off += warp_cnt[ww * max_index + u];
+    const int pos = grp_ptr[u] + blockhist[(size_t)blockIdx.x * max_index + u] + off + rank;
+    srow[pos] = r;
+    spos[r] = pos;
+  }
+}
+
+extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int tile_rows, int chunk_rows,
+                                  int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
+                                  int* counts, int* scratch, sard_stream_t stream) {
+  SARD_REQUIRE(max_index > 0 && max_index <= 4096, "max_index");
+  SARD_REQUIRE(tile_rows > 0 && chunk_rows > 0, "tile/chunk rows");
+  cudaStream_t st = as_stream(stream);
+  SARD_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
+  const int nb = n > 0 ? ceil_div(n, SORT_BLOCK) : 0;
+  int* blockhist = scratch;
+  int* cnt = scratch + (size_t)nb * max_index;
+  if (nb > 0) {
+    sort_hist_kernel<<<nb, SORT_BLOCK, max_index * sizeof(int), st>>>(body, n, max_index, blockhist, counts);
+    SARD_LAUNCH_OK("sort_hist_kernel");
+  }
+  sort_scan_kernel<<<1, 256, 0, st>>>(nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
+                                      reinterpret_cast<int4*>(tiles), reinterpret_cast<int4*>(chunks),
+                                      grp_chunk_ptr, counts);
+  SARD_LAUNCH_OK("sort_scan_kernel");
+  if (nb > 0) {
+    sort_scatter_kernel<<<nb, SORT_BLOCK, (SORT_BLOCK / 32) * max_index * sizeof(int), st>>>(
+        body, n, max_index, blockhist, grp_ptr, srow, spos);
+    SARD_LAUNCH_OK("sort_scatter_kernel");
+  }
+  return 0;
+}

@@ -1,0 +1,345 @@
+"""Device-side state of the two nets: flat parameters, gradient buckets, workspaces, descriptors
+for the C++ schedules, and the per-minibatch step (forward, loss, backward, clip, Adam) that the
+agent drives.  One instance per net; everything here only enqueues work on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT, EXT_DIM, PHASE_ALL, PHASE_COMPUTE, PHASE_GATHER, POST_NONE, POST_SIN, SardIndexLinear,
+                   SardPolicyNet, SardValueNet, check, lib, ptr, stream)
+from .nets import (AdamState, FlatStore, STAGE_NAMES, _dense, _encoders, _params_of, _tower, dense_segments)
+from .packed import PackedRollout, Run
+
+N_STATS = 16
+
+
+class Comm:
+    """Collectives used by the data-parallel step (torch.distributed / NCCL); None = single GPU."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allgather(self, local: torch.Tensor, out: torch.Tensor):
+        self.dist.all_gather_into_tensor(out, local, group=self.group)
+
+    def allreduce(self, t: torch.Tensor):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class _EngineBase:
+    def __init__(self, module):
+        self.module = module
+        self.device = None
+        self.store: Optional[FlatStore] = None
+        self.opt: Optional[AdamState] = None
+        self.ws = {}
+        self.mom_local = {}
+        self.mom_all = {}
+
+    def _workspace(self, key, need: int) -> torch.Tensor:
+        w = self.ws.get(key)
+        if w is None or w.numel() < need:
+            w = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, device=self.device)
+            self.ws[key] = w
+        return w
+
+    def _moments(self, key, D: int, world: int):
+        rec = 1 + 2 * D
+        ml = self.mom_local.get(key)
+        if ml is None or ml.numel() != rec:
+            ml = torch.zeros(rec, dtype=torch.float64, device=self.device)
+            self.mom_local[key] = ml
+        ma = None
+        if world > 1:
+            ma = self.mom_all.get(key)
+            if ma is None or ma.numel() != rec * world:
+                ma = torch.zeros(rec * world, dtype=torch.float64, device=self.device)
+                self.mom_all[key] = ma
+        return ml, ma
+
+
+class ValueEngine(_EngineBase):
+    """Transform2ActValue on the device (transform2act_critic.py:13-108)."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        m = module
+        params = (_params_of(m.hfield_enc, 'hfield_enc.') + _params_of(m.obj_enc, 'obj_enc.') +
+                  _params_of(m.goal_enc, 'goal_enc.') + _params_of(m.gnn, 'gnn.') + _params_of(m.mlp, 'mlp.') +
+                  _params_of(m.value_head, 'value_head.'))
+        self.store = FlatStore([params])
+        self.net = None
+        self.GA = None
+        self.consts = None
+
+    def sync(self, opt: Optional[AdamState] = None):
+        dev = self.module.value_head.weight.device
+        if dev.type != 'cuda':
+            raise _lib.SardError('Transform2ActValue must be on a CUDA device: there is no CPU implementation')
+        rebuilt = False
+        if self.device != dev or not self.store.is_adopted():
+            self.device = dev
+            self.store.adopt(dev)
+            self.GA = torch.zeros(N_STATS + self.store.size, dtype=torch.float32, device=dev)
+            self.ws.clear(); self.mom_local.clear(); self.mom_all.clear()
+            rebuilt = True
+        m = self.module
+        if rebuilt or self.net is None:
+            net = SardValueNet()
+            net.tower = _tower(self.store, m.norm, m.gnn)
+            _encoders(self.store, (m.hfield_enc, m.obj_enc, m.goal_enc), net.enc)
+            net.n_mlp = len(m.mlp.affine_layers)
+            for j, lin in enumerate(m.mlp.affine_layers):
+                net.mlp[j] = _dense(self.store, lin, m.mlp.activation)
+            net.head = _dense(self.store, m.value_head)
+            self.consts = torch.zeros(max(m.sym_embed_dim, 1), dtype=torch.float32, device=dev)
+            net.nconst = m.sym_embed_dim if m.enable_infer else 0
+            net.consts = ptr(self.consts)
+            net.onehot = 1
+            net.P, net.G = ptr(self.store.flat), self.GA.data_ptr() + 4 * N_STATS
+            self.net = net
+        if opt is not None and (rebuilt or opt is not self.opt or opt.segs is None):
+            self.opt = opt
+            opt.ensure(self.store.flat)
+            opt.set_segments(dense_segments(self.store.flat, opt.m, opt.v, self.GA.data_ptr() + 4 * N_STATS,
+                                            self.store.group_range), dev)
+
+    def set_embeds(self, embeds: Optional[torch.Tensor]):
+        if embeds is not None and self.net.nconst > 0:
+            self.consts.copy_(embeds.to(device=self.device, dtype=torch.float32))
+
+    def run(self, arena: PackedRollout, run: Run, train, inv_B: float = 0.0, comm: Optional[Comm] = None):
+        """train: 0/False eval, 1/True update norm + loss + backward, 2 update norm + forward only."""
+        mode = int(train)
+        net = self.net
+        need = lib.sard_value_workspace(C.byref(net), run.n, run.B)
+        ws = self._workspace('v', need)
+        world = comm.world if comm is not None else 1
+        ml, ma = self._moments('v', net.tower.D, world)
+        st = stream()
+        sq = self.GA.data_ptr() + 4 * 5
+        if train and world > 1:
+            check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), mode, PHASE_GATHER, inv_B, ptr(ml),
+                                     None, 1, sq, ptr(ws), ws.numel(), st))
+            comm.allgather(ml, ma)
+            check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), mode, PHASE_COMPUTE, inv_B, ptr(ml),
+                                     ptr(ma), world, sq, ptr(ws), ws.numel(), st))
+        else:
+            check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), mode, PHASE_ALL,
+                                     inv_B, ptr(ml), None, 1, sq, ptr(ws), ws.numel(), st))
+
+    def train_step(self, arena: PackedRollout, run: Run, B_global: int, log_row: Optional[torch.Tensor] = None,
+                   comm: Optional[Comm] = None):
+        """AgentPG.update_value (agent_pg.py:18-25): forward, MSE, backward, Adam."""
+        opt = self.opt
+        self.GA.zero_()
+        self.run(arena, run, True, 1.0 / B_global, comm)
+        if comm is not None and comm.world > 1:
+            comm.allreduce(self.GA)
+        st = stream()
+        check(lib.sard_adam_prepare(ptr(self.GA), 1.0 / B_global, 1.0, 0.0, None, -1.0, 0, 0, 1, opt.betas[0], opt.betas[1],
+                                    ptr(opt.ctl_f), ptr(opt.ctl_i), ptr(log_row), st))
+        check(lib.sard_adam_apply(ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.betas[0], opt.betas[1], opt.eps, 1,
+                                  ptr(opt.ctl_f), ptr(opt.ctl_i), st))
+
+
+class PolicyEngine(_EngineBase):
+    """Transform2ActPolicy on the device (transform2act_policy.py:43-419)."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        m = module
+        shared = (_params_of(m.hfield_enc, 'hfield_enc.') + _params_of(m.obj_enc, 'obj_enc.') +
+                  _params_of(m.goal_enc, 'goal_enc.'))
+        groups = [shared]
+        for s, name in enumerate(STAGE_NAMES):
+            plist = _params_of(getattr(m, f'{name}_gnn'), f'{name}_gnn.')
+            if name == 'attr':
+                plist.append(('attr_action_log_std', m.attr_action_log_std))
+            if name == 'control':
+                plist.append(('control_action_log_std', m.control_action_log_std))
+            groups.append(plist)
+        self.store = FlatStore(groups)
+        self.max_index = m.max_index
+        self.ever_live = [np.zeros(self.max_index, dtype=bool) for _ in range(3)]
+        self.slot_of_index = None
+        self.net = None
+        self.GA = None
+        self.gt_off = [0, 0, 0]
+        self.consts = None
+        self.sq_scratch = None
+        self.sq_out = None
+        self._table_ptrs = None
+
+    # -- layout ---------------------------------------------------------------------------
+    def _tables(self, s):
+        return getattr(self.module, f'{STAGE_NAMES[s]}_ind_mlp').layers()
+
+    def sync(self, opt: Optional[AdamState] = None, new_live: Optional[Sequence[np.ndarray]] = None):
+        m = self.module
+        dev = m.control_action_log_std.device
+        if dev.type != 'cuda':
+            raise _lib.SardError('Transform2ActPolicy must be on a CUDA device: there is no CPU implementation')
+        rebuilt = False
+        if self.device != dev or not self.store.is_adopted():
+            self.device = dev
+            self.store.adopt(dev)
+            self.ws.clear(); self.mom_local.clear(); self.mom_all.clear()
+            self.consts = torch.zeros(max(m.sym_embed_dim, 1), dtype=torch.float32, device=dev)
+            self.sq_scratch = torch.zeros(1024, dtype=torch.float32, device=dev)
+            self.sq_out = torch.zeros(1, dtype=torch.float32, device=dev)
+            rebuilt = True
+        grew = False
+        if new_live is not None:
+            for s in range(3):
+                idx = np.asarray(new_live[s], dtype=np.int64)
+                if len(idx) and (idx.max() >= self.max_index or idx.min() < 0):
+                    raise _lib.SardError(f'body index out of range [0,{self.max_index})')
+                if len(idx) and not self.ever_live[s][idx].all():
+                    self.ever_live[s][idx] = True
+                    grew = True
+        tp = tuple(t.W.data_ptr() for s in range(3) for t in self._tables(s))
+        if tp != self._table_ptrs:
+            self._table_ptrs = tp
+            rebuilt = True
+        if rebuilt or grew or self.net is None:
+            self._build(dev)
+            rebuilt = True
+        if opt is not None and (rebuilt or opt is not self.opt or opt.segs is None):
+            self.opt = opt
+            opt.ensure(self.store.flat)
+            self._build_segments(opt)
+
+    def _build(self, dev):
+        m = self.module
+        slot = np.full((3, self.max_index), -1, dtype=np.int32)
+        sizes = []
+        for s in range(3):
+            live = np.flatnonzero(self.ever_live[s])
+            slot[s, live] = np.arange(len(live), dtype=np.int32)
+            S = len(live)
+            sizes.append(sum(S * (t.out_dim * t.input_dim + t.out_dim) + 8 for t in self._tables(s)))
+        self.slot_of_index = torch.from_numpy(slot).to(dev)
+        total = N_STATS + self.store.size
+        for s in range(3):
+            self.gt_off[s] = total
+            total += (sizes[s] + 3) // 4 * 4
+        self.GA = torch.zeros(total, dtype=torch.float32, device=dev)
+        net = SardPolicyNet()
+        _encoders(self.store, (m.hfield_enc, m.obj_enc, m.goal_enc), net.enc)
+        net.nconst = m.sym_embed_dim if m.enable_infer else 0
+        net.consts = ptr(self.consts)
+        net.P, net.G = ptr(self.store.flat), self.GA.data_ptr() + 4 * N_STATS
+        for s, name in enumerate(STAGE_NAMES):
+            st = net.stage[s]
+            st.stage = s
+            st.tower = _tower(self.store, getattr(m, f'{name}_norm'), getattr(m, f'{name}_gnn'))
+            if s == 2:
+                st.lead, st.tail = m.control_state_dim, 0
+            else:
+                st.lead, st.tail = m.attr_fixed_dim, m.attr_design_dim
+            tabs = self._tables(s)
+            st.n_il = len(tabs)
+            S = int(self.ever_live[s].sum())
+            off = 0
+            for j, t in enumerate(tabs):
+                il = SardIndexLinear()
+                il.out, il.in_ = t.out_dim, t.input_dim
+                il.W, il.b = ptr(t.W.data), ptr(t.b.data)
+                il.gW = off; off += S * t.out_dim * t.input_dim
+                il.gb = off; off += (S * t.out_dim + 3) // 4 * 4
+                st.il[j] = il
+            st.il_act = ACT[getattr(m, f'{name}_ind_mlp').activation]
+            st.out_dim = tabs[-1].out_dim
+            st.post = POST_SIN if s == 1 else POST_NONE
+            st.log_std = -1 if s == 0 else self.store.off(m.attr_action_log_std if s == 1 else m.control_action_log_std)
+            st.tie_c0, st.tie_c1 = m.tie_columns(s)
+            st.max_index = self.max_index
+            st.slot_of_index = self.slot_of_index.data_ptr() + 4 * self.max_index * s
+            st.GT = self.GA.data_ptr() + 4 * self.gt_off[s]
+        self.net = net
+
+    def _build_segments(self, opt: AdamState):
+        segs = dense_segments(self.store.flat, opt.m, opt.v, self.GA.data_ptr() + 4 * N_STATS, self.store.group_range)
+        for s in range(3):
+            live = np.flatnonzero(self.ever_live[s])
+            st = self.net.stage[s]
+            for j, t in enumerate(self._tables(s)):
+                mW, vW = opt.table_state(t.W)
+                mb, vb = opt.table_state(t.b)
+                rw, rb = t.out_dim * t.input_dim, t.out_dim
+                for k, u in enumerate(live):
+                    u = int(u)
+                    segs.append((t.W.data.data_ptr() + 4 * u * rw, mW.data_ptr() + 4 * u * rw, vW.data_ptr() + 4 * u * rw,
+                                 st.GT + 4 * (st.il[j].gW + k * rw), rw, 1 + s))
+                    segs.append((t.b.data.data_ptr() + 4 * u * rb, mb.data_ptr() + 4 * u * rb, vb.data_ptr() + 4 * u * rb,
+                                 st.GT + 4 * (st.il[j].gb + k * rb), rb, 1 + s))
+        opt.set_segments(segs, self.device)
+
+    def set_embeds(self, embeds: Optional[torch.Tensor]):
+        if embeds is not None and self.net.nconst > 0:
+            self.consts.copy_(embeds.to(device=self.device, dtype=torch.float32))
+
+    # -- runs -----------------------------------------------------------------------------
+    def run_stage(self, s: int, arena: PackedRollout, run: Run, train: bool, clip_eps: float = 0.2, inv_B: float = 0.0,
+                  outputs: Optional[torch.Tensor] = None, log_prob_run: Optional[torch.Tensor] = None,
+                  comm: Optional[Comm] = None, phase: int = PHASE_ALL):
+        net = self.net
+        if net.stage[s].tie_c1 > net.stage[s].tie_c0 and not arena.has_orbits:
+            raise _lib.SardError('orbit representatives missing: call PackedRollout.set_orbits first')
+        need = lib.sard_policy_workspace(C.byref(net), s, run.n, run.B)
+        ws = self._workspace(s, need)
+        world = comm.world if comm is not None else 1
+        ml, ma = self._moments(s, net.stage[s].tower.D, world)
+        args = (C.byref(net), s, C.byref(arena.c), C.byref(run.sel), int(train))
+        tail = (ptr(self.GA), ptr(outputs), ptr(log_prob_run), ptr(ws), ws.numel(), stream())
+        if train and world > 1:
+            check(lib.sard_policy_run(*args, PHASE_GATHER, clip_eps, inv_B, ptr(ml), None, 1, *tail))
+            comm.allgather(ml, ma)
+            check(lib.sard_policy_run(*args, PHASE_COMPUTE, clip_eps, inv_B, ptr(ml), ptr(ma), world, *tail))
+        else:
+            check(lib.sard_policy_run(*args, phase, clip_eps, inv_B, ptr(ml), None, 1, *tail))
+
+    def train_step(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
+                   active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
+                   log_row: Optional[torch.Tensor] = None, comm: Optional[Comm] = None):
+        """ppo_loss + backward + clip + Adam (transform2act_agent.py:351-358), gated on device (:404-407)."""
+        opt = self.opt
+        self.GA.zero_()
+        for s in (2, 1, 0):                       # the reference evaluates execution, attribute, skeleton
+            if runs[s] is not None:
+                self.run_stage(s, arena, runs[s], True, clip_eps, 1.0 / B_global, comm=comm)
+            elif comm is not None and comm.world > 1 and active_global[s]:
+                # another rank has graphs of this stage: contribute an empty moments record
+                ml, ma = self._moments(s, self.net.stage[s].tower.D, comm.world)
+                ml.zero_()
+                comm.allgather(ml, ma)
+                self._empty_norm_update(s, ma, comm.world)
+        world = 1
+        if comm is not None and comm.world > 1:
+            comm.allreduce(self.GA)
+            world = comm.world
+        mask = (1 if any(active_global) else 0) | sum((1 << (1 + s)) for s in range(3) if active_global[s])
+        st = stream()
+        check(lib.sard_sqnorm(self.GA.data_ptr() + 4 * N_STATS, self.GA.numel() - N_STATS, ptr(self.sq_scratch),
+                              ptr(self.sq_out), st))
+        inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0
+        check(lib.sard_adam_prepare(ptr(self.GA), 1.0 / B_global, 1.0 / world, inv_cat, ptr(self.sq_out), float(max_norm),
+                                    1 if clip_first_only else 0, 1, mask, opt.betas[0], opt.betas[1], ptr(opt.ctl_f),
+                                    ptr(opt.ctl_i), ptr(log_row), st))
+        check(lib.sard_adam_apply(ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.betas[0], opt.betas[1], opt.eps, mask,
+                                  ptr(opt.ctl_f), ptr(opt.ctl_i), st))
+
+    def _empty_norm_update(self, s, ma, world):
+        tw = self.net.stage[s].tower
+        check(lib.sard_norm_update(ptr(ma), world, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, stream()))

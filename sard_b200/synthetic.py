@@ -281,3 +281,22 @@ def generate_rollout(shape: EnvShape, num_transitions: int, seed: int = 1234, *,
         goal=np.concatenate(go_l)[:T].astype(dtype), actions=actions,
         rewards=np.concatenate(rew_l)[:T].astype(dtype), masks=np.concatenate(mask_l)[:T].astype(dtype),
         exps=np.ones(T, dtype=dtype))
+
+
+class SyntheticEnv:
+    """The attributes ``Transform2ActAgent.setup_env`` reads from a DERL env (agent :111-124), for a shape."""
+
+    def __init__(self, shape: EnvShape):
+        self.shape = shape
+        self.index_base = shape.index_base
+        self.attr_fixed_dim = shape.attr_fixed_dim
+        self.attr_design_dim = ATTR_DESIGN_DIM
+        self.sim_obs_dim = shape.sim_obs_dim
+        self.control_action_dim = 1
+        self.skel_num_action = 3
+        self.sim_obs_hfield_dim = shape.hfield_dim
+        self.sim_obs_obj_dim = shape.obj_dim
+        self.sim_obs_goal_dim = shape.goal_dim
+
+    def seed(self, seed):
+        pass

@@ -1,0 +1,344 @@
+"""Drop-in ``Transform2ActAgent`` PPO driver (reference: design_opt/agents/transform2act_agent.py
+on top of khrylib/rl/agents/{agent,agent_pg,agent_ppo}.py).
+
+The learning half (``update_params`` -> value pre-pass -> GAE -> ``update_policy`` with its
+minibatch loop of ``update_value`` + ``ppo_loss`` + clip + Adam) runs on the device through
+:mod:`sard_b200.engine`; rollouts (``sample``), logging and checkpoint I/O are host code with the
+reference's behaviour.  The KL/loss gate is evaluated on the device, so the minibatch loop has no
+host synchronisation; the per-step logs are read back once at the end.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+import time
+from collections import Counter
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Comm
+from .nets import AdamState
+from .packed import EpochPlan, Ordering, PackedRollout, host_rollout_from_lists, stage_partition
+from .rl_core import estimate_advantages
+from .synthetic import HostRollout
+from .transform2act_critic import Transform2ActValue
+from .transform2act_policy import Transform2ActPolicy
+
+EVAL_CHUNK = 16384   # graphs per eval-mode launch (the reference uses 10000; results do not depend on it)
+
+
+def tensorfy(np_list, device=torch.device('cpu')):
+    """Reference helper kept for API compatibility (agent :20-24)."""
+    if isinstance(np_list[0], list):
+        return [[torch.tensor(x).to(device) if i in {0, 1, 5, 6, 7} else x for i, x in enumerate(y)] for y in np_list]
+    return [torch.tensor(y).to(device) for y in np_list]
+
+
+class Transform2ActAgent:
+    """``Transform2ActAgent(cfg, dtype, device, seed, num_threads, training=True, checkpoint=0)``.
+
+    ``env`` may be passed explicitly (any object with the attributes read in ``setup_env``); when
+    omitted the reference's ``design_opt.envs.env_dict`` is looked up, which needs the reference's
+    MuJoCo stack on the host.
+    """
+
+    def __init__(self, cfg, dtype, device, seed, num_threads, training=True, checkpoint=0, env=None, comm=None):
+        self.cfg = cfg
+        self.training = training
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.loss_iter = 0
+        self.comm: Optional[Comm] = comm
+        self.setup_env(env)
+        self.seed(seed)
+        self.setup_logger()
+        self.setup_policy()
+        self.setup_value()
+        self.setup_optimizer()
+        self.scheduled_params = {}
+        self.gamma, self.tau, self.clip_epsilon = cfg.gamma, cfg.tau, cfg.clip_epsilon
+        self.opt_num_epochs = cfg.num_optim_epoch
+        self.mini_batch_size = cfg.mini_batch_size
+        self.use_mini_batch = cfg.mini_batch_size < cfg.min_batch_size
+        self.policy_grad_clip = [(self.policy_net.parameters(), 40)]
+        # The reference's clip list holds a generator: only its first use clips (agent_ppo.py:53-56).
+        self.clip_first_step_only = True
+        self.value_opt_niter = 1
+        self.num_threads = num_threads
+        self.noise_rate = 1.0
+        self.running_state = None
+        self.custom_reward = None
+        self.end_reward = False
+        self.sample_modules = [self.policy_net]
+        self.update_modules = [self.policy_net, self.value_net]
+        self.enable_infer = cfg.enable_infer
+        self.total_time_steps = 0
+        self.last_update_stats = {}
+        if checkpoint != 0:
+            self.load_checkpoint(checkpoint)
+
+    # ---- setup ------------------------------------------------------------------------------
+    def setup_env(self, env=None):
+        if env is None:
+            try:
+                from design_opt.envs import env_dict          # the reference's MuJoCo envs, if installed
+            except Exception as e:                             # noqa: BLE001
+                raise RuntimeError('no env given and design_opt.envs is not importable; rollouts stay on the '
+                                   "reference's host stack (see INTEGRATION.md)") from e
+            env = env_dict[self.cfg.env_name](self.cfg, self)
+        self.env = env
+        self.attr_fixed_dim = env.attr_fixed_dim
+        self.attr_design_dim = env.attr_design_dim
+        self.sim_obs_dim = env.sim_obs_dim
+        self.state_dim = self.attr_fixed_dim + self.sim_obs_dim + self.attr_design_dim
+        self.control_action_dim = env.control_action_dim
+        self.skel_num_action = env.skel_num_action
+        self.action_dim = self.control_action_dim + self.attr_design_dim
+        self.sim_obs_hfield_dim = env.sim_obs_hfield_dim
+        self.sim_obs_obj_dim = env.sim_obs_obj_dim
+        self.sim_obs_goal_dim = env.sim_obs_goal_dim
+
+    def seed(self, seed):
+        if hasattr(self.env, 'seed'):
+            self.env.seed(seed)
+
+    def setup_logger(self):
+        self.tb_logger = None
+        self.logger = None
+        self.best_rewards = -1000.0
+        self.save_best_flag = False
+
+    def setup_policy(self):
+        self.policy_net = Transform2ActPolicy(self.cfg.policy_specs, self)
+        self.policy_net.to(self.device)
+
+    def setup_value(self):
+        self.value_net = Transform2ActValue(self.cfg.value_specs, self)
+        self.value_net.to(self.device)
+
+    def setup_optimizer(self):
+        cfg = self.cfg
+        if cfg.policy_optimizer != 'Adam' or cfg.value_optimizer != 'Adam':
+            raise NotImplementedError('only Adam is on the CUDA path (design_opt/cfg/derl.yml)')
+        if cfg.policy_weightdecay != 0.0 or cfg.value_weightdecay != 0.0:
+            raise NotImplementedError('weight decay would touch never-seen IndexLinear rows; not on the CUDA path')
+        self.optimizer_policy = AdamState(cfg.policy_lr)
+        self.optimizer_value = AdamState(cfg.value_lr)
+
+    # ---- checkpoint I/O (agent :167-210) ---------------------------------------------------------
+    def save_checkpoint_to(self, cp_path, epoch=0):
+        cp = {'policy_dict': {k: v.detach().cpu() for k, v in self.policy_net.state_dict().items()},
+              'value_dict': {k: v.detach().cpu() for k, v in self.value_net.state_dict().items()},
+              'running_state': self.running_state, 'loss_iter': self.loss_iter, 'best_rewards': self.best_rewards,
+              'epoch': epoch, 'symmetry': self.policy_net.group.cur_subgroup_name if self.enable_infer else None}
+        with open(cp_path, 'wb') as f:
+            pickle.dump(cp, f)
+
+    def save_checkpoint(self, epoch):
+        cfg = self.cfg
+        extra = cfg.agent_specs.get('additional_saves', None)
+        if (cfg.save_model_interval > 0 and (epoch + 1) % cfg.save_model_interval == 0) or \
+           (extra is not None and (epoch + 1) % extra[0] == 0 and epoch + 1 <= extra[1]):
+            self.save_checkpoint_to('%s/epoch_%04d.p' % (cfg.model_dir, epoch + 1), epoch)
+        if self.save_best_flag:
+            self.save_checkpoint_to('%s/best.p' % cfg.model_dir, epoch)
+
+    def load_checkpoint(self, checkpoint):
+        cfg = self.cfg
+        if isinstance(checkpoint, int):
+            cp_path = '%s/epoch_%04d.p' % (cfg.model_dir, checkpoint)
+        elif os.path.exists(str(checkpoint)):
+            cp_path = str(checkpoint)
+        else:
+            cp_path = '%s/%s.p' % (cfg.model_dir, checkpoint)
+        with open(cp_path, 'rb') as f:
+            cp = pickle.load(f)
+        self.policy_net.load_state_dict(cp['policy_dict'])
+        self.value_net.load_state_dict(cp['value_dict'])
+        self.running_state = cp['running_state']
+        self.loss_iter = cp['loss_iter']
+        self.best_rewards = cp.get('best_rewards', self.best_rewards)
+        if self.enable_infer and cp.get('symmetry') is not None:
+            self.policy_net.group.cur_subgroup_name = cp['symmetry']
+
+    def pre_epoch_update(self, epoch):
+        for p in self.scheduled_params.values():
+            p.set_epoch(epoch)
+
+    # ---- rollouts: host side, outside the scope of the CUDA path ---------------------------------
+    def sample(self, min_batch_size, mean_action=False, render=False, nthreads=None):
+        raise NotImplementedError('MuJoCo rollouts stay on the reference host stack; feed update_params() a '
+                                  'TrajBatchDisc-like batch (see INTEGRATION.md)')
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def pack(self, batch) -> PackedRollout:
+        """``TrajBatchDisc`` (or a ``HostRollout``) -> device arena: one packed upload instead of tensorfy."""
+        host = batch if isinstance(batch, HostRollout) else host_rollout_from_lists(
+            batch.states, batch.actions, batch.rewards, batch.masks, getattr(batch, 'exps', None))
+        return PackedRollout(host, self.device, pin=True)
+
+    def _prepare(self, arena: PackedRollout):
+        self.policy_net.prepare(arena, self.optimizer_policy)
+        self.value_net.prepare(self.optimizer_value)
+
+    def _eval_values(self, arena: PackedRollout):
+        order = Ordering(arena, np.arange(arena.T))
+        eng = self.value_net.engine
+        for lo in range(0, arena.T, EVAL_CHUNK):
+            eng.run(arena, order.run(lo, min(arena.T, lo + EVAL_CHUNK)), 0)
+        return order
+
+    def _eval_log_probs(self, arena: PackedRollout):
+        order = Ordering(arena, stage_partition(arena.stage_np))
+        eng = self.policy_net.engine
+        bounds = np.searchsorted(order.stage_np, [0, 1, 2, 3])
+        for s in (2, 1, 0):
+            for lo in range(int(bounds[s]), int(bounds[s + 1]), EVAL_CHUNK):
+                eng.run_stage(s, arena, order.run(lo, min(int(bounds[s + 1]), lo + EVAL_CHUNK)), 0)
+        return order
+
+    def update_params(self, batch):
+        """agent :274-303.  Returns ``(seconds, log)`` like the reference."""
+        t0 = time.time()
+        for m in self.update_modules:
+            m.train(True)
+        with torch.cuda.device(self.device):
+            arena = self.pack(batch)
+            self._prepare(arena)
+            for m in self.update_modules:
+                m.train(False)
+            self._eval_values(arena)
+            for m in self.update_modules:
+                m.train(True)
+            adv, ret = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), self.gamma, self.tau)
+            arena.advantages.copy_(adv.reshape(-1))
+            arena.returns.copy_(ret.reshape(-1))
+            if self.cfg.agent_specs.get('reinforce', False):
+                arena.advantages.copy_(arena.returns)
+            log = self.update_policy_packed(arena)
+        return time.time() - t0, log
+
+    def update_policy(self, states, actions, returns, advantages, exps):
+        """Reference signature (agent :313): lists of states/actions plus ``[T,1]`` tensors."""
+        with torch.cuda.device(self.device):
+            arena = PackedRollout.from_lists(states, actions, device=self.device)
+            self._prepare(arena)
+            arena.returns.copy_(returns.reshape(-1).to(self.device, torch.float32))
+            arena.advantages.copy_(advantages.reshape(-1).to(self.device, torch.float32))
+            return self.update_policy_packed(arena)
+
+    def draw_perm(self, T: int) -> np.ndarray:
+        perm = np.arange(T)
+        np.random.shuffle(perm)          # same RNG call as the reference (agent :333)
+        return perm
+
+    def update_policy_packed(self, arena: PackedRollout, perms: Optional[List[np.ndarray]] = None):
+        comm = self.comm
+        world = comm.world if comm is not None else 1
+        peng, veng = self.policy_net.engine, self.value_net.engine
+        for m in self.update_modules:
+            m.train(False)
+        self._eval_log_probs(arena)
+        for m in self.update_modules:
+            m.train(True)
+        T = arena.T
+        M = self.mini_batch_size if self.use_mini_batch else T
+        batch_design = bool(self.cfg.agent_specs.get('batch_design', False))
+        n_mb = T // M
+        n_steps = self.opt_num_epochs * n_mb
+        plog = torch.zeros(max(n_steps, 1), 8, dtype=torch.float32, device=self.device)
+        vlog = torch.zeros(max(n_steps, 1), 8, dtype=torch.float32, device=self.device)
+        step = 0
+        h2d = 0
+        cur_perm = np.arange(T)
+        for ep in range(self.opt_num_epochs):
+            # like the reference, each epoch permutes the already permuted lists (agent :331-342)
+            p = perms[ep] if perms is not None else self.draw_perm(T)
+            cur_perm = cur_perm[p]
+            plan = EpochPlan(arena, cur_perm, M, batch_design)
+            cur_perm = plan.perm
+            h2d += plan.h2d_bytes
+            counts = np.concatenate([plan.stage_graphs, plan.stage_nodes], axis=1)      # [n_mb, 6]
+            if world > 1:
+                ct = torch.from_numpy(counts).to(self.device)
+                comm.allreduce(ct)
+                counts = ct.cpu().numpy()
+            for k in range(plan.n_mb):
+                B_glob = int(counts[k, :3].sum())
+                active = [bool(counts[k, s] > 0) for s in range(3)]
+                veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
+                peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
+                                40.0, self.clip_first_step_only, plog[step], comm)
+                step += 1
+        logs = plog[:step].cpu().numpy()
+        vlogs = vlog[:step].cpu().numpy()
+        self.last_update_stats = {'h2d_bytes': arena.h2d_bytes + h2d, 'd2h_bytes': int(logs.nbytes + vlogs.nbytes),
+                                  'steps': step, 'valid_steps': int(logs[:, 3].sum()) if step else 0,
+                                  'value_loss': vlogs[:, 5].copy(), 'policy_log': logs}
+        return self._summarise(arena, logs, cur_perm)
+
+    def _summarise(self, arena: PackedRollout, logs: np.ndarray, last_perm: np.ndarray) -> dict:
+        """Epoch log with the reference's keys (agent :371-387)."""
+        log2 = dict()
+        attr_ids = np.flatnonzero(arena.stage_np == 1)
+        if len(attr_ids):
+            num_agents = arena.num_nodes_np[attr_ids]
+            log2['num_agent_mean'] = float(np.mean(num_agents))
+            log2['num_agent_std'] = float(np.std(num_agents))
+            edst = arena.edst.cpu().numpy()
+            eptr = arena.edge_ptr.cpu().numpy()
+            designs = Counter(tuple(edst[eptr[i]:eptr[i + 1]].tolist()) for i in attr_ids)
+            log2['num_designs'] = len(designs)
+            log2['num_designs_std'] = float(np.std(list(designs.values())))
+            acts = arena.actions.cpu().numpy()
+            a = [np.abs(acts[arena.node_ptr_np[i]:arena.node_ptr_np[i + 1], 1:3]).mean() for i in attr_ids]
+            log2['attr_mean'] = float(np.mean(a))
+            log2['attr_std'] = float(np.std(a))
+        valid = logs[:, 3] > 0.5 if len(logs) else np.zeros(0, bool)
+        for j, k in enumerate(('surr_loss', 'entropy', 'approx_kl')):
+            v = logs[valid, j] if len(logs) else np.zeros(0)
+            log2[k] = float(np.sum(v) / (np.count_nonzero(v) + 1e-6))
+        return log2
+
+    # ---- single-step API of the reference ------------------------------------------------------------------
+    def update_value(self, states, returns):
+        """agent_pg.py:18-25 for one list of states (one optimiser step)."""
+        with torch.cuda.device(self.device):
+            arena = PackedRollout.from_lists(states, device=self.device)
+            self._prepare(arena)
+            arena.returns.copy_(returns.reshape(-1).to(self.device, torch.float32))
+            order = Ordering(arena, np.arange(arena.T))
+            self.value_net.engine.train_step(arena, order.run(0, arena.T), arena.T, None, self.comm)
+
+    def ppo_loss(self, states, actions, advantages, fixed_log_probs):
+        """agent :390-409.  Forward + loss (+ backward into the engine's gradient bucket); returns
+        ``(surr_loss tensor, log dict, valid_loss)``.  ``policy_step_from_loss()`` applies clip + Adam."""
+        with torch.cuda.device(self.device):
+            arena = PackedRollout.from_lists(states, actions, device=self.device)
+            self._prepare(arena)
+            arena.advantages.copy_(advantages.reshape(-1).to(self.device, torch.float32))
+            arena.fixed_log_probs.copy_(fixed_log_probs.reshape(-1).to(self.device, torch.float32))
+            order = Ordering(arena, stage_partition(arena.stage_np))
+            runs = order.stage_runs(0, arena.T)
+            peng = self.policy_net.engine
+            peng.GA.zero_()
+            for s in (2, 1, 0):
+                if runs[s] is not None:
+                    peng.run_stage(s, arena, runs[s], 1, self.clip_epsilon, 1.0 / arena.T)
+            stats = peng.GA[:8].cpu().numpy()
+            n_skel = int(arena.num_nodes_np[arena.stage_np == 0].sum())
+            surr = -float(stats[0]) / arena.T
+            kl = float(stats[1]) / arena.T
+            ent = float(stats[4]) + (float(stats[2]) / n_skel if n_skel else 0.0)
+            log = {'surr_loss': surr, 'entropy': ent, 'approx_kl': kl}
+            valid = not (kl > 0.1 or surr > 10)
+            self._pending = (arena, runs)
+            return torch.tensor(surr, device=self.device), log, valid
+
+    def clip_policy_grad(self):
+        """Clipping is fused into the optimiser step (``sard_adam_prepare``); kept for API compatibility."""
+        return None

@@ -85,3 +85,58 @@ def assert_close(a, b, rtol, atol, what=''):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError(f'{what}: max violation at {i}: got {a[i]!r} want {b[i]!r} '
                              f'(|err|={err[i]:.3e}, tol={tol[i]:.3e}); max|err|={err.max():.3e}')
+
+
+# ---------------------------------------------------------------------------------------------
+# product-side helpers (GPU tests)
+# ---------------------------------------------------------------------------------------------
+def small_config(subgroup, mini_batch=32, n_epochs=2, T=96, max_index=40):
+    """The configuration make_golden.py used (small_cfg there), as a sard_b200 Config."""
+    from sard_b200.config import Config
+    gnn = {'layer_type': 'graph_conv', 'hdims': [16, 16, 16], 'aggr': 'add', 'bias': True}
+    imlp = {'hdims': [16, 16], 'rescale_linear': True, 'max_index': max_index}
+    d = {
+        'agent_specs': {'batch_design': True}, 'gamma': 0.995, 'tau': 0.95,
+        'policy_specs': {'htype': 'tanh', 'skel_gnn_specs': gnn, 'skel_index_mlp': imlp, 'control_gnn_specs': gnn,
+                         'control_index_mlp': imlp, 'attr_gnn_specs': gnn, 'attr_index_mlp': imlp,
+                         'control_log_std': 0, 'attr_log_std': -2.3, 'fix_control_std': False, 'fix_attr_std': False},
+        'value_specs': {'htype': 'tanh', 'design_flag_in_state': True, 'onehot_design_flag': True, 'mlp': [32, 16],
+                        'gnn_specs': gnn},
+        'policy_lr': 5e-5, 'value_lr': 3e-4, 'clip_epsilon': 0.2, 'min_batch_size': T, 'mini_batch_size': mini_batch,
+        'num_optim_epoch': n_epochs, 'robot': {'joint_params': {}}, 'init_subgroup_name': subgroup,
+    }
+    return Config(d)
+
+
+def build_agent(case, device, prefix='init'):
+    """sard_b200 agent with the golden case's weights loaded."""
+    import torch
+    from sard_b200 import synthetic
+    from sard_b200.transform2act_agent import Transform2ActAgent
+    cfg = small_config(case.meta['subgroup'], case.meta['mini_batch'], case.meta['n_epochs'], case.meta['T'])
+    ag = Transform2ActAgent(cfg, torch.float32, device, 0, 1, env=synthetic.SyntheticEnv(case.shape))
+    load_sd(ag.policy_net, case.sd(prefix + '.policy.', torch.float32, requires_grad=False))
+    load_sd(ag.value_net, case.sd(prefix + '.value.', torch.float32, requires_grad=False))
+    return ag
+
+
+def load_sd(module, sd):
+    own = module.state_dict()
+    missing = [k for k in own if k not in sd]
+    extra = [k for k in sd if k not in own]
+    assert not missing and not extra, (missing, extra)
+    module.load_state_dict(sd)
+
+
+def assert_mostly_close(a, b, rtol, atol, frac=0.999, hard_atol=None, what=''):
+    """Like assert_close for at least ``frac`` of the elements; every element within ``hard_atol``.
+
+    Used for weights after Adam steps: an element whose gradient is at fp32 noise level can move by
+    +-lr in either direction at the first step, which is inherent to Adam, not to the kernel."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1); b = np.asarray(b, dtype=np.float64).reshape(-1)
+    assert a.shape == b.shape, f'{what}: shape'
+    err = np.abs(a - b)
+    ok = err <= atol + rtol * np.abs(b)
+    assert ok.mean() >= frac, f'{what}: only {ok.mean():.5f} of elements within tolerance (max err {err.max():.3e})'
+    if hard_atol is not None:
+        assert err.max() <= hard_atol, f'{what}: max err {err.max():.3e} > {hard_atol:.3e}'
