@@ -40,6 +40,21 @@ const char* sard_last_error_string(void);
 /* sizeof() of the 13 ABI structs in declaration order, for binding self-checks (host memory, no GPU). */
 int sard_struct_sizes(int* out, int capacity);
 
+/* Kernels launched by the library since load (monotonic; host counter). */
+long long sard_launch_count(void);
+
+/* Per-call-site kernel timing for the roofline numbers (CUDA events on the launching stream).
+ * Sites label the GEMM / aggregate launches of the network schedules: site = 3*kind + pass with
+ * kind in {0 in_fc, 1 graphconv, 2 index-linear, 3 obs-encoder, 4 critic mlp, 5 value head, 6 csr aggregate}
+ * and pass in {0 forward, 1 backward-data / adjoint, 2 backward-weight}.
+ * sard_prof_enable(mask, capacity): time launches whose site bit is set in mask (0 disables), keeping
+ * at most `capacity` event pairs.  sard_prof_collect synchronises the recorded events and returns,
+ * per site, {launches, total ms, algorithmic flops, algorithmic bytes} in rows[site*4 .. site*4+3]
+ * (host doubles, n_sites rows), then clears the records. */
+#define SARD_PROF_SITES 24
+int sard_prof_enable(unsigned mask, int capacity);
+int sard_prof_collect(double* rows, int n_sites);
+
 /* =====================================================================================
  * Packing: graph indexing layouts (bit-exact integer work)
  * ===================================================================================== */

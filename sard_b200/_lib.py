@@ -104,6 +104,9 @@ _PROTOS = {
     'sard_abi_version': (ci, []),
     'sard_last_error_string': (C.c_char_p, []),
     'sard_struct_sizes': (ci, [P(ci), ci]),
+    'sard_launch_count': (cll, []),
+    'sard_prof_enable': (ci, [C.c_uint, ci]),
+    'sard_prof_collect': (ci, [P(cd), ci]),
     'sard_build_csr': (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     'sard_orbit_rep': (ci, [vp, vp, ci, vp, ci, vp, vp, vp]),
     'sard_gather_nodes': (ci, [P(SardArena), P(SardSel), P(SardGatherOut), vp]),

@@ -7,6 +7,17 @@
 #include "../../include/sard_b200.h"
 
 int sard_set_error(const char* fmt, ...);
+extern long long g_sard_launches;          // kernels launched by this library (bench.py's gpu_launches)
+extern thread_local int g_sard_site;       // call-site label of the next linear / aggregate launch (profiling)
+
+// Optional per-call-site timing with CUDA events on the launching stream (sard_prof_*): a no-op
+// unless the site's bit is enabled, so the timed path pays one branch.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(cudaStream_t stream, double flops, double bytes);
+  ~ProfScope();
+};
 
 #define SARD_CUDA(call)                                                                      \
   do {                                                                                       \
@@ -17,6 +28,7 @@ int sard_set_error(const char* fmt, ...);
 
 #define SARD_LAUNCH_OK(name)                                                                 \
   do {                                                                                       \
+    ++g_sard_launches;                                                                       \
     cudaError_t e__ = cudaGetLastError();                                                    \
     if (e__ != cudaSuccess)                                                                  \
       return sard_set_error("launch %s failed: %s", name, cudaGetErrorString(e__));          \

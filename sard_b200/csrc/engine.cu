@@ -31,6 +31,10 @@ extern "C" int sard_struct_sizes(int* out, int capacity) {
 
 namespace {
 
+// profiling call-site labels: 3*kind + pass (see sard_prof_enable)
+enum { K_INFC = 0, K_GCONV = 1, K_IL = 2, K_ENC = 3, K_MLP = 4, K_HEAD = 5, K_AGG = 6 };
+inline void site(int kind, int pass) { g_sard_site = 3 * kind + pass; }
+
 struct Bump {
   float* base; long long off;
   float* f(long long n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~3LL; return p; }
@@ -104,11 +108,13 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
     g.A = t.x; g.lda = t.ldx; g.B0 = P + tw.in_w; g.ldb0 = tw.D; g.b_split = tw.D; g.bias = P + tw.in_b;
     g.M = n; g.N = tw.h[0]; g.R = tw.D; g.act = SARD_ACT_NONE;
     if (tw.L > 0) { g.Y = t.xa[0] + tw.h[0]; g.ldy = 2 * tw.h[0]; } else { g.Y = t.hout; g.ldy = tw.h[0]; }
+    site(K_INFC, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   for (int l = 1; l <= tw.L; ++l) {
     const int hi = tw.h[l - 1], ho = tw.h[l];
     float* xin = t.xa[l - 1];
+    site(K_AGG, 0);
     SARD_TRY(sard_csr_aggregate(xin + hi, 2 * hi, xin, 2 * hi, nullptr, 0, nullptr, 0, 0, n, hi, t.nd_graph, t.nd_arena,
                                 sel->cum, sel->node_base, arena->in_ptr, arena->in_nbr, st));
     SardGemm g = gemm0();
@@ -116,6 +122,7 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
     g.bias = tw.has_bias ? P + tw.bl[l - 1] : nullptr;
     g.M = n; g.N = ho; g.R = 2 * hi; g.act = tw.act;
     if (l < tw.L) { g.Y = t.xa[l] + ho; g.ldy = 2 * ho; } else { g.Y = t.hout; g.ldy = ho; }
+    site(K_GCONV, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   return 0;
@@ -134,13 +141,16 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
     w.P = dz; w.ldp = ho; w.Q = xin; w.ldq = 2 * hi; w.M = n; w.N1 = ho; w.N2 = 2 * hi;
     w.dW0 = G + tw.wl[l - 1]; w.ldw0 = hi; w.dW1 = G + tw.wr[l - 1]; w.ldw1 = hi; w.w_split = hi;
     w.db = tw.has_bias ? G + tw.bl[l - 1] : nullptr; w.partials = wg_scratch;
+    site(K_GCONV, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, st));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
     g.M = n; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
+    site(K_GCONV, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
     // dz_{l-1} = (dxa[:, hi:2hi] + A^T dxa[:, 0:hi]) * act'(y_{l-1});  layer 0 (in_fc) has no activation
     const float* yprev = (l - 1 >= 1) ? xin + hi : nullptr;
+    site(K_AGG, 1);
     SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[cur ^ 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
                                 t.nd_graph, t.nd_arena, sel->cum, sel->node_base, arena->out_ptr, arena->out_nbr, st));
     cur ^= 1;
@@ -148,12 +158,14 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
   SardWGrad w = wgrad0();
   w.P = t.dz[cur]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;
   w.dW0 = G + tw.in_w; w.ldw0 = tw.D; w.w_split = tw.D; w.db = G + tw.in_b; w.partials = wg_scratch;
+  site(K_INFC, 2);
   return sard_linear_bwd_weight(&w, st);
 }
 
 // ext[B, 3*64] written at `ext` with leading dimension ld_ext; e1[k]: [B,64] hidden activations
 int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena* arena, const SardSel* sel,
                      float* const e1[3], float* ext, int ld_ext, sard_stream_t st) {
+  site(K_ENC, 0);
   for (int k = 0; k < 3; ++k) {
     SardGemm g = gemm0();
     g.A = arena->ext[k]; g.lda = arena->ext_dim[k]; g.a_rows = sel->ids;
@@ -179,12 +191,15 @@ int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const
     SardWGrad w = wgrad0();
     w.P = dz2; w.ldp = ld_dext; w.Q = e1[k]; w.ldq = enc[k][0].out; w.M = sel->B; w.N1 = enc[k][1].out; w.N2 = enc[k][1].in;
     w.dW0 = G + enc[k][1].w; w.ldw0 = enc[k][1].in; w.w_split = enc[k][1].in; w.db = G + enc[k][1].b; w.partials = wg_scratch;
+    site(K_ENC, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, st));
     SardGemm g = gemm0();
     g.A = dz2; g.lda = ld_dext; g.B0 = P + enc[k][1].w; g.ldb0 = enc[k][1].in; g.b_split = enc[k][1].in;
     g.M = sel->B; g.N = enc[k][1].in; g.R = enc[k][1].out; g.Y = de1; g.ldy = enc[k][1].in;
     g.Dact = e1[k]; g.ldd = enc[k][0].out; g.dact0 = SARD_ACT_RELU; g.dact1 = SARD_ACT_RELU; g.dsplit = g.N;
+    site(K_ENC, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
+    site(K_ENC, 2);
     SardWGrad w1 = wgrad0();
     w1.P = de1; w1.ldp = enc[k][0].out; w1.Q = arena->ext[k]; w1.ldq = arena->ext_dim[k]; w1.q_rows = sel->ids;
     w1.M = sel->B; w1.N1 = enc[k][0].out; w1.N2 = enc[k][0].in;
@@ -288,6 +303,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in; g.bias = P + net->mlp[j].b;
     g.M = B; g.N = net->mlp[j].out; g.R = net->mlp[j].in; g.act = net->mlp[j].act;
     g.Y = vb.m[j]; g.ldy = (j < net->n_mlp - 1) ? net->mlp[j].out : vb.ldcat;
+    site(K_MLP, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   SARD_REQUIRE(net->n_mlp > 0, "critic without mlp is not supported");
@@ -296,6 +312,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     g.A = vb.cat; g.lda = vb.ldcat; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat; g.bias = P + net->head.b;
     g.M = B; g.N = 1; g.R = vb.ldcat; g.Y = vb.v; g.ldy = 1;
     SARD_REQUIRE(net->head.in == vb.ldcat, "value head width");
+    site(K_HEAD, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   if (!bwd) return sard_value_loss(vb.v, sel->ids, B, nullptr, 0.f, nullptr, nullptr, arena->values, st);
@@ -307,12 +324,14 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     SardWGrad w = wgrad0();
     w.P = vb.dv; w.ldp = 1; w.Q = vb.cat; w.ldq = vb.ldcat; w.M = B; w.N1 = 1; w.N2 = vb.ldcat;
     w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg;
+    site(K_HEAD, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, st));
     SardGemm g = gemm0();
     g.A = vb.dv; g.lda = 1; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat;
     g.M = B; g.N = vb.ldcat; g.R = 1; g.Y = vb.dcat; g.ldy = vb.ldcat;
     g.Dact = vb.cat; g.ldd = vb.ldcat; g.dact0 = net->mlp[net->n_mlp - 1].act; g.dact1 = SARD_ACT_RELU;
     g.dsplit = vb.ldcat - 3 * SARD_EXT_DIM;
+    site(K_HEAD, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
   }
   SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
@@ -325,6 +344,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     w.P = dzj; w.ldp = ldz; w.M = B; w.N1 = net->mlp[j].out; w.N2 = net->mlp[j].in;
     if (j == 0) { w.Q = vb.t.hout; w.ldq = hL; w.q_rows = vb.t.root_row; } else { w.Q = vb.m[j - 1]; w.ldq = net->mlp[j - 1].out; }
     w.dW0 = G + net->mlp[j].w; w.ldw0 = net->mlp[j].in; w.w_split = net->mlp[j].in; w.db = G + net->mlp[j].b; w.partials = vb.wg;
+    site(K_MLP, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, st));
     SardGemm g = gemm0();
     g.A = dzj; g.lda = ldz; g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in;
@@ -337,6 +357,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
       g.Y = vb.dm[cur]; g.ldy = net->mlp[j - 1].out;
       g.Dact = vb.m[j - 1]; g.ldd = net->mlp[j - 1].out; g.dact0 = net->mlp[j - 1].act; g.dact1 = g.dact0;
     }
+    site(K_MLP, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
     if (j > 0) { dzj = vb.dm[cur]; ldz = net->mlp[j - 1].out; cur ^= 1; }
   }
@@ -453,6 +474,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     } else {
       g.act = s.il_act; g.Y = sb.H[j]; g.ldy = s.il[j].out;
     }
+    site(K_IL, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   // loss (eval: log-probs only)
@@ -490,6 +512,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     w.grp_chunk_ptr = sb.grp_chunk_ptr; w.n_groups = s.max_index; w.slot_of_group = s.slot_of_index;
     w.dW0 = s.GT + s.il[j].gW; w.ldw0 = s.il[j].in; w.w_split = s.il[j].in; w.w_slot_stride = (long long)s.il[j].out * s.il[j].in;
     w.db = s.GT + s.il[j].gb; w.b_slot_stride = s.il[j].out; w.partials = sb.wg;
+    site(K_IL, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, st));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ldz; g.a_rows = dz_rows;
@@ -498,6 +521,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     g.tiles = sb.tiles; g.num_tiles = sb.counts; g.max_tiles = sb.max_tiles;
     if (j == 0) { g.Y = sb.dxs; g.ldy = sb.ldxs; }
     else { g.Y = sb.dH[cur]; g.ldy = s.il[j - 1].out; g.Dact = sb.H[j - 1]; g.ldd = s.il[j - 1].out; g.dact0 = s.il_act; g.dact1 = s.il_act; }
+    site(K_IL, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
     if (j > 0) { dz = sb.dH[cur]; ldz = s.il[j - 1].out; dz_rows = nullptr; cur ^= 1; }
   }

@@ -158,6 +158,9 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   SARD_REQUIRE(g->R > 0, "gemm: empty reduction");
   SARD_REQUIRE(g->B1 != nullptr || g->b_split >= (NT ? g->R : g->N), "gemm: b_split without second source");
   cudaStream_t st = as_stream(stream);
+  const double groups = g->b_group_stride ? 13.0 : 1.0;   // weight slabs touched (live indices, nominal)
+  ProfScope prof(st, 2.0 * g->M * (double)g->N * g->R,
+                 4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
   if (g->N <= 16) {
     constexpr int BM = 128, BN = 16;
     const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
@@ -318,6 +321,9 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream) 
     nchunks = ceil_div(w->M, w->chunk_rows);
   }
   if (nchunks <= 0) return 0;
+  const double wgroups = w->grp_chunk_ptr ? 13.0 : 1.0;
+  ProfScope prof(st, 2.0 * w->M * (double)w->N1 * w->N2,
+                 4.0 * ((double)w->M * w->N1 + (double)w->M * w->N2 + wgroups * (double)w->N1 * w->N2));
   dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
   wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
   SARD_LAUNCH_OK("wgrad_kernel");

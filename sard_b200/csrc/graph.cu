@@ -44,6 +44,9 @@ extern "C" int sard_csr_aggregate(const float* in, int ld_in, float* out, int ld
   SARD_REQUIRE(!yprev || ld_yprev % 4 == 0, "aggregate: ld_yprev");
   SARD_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0), "aggregate: 16-byte alignment");
   AggP p{in, ld_in, out, ld_out, base, ld_base, yprev, ld_yprev, dact, n, F / 4, nd_graph, nd_arena, cum, node_base, nbr_ptr, nbr};
+  // algorithmic bytes: read the feature rows once, write them once, plus the index arrays (2 n F 4 + (n+1+e) 4,
+  // e = 2(n - graphs) for trees ~ 2n)
+  ProfScope prof(as_stream(stream), (double)n * F, 4.0 * ((2.0 + (base ? 1.0 : 0.0) + (yprev ? 1.0 : 0.0)) * (double)n * F + 5.0 * n));
   csr_aggregate_kernel<<<grid_for((long long)n * (F / 4), 256, 16), 256, 0, as_stream(stream)>>>(p);
   SARD_LAUNCH_OK("csr_aggregate_kernel");
   return 0;

@@ -1,0 +1,61 @@
+// Launch counter and optional per-call-site kernel timing (see sard_prof_* in sard_b200.h).
+#include "common.cuh"
+#include <vector>
+
+long long g_sard_launches = 0;
+thread_local int g_sard_site = -1;
+
+namespace {
+struct Rec { int site; double flops, bytes; cudaEvent_t a, b; };
+unsigned g_mask = 0;
+int g_capacity = 0;
+std::vector<Rec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+}  // namespace
+
+ProfScope::ProfScope(cudaStream_t stream, double flops, double bytes) : slot(-1), st(stream) {
+  const int site = g_sard_site;
+  if (g_mask == 0 || site < 0 || site >= SARD_PROF_SITES || !((g_mask >> site) & 1u)) return;
+  if ((int)g_recs.size() >= g_capacity) return;
+  Rec r;
+  r.site = site; r.flops = flops; r.bytes = bytes;
+  for (cudaEvent_t* e : {&r.a, &r.b}) {
+    if (!g_pool.empty()) { *e = g_pool.back(); g_pool.pop_back(); }
+    else if (cudaEventCreate(e) != cudaSuccess) return;
+  }
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+  slot = (int)g_recs.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_recs[slot].b, st);
+}
+
+extern "C" long long sard_launch_count(void) { return g_sard_launches; }
+
+extern "C" int sard_prof_enable(unsigned mask, int capacity) {
+  g_mask = mask;
+  g_capacity = capacity;
+  if (capacity > 0) g_recs.reserve(capacity);
+  return 0;
+}
+
+extern "C" int sard_prof_collect(double* rows, int n_sites) {
+  for (int i = 0; i < n_sites * 4; ++i) rows[i] = 0.0;
+  for (const Rec& r : g_recs) {
+    SARD_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    SARD_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.site < n_sites) {
+      rows[r.site * 4 + 0] += 1.0;
+      rows[r.site * 4 + 1] += (double)ms;
+      rows[r.site * 4 + 2] += r.flops;
+      rows[r.site * 4 + 3] += r.bytes;
+    }
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return 0;
+}
