@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the SARD PPO-update hot path (BASELINE.json metric: PPO transitions/sec,
+policy+value fwd/bwd, and kernel roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+Workload (config.workload): locomotion_ft.yml PPO update -- synthetic rollouts of the env's
+observation/graph shape, T = 50 000 transitions per GPU, minibatch 2048 per GPU, 10 optimisation
+epochs (design_opt/cfg/derl.yml:65-69).  One *step* = one whole ``update_params``
+(value pre-pass, GAE, fixed log-prob pre-pass, 240 minibatch updates of value fwd/bwd/Adam +
+policy fwd/bwd/clip/Adam) = 491 520 transition-updates per GPU.
+
+``value``  : transition-updates/s with the rollout arena already resident in HBM.
+``e2e``    : the same through ``Transform2ActAgent.update_params(batch)`` with the reference's
+             host-side batch (list of per-transition states, TrajBatchDisc layout): host packing,
+             host->device copies and the device->host log read are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'PPO transitions/sec (policy+value fwd/bwd)'
+UNIT = 'transition-updates/s'
+SITE_KINDS = ('in_fc', 'graphconv', 'index_linear', 'obs_encoder', 'critic_mlp', 'value_head', 'csr_aggregate')
+SITE_PASS = ('fwd', 'bwd_data', 'bwd_weight')
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FFMA lanes x 2 flop x boost clock
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--env', default='locomotion_ft')
+    ap.add_argument('--transitions', type=int, default=50000)
+    ap.add_argument('--mini-batch', type=int, default=2048)
+    ap.add_argument('--epochs', type=int, default=10)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sites-out', default='', help='write the per-call-site kernel time table (JSON) here')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_burst': d['bf16_tflops'], 'bf16_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:                 # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_setup(env_name, n_graphs, seed=1234):
+    """The reference algorithm restated on CPU (oracle/sard_oracle.py, fp64 like design_opt/train.py:51)
+    with the full derl.yml network sizes, on a bounded sample of the bench workload."""
+    import torch
+    from oracle import sard_oracle as O
+    from sard_b200 import synthetic
+    from sard_b200.config import derl_config
+    from sard_b200.transform2act_agent import Transform2ActAgent
+    shape = synthetic.ENV_SHAPES[env_name]
+    torch.manual_seed(0)
+    holder = Transform2ActAgent(derl_config(), torch.float32, 'cpu', 0, 1, env=synthetic.SyntheticEnv(shape))
+
+    def sd64(m):
+        out = {}
+        for k, v in m.state_dict().items():
+            if k.endswith('.inv'):
+                continue
+            t = v.detach().double().clone() if v.is_floating_point() else v.clone()
+            if t.is_floating_point() and not any(k.endswith(s) for s in ('.mean', '.var', '.std')):
+                t.requires_grad_(True)
+            out[k] = t
+        return out
+
+    psd, vsd = sd64(holder.policy_net), sd64(holder.value_net)
+    spec = O.Spec(attr_fixed_dim=shape.attr_fixed_dim, index_base=shape.index_base,
+                  embeds=holder.policy_net.group.get_cur_subgroup_embeds().double(),
+                  orbits={int(k): [int(x) for x in v] for k, v in holder.policy_net.group.get_cur_orbits().items()})
+    roll = synthetic.generate_rollout(shape, 12000, seed=seed)
+    # a minibatch as the reference sees it after shuffling: execution-stage dominated, stage-sorted
+    idx = np.sort(np.random.default_rng(seed).permutation(roll.num_transitions)[:n_graphs])
+    idx = idx[np.argsort(roll.stage[idx], kind='stable')]
+    sub = roll.select(idx)
+    b = sub.to_traj_batch()
+    states = [[torch.tensor(x) if i in (0, 1, 5, 6, 7) else x for i, x in enumerate(s)] for s in b.states]
+    actions = [torch.tensor(a) for a in b.actions]
+    agent = O.OracleAgent(psd, vsd, spec)
+    g = torch.Generator().manual_seed(1)
+    ret = torch.randn(n_graphs, 1, dtype=torch.float64, generator=g)
+    adv = torch.randn(n_graphs, 1, dtype=torch.float64, generator=g)
+    with torch.no_grad():
+        fixed = O.policy_log_prob(psd, spec, states, actions, training=False)
+    return agent, states, actions, ret, adv, fixed
+
+
+def oracle_time(env_name, steps, warmup, n_graphs):
+    import torch
+    agent, states, actions, ret, adv, fixed = oracle_setup(env_name, n_graphs)
+    for _ in range(warmup):
+        agent.update_value(states, ret); agent.policy_step(states, actions, adv, fixed)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        agent.update_value(states, ret)
+        agent.policy_step(states, actions, adv, fixed)
+    dt = time.perf_counter() - t0
+    return n_graphs * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    val, per_step, threads = oracle_time(args.env, args.steps, max(args.warmup, 1), args.mini_batch)
+    sample = (f'{args.steps} minibatch updates of {args.mini_batch} transitions ({args.env} shape, fp64, value fwd/bwd/Adam + '
+              f'policy fwd/bwd/clip/Adam, full derl.yml nets) after {max(args.warmup, 1)} warm-up')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, 1),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'oracle port of the reference PPO update (the reference is pure Python and cannot travel to the GPU box); '
+                'calibrated against the unmodified reference in the build container: same s/step within 10%',
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {'workload': f'{args.env}.yml PPO update_params, synthetic rollouts of the env obs/graph shape',
+            'env': args.env, 'transitions_per_gpu': args.transitions, 'mini_batch_per_gpu': args.mini_batch,
+            'optim_epochs': args.epochs, 'global_mini_batch': args.mini_batch * world,
+            'transition_updates_per_step_per_gpu': (args.transitions // args.mini_batch) * args.mini_batch * args.epochs,
+            'parallelism': f'dp{world} (transition-sharded, NCCL allreduce)' if world > 1 else 'single GPU',
+            'l2': 'arena + activations exceed L2 (129 MB obs + 240 different minibatches per step); '
+                  '256 MiB flush written between steps'}
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from sard_b200 import _lib, synthetic
+    from sard_b200.config import DERL_YML, Config
+    from sard_b200.engine import Comm
+    from sard_b200.rl_core import estimate_advantages
+    from sard_b200.transform2act_agent import Transform2ActAgent
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the SARD B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    comm = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        comm = Comm()
+    lib = _lib.lib
+
+    shape = synthetic.ENV_SHAPES[args.env]
+    d = dict(DERL_YML)
+    d.update(min_batch_size=args.transitions, mini_batch_size=args.mini_batch, num_optim_epoch=args.epochs)
+    cfg = Config(d)
+    torch.manual_seed(0)                       # identical initial weights on every rank
+    np.random.seed(1234)                       # identical shuffle stream on every rank
+    agent = Transform2ActAgent(cfg, torch.float32, dev, 0, 1, env=synthetic.SyntheticEnv(shape), comm=comm)
+    roll = synthetic.generate_rollout(shape, args.transitions, seed=1234 + rank, dtype=np.float32)
+    upd_per_step = (args.transitions // args.mini_batch) * args.mini_batch * args.epochs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def resident_step(arena):
+        flush.fill_(1)
+        for m in agent.update_modules:
+            m.train(False)
+        agent._eval_values(arena)
+        for m in agent.update_modules:
+            m.train(True)
+        a, r = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), agent.gamma, agent.tau)
+        arena.advantages.copy_(a.reshape(-1)); arena.returns.copy_(r.reshape(-1))
+        agent.update_policy_packed(arena)
+
+    arena = agent.pack(roll)
+    agent._prepare(arena)
+    for _ in range(args.warmup):
+        resident_step(arena)
+    barrier()
+
+    # ---- per-call-site table (diagnostic pass, not part of any reported throughput) ----------------
+    site_rows = None
+    top_site = None
+    if rank == 0:
+        lib.sard_prof_enable(0xFFFFFFFF, 200000)
+        resident_step(arena)
+        torch.cuda.synchronize()
+        import ctypes as C
+        buf = (C.c_double * (4 * 24))()
+        _lib.check(lib.sard_prof_collect(buf, 24))
+        lib.sard_prof_enable(0, 0)
+        site_rows = []
+        for s in range(21):
+            n, ms, fl, by = buf[4 * s:4 * s + 4]
+            if n > 0:
+                site_rows.append({'site': f'{SITE_KINDS[s // 3]}.{SITE_PASS[s % 3]}', 'id': s, 'launches': int(n), 'ms': ms,
+                                  'tflops': fl / ms / 1e9 if ms > 0 else 0.0, 'gbs': by / ms / 1e6 if ms > 0 else 0.0})
+        site_rows.sort(key=lambda r: -r['ms'])
+        top_site = site_rows[0]['id'] if site_rows else None
+    if world > 1:
+        t = torch.tensor([top_site if top_site is not None else -1], device=dev)
+        dist.broadcast(t, 0)
+        top_site = int(t.item())
+    barrier()
+
+    # ---- timed region: K steps on resident data -----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if top_site is not None and top_site >= 0 and rank == 0:
+        lib.sard_prof_enable(1 << top_site, 400000)
+    launches0 = lib.sard_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        resident_step(arena)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.sard_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    roof = None
+    if rank == 0 and top_site is not None and top_site >= 0:
+        import ctypes as C
+        buf = (C.c_double * (4 * 24))()
+        _lib.check(lib.sard_prof_collect(buf, 24))
+        lib.sard_prof_enable(0, 0)
+        n, tms, fl, by = buf[4 * top_site:4 * top_site + 4]
+        pk = peaks()
+        kind = SITE_KINDS[top_site // 3]
+        if kind == 'csr_aggregate':
+            ach = by / tms / 1e6
+            roof = {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'], 'traffic': None}
+        else:
+            ach = fl / tms / 1e9
+            roof = {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+                    'frac': ach / pk['bf16_sustained'], 'traffic': None,
+                    'pipe': 'fp32 FFMA (SIMT); parity target rtol 1e-4 rules out single-pass TF32/bf16',
+                    'fp32_peak_tflops': FP32_PEAK_TFLOPS, 'frac_of_fp32_peak': ach / FP32_PEAK_TFLOPS,
+                    'algorithmic_gbs': by / tms / 1e6}
+        roof.update({'kernel': f'{kind}.{SITE_PASS[top_site % 3]}', 'launches_timed': int(n), 'avg_launch_us': tms / n * 1e3 if n else None,
+                     'share_of_step': tms / ms, 'peak_source': pk['source'] + ' (sustained figure: kernel timed inside a long step)'})
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * upd_per_step * args.steps / (ms / 1e3)
+
+    # ---- e2e: public API with the reference's host batch --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        batch = roll.to_traj_batch()
+        agent.update_params(batch)            # warm-up of the host path
+        barrier()
+        k = max(1, min(args.steps, 3))
+        e0.record()
+        for _ in range(k):
+            agent.update_params(batch)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        st = agent.last_update_stats
+        e2e = {'value': world * upd_per_step * k / (ems / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': int(st['h2d_bytes']),
+               'd2h_bytes_per_step': int(st['d2h_bytes']), 'ms_per_step': ems / k, 'steps': k,
+               'api': 'Transform2ActAgent.update_params(TrajBatchDisc-style list of states)'}
+        # the same with the batch already flattened on the host (HostRollout): isolates the Python list walk
+        agent.update_params(roll)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            agent.update_params(roll)
+        e1.record()
+        barrier()
+        e2e['packed_host_value'] = world * upd_per_step * k / (e0.elapsed_time(e1) / 1e3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, per, thr = oracle_time(args.env, 2, 1, args.mini_batch)
+        cpu = {'value': v, 'unit': UNIT, 'cores': thr, 'kind': 'port',
+               'sample': f'2 minibatch updates of {args.mini_batch} transitions (fp64, full nets) after 1 warm-up; {per:.2f} s each'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e,
+            'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+            'valid_policy_steps_last': int(agent.last_update_stats.get('valid_steps', -1)),
+        }
+        print(json.dumps(line), flush=True)
+        if args.sites_out and site_rows is not None:
+            with open(args.sites_out, 'w') as f:
+                json.dump({'ms_per_update': ms / args.steps, 'sites': site_rows}, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()
