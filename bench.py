@@ -236,8 +236,14 @@ def run_native(args):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    host_rng = np.random.default_rng(99 + rank)
+
     def resident_step(arena):
         flush.fill_(1)
+        # fresh synthetic rewards every step: re-using one batch would let the policy over-fit its
+        # advantages and trip the KL gate (transform2act_agent.py:404-407), which real rollouts do not
+        arena.rewards.normal_(0.01, 0.1, generator=gen)
         for m in agent.update_modules:
             m.train(False)
         agent._eval_values(arena)
@@ -331,6 +337,7 @@ def run_native(args):
         k = max(1, min(args.steps, 3))
         e0.record()
         for _ in range(k):
+            batch.rewards = host_rng.normal(0.01, 0.1, size=args.transitions)
             agent.update_params(batch)
         e1.record()
         barrier()
@@ -348,6 +355,7 @@ def run_native(args):
         barrier()
         e0.record()
         for _ in range(k):
+            roll.rewards = host_rng.normal(0.01, 0.1, size=args.transitions).astype(np.float32)
             agent.update_params(roll)
         e1.record()
         barrier()

@@ -207,7 +207,7 @@ typedef struct {
   const float* Q; int ldq; const int* q_rows;    /* layer input [M, N2] */
   int M, N1, N2;
   const int* chunks; const int* num_chunks; int max_chunks;   /* optional int4 {row_start,row_end,index,0} */
-  int chunk_rows;                                /* rows per chunk when chunks == NULL */
+  int chunk_rows;                                /* rows per chunk when chunks == NULL (0: automatic) */
   const int* grp_chunk_ptr; int n_groups;        /* grouped: chunks of index u are [ptr[u], ptr[u+1]) */
   const int* slot_of_group;                      /* grouped: destination slot of each index (-1: skip) */
   float* dW0; int ldw0; float* dW1; int ldw1; int w_split;   /* dW[c1, c2] destination, split on c2 */
@@ -215,7 +215,10 @@ typedef struct {
   float* db; int b_slot_stride;                  /* optional bias grad [N1] (per slot when grouped) */
   float* partials;                               /* scratch float[max_chunks * N1 * (N2+1)] */
 } SardWGrad;
-/* dW += dZ^T A, db += colsum(dZ): two kernels (per-chunk partial products, ordered reduction). */
+/* dW += dZ^T A, db += colsum(dZ): two kernels (per-chunk partial products, ordered reduction).
+ * Ungrouped calls may pass chunk_rows = 0 to let the library pick sard_wgrad_chunk_rows(M,N1,N2)
+ * (the partials scratch must then hold ceil(M/that) * N1 * (N2+1) floats). */
+int sard_wgrad_chunk_rows(int M, int N1, int N2);
 int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream);
 
 /* =====================================================================================

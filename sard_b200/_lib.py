@@ -121,6 +121,7 @@ _PROTOS = {
     'sard_linear_fwd': (ci, [P(SardGemm), vp]),
     'sard_linear_bwd_data': (ci, [P(SardGemm), vp]),
     'sard_linear_bwd_weight': (ci, [P(SardWGrad), vp]),
+    'sard_wgrad_chunk_rows': (ci, [ci, ci, ci]),
     'sard_gauss_loss': (ci, [P(SardPolicyLoss), vp]),
     'sard_cat_loss': (ci, [P(SardPolicyLoss), vp]),
     'sard_loss_reduce': (ci, [vp, ci, ci, vp, vp, ci, vp, vp]),

@@ -42,8 +42,9 @@ struct Bump {
 };
 
 inline int r4(int v) { return (v + 3) & ~3; }
-inline long long wg_partials(int M, int N1, int N2, int chunk_rows) {
-  return (long long)ceil_div(M, chunk_rows) * N1 * (N2 + 1);
+inline long long wg_partials(int M, int N1, int N2, int /*unused*/) {
+  if (M <= 0) return 0;
+  return (long long)ceil_div(M, sard_wgrad_chunk_rows(M, N1, N2)) * N1 * (N2 + 1);
 }
 
 constexpr int WG_CHUNK = 256;     // rows per weight-gradient chunk
@@ -87,7 +88,7 @@ long long tower_wg_need(const SardTower& tw, int n) {
 }
 
 SardGemm gemm0() { SardGemm g; memset(&g, 0, sizeof(g)); return g; }
-SardWGrad wgrad0() { SardWGrad w; memset(&w, 0, sizeof(w)); w.chunk_rows = WG_CHUNK; return w; }
+SardWGrad wgrad0() { SardWGrad w; memset(&w, 0, sizeof(w)); w.chunk_rows = 0; return w; }   // 0: auto chunking
 
 int tower_gather(const SardTower& tw, const SardArena* arena, const SardSel* sel, int lead, int tail, int nconst,
                  const float* consts, int onehot, TowerBufs& t, sard_stream_t st) {

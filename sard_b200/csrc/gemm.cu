@@ -167,6 +167,11 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
     if (tiles <= 0) return 0;
     dim3 grid(tiles, ceil_div(g->N, BN));
     gemm_kernel<BM, BN, 16, 4, 2, NT><<<grid, 256, 0, st>>>(*g);
+  } else if (!g->tiles && (long long)ceil_div(g->M, 128) * ceil_div(g->N, 64) < 2 * 148) {
+    // few large tiles would leave most of the 148 SMs idle: use 64x64 tiles (4x the CTAs)
+    constexpr int BM = 64, BN = 64;
+    dim3 grid(ceil_div(g->M, BM), ceil_div(g->N, BN));
+    gemm_kernel<BM, BN, 16, 4, 4, NT><<<grid, 256, 0, st>>>(*g);
   } else {
     constexpr int BM = 128, BN = 64;
     const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
@@ -308,8 +313,23 @@ __global__ void wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
   }
 }
 
-extern "C" int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream) {
-  if (w->M <= 0 || w->N1 <= 0 || w->N2 <= 0) return 0;
+// Rows per chunk for an ungrouped weight gradient: enough chunks to put ~2 CTAs on every SM, at least
+// 16 rows each (the partial products are reduced in chunk order afterwards).
+extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
+  const long long tiles = (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
+  long long chunks = (2 * 148 + tiles - 1) / tiles;
+  if (chunks < 1) chunks = 1;
+  long long rows = (M + chunks - 1) / chunks;
+  rows = (rows + 15) / 16 * 16;
+  if (rows < 16) rows = 16;
+  if (rows > 1024) rows = 1024;
+  return (int)rows;
+}
+
+extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t stream) {
+  if (w_in->M <= 0 || w_in->N1 <= 0 || w_in->N2 <= 0) return 0;
+  SardWGrad wl = *w_in;
+  SardWGrad* w = &wl;
   SARD_REQUIRE(w->dW1 != nullptr || w->w_split >= w->N2, "wgrad: w_split without second destination");
   SARD_REQUIRE(w->partials != nullptr, "wgrad: partials scratch");
   cudaStream_t st = as_stream(stream);
@@ -317,15 +337,20 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream) 
   if (w->chunks) {
     nchunks = w->max_chunks;
   } else {
-    SARD_REQUIRE(w->chunk_rows > 0, "wgrad: chunk_rows");
+    if (w->chunk_rows <= 0) w->chunk_rows = sard_wgrad_chunk_rows(w->M, w->N1, w->N2);
     nchunks = ceil_div(w->M, w->chunk_rows);
   }
   if (nchunks <= 0) return 0;
   const double wgroups = w->grp_chunk_ptr ? 13.0 : 1.0;
   ProfScope prof(st, 2.0 * w->M * (double)w->N1 * w->N2,
                  4.0 * ((double)w->M * w->N1 + (double)w->M * w->N2 + wgroups * (double)w->N1 * w->N2));
-  dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
-  wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
+  if (w->N1 <= 16) {
+    dim3 grid(nchunks, 1, ceil_div(w->N2, 64));
+    wgrad_kernel<16, 64, 16, 4, 4><<<grid, 64, 0, st>>>(*w);
+  } else {
+    dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
+    wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
+  }
   SARD_LAUNCH_OK("wgrad_kernel");
   dim3 rgrid(ceil_div((long long)w->N1 * (w->N2 + 1), 256), w->grp_chunk_ptr ? w->n_groups : 1);
   wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(*w, w->chunks ? 0 : nchunks);
