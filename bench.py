@@ -264,8 +264,9 @@ def run_native(args):
     top_site = None
     if rank == 0:
         lib.sard_prof_enable(0xFFFFFFFF, 200000)
-        resident_step(arena)
-        torch.cuda.synchronize()
+    resident_step(arena)                   # every rank takes part (the step contains collectives)
+    torch.cuda.synchronize()
+    if rank == 0:
         import ctypes as C
         buf = (C.c_double * (4 * 24))()
         _lib.check(lib.sard_prof_collect(buf, 24))
