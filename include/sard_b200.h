@@ -196,6 +196,11 @@ typedef struct {
   int max_tiles;               /* host upper bound (grid size) */
 } SardGemm;
 
+/* Engine behind sard_linear_fwd / sard_linear_bwd_data: 0 = fp32 FFMA SIMT tiles, 1 = tcgen05 tensor cores
+ * with error-compensated 3xTF32 (hi/lo split, fp32 accumulation in TMEM) for N > 16 and R >= 8. */
+int sard_set_gemm_engine(int engine);
+int sard_get_gemm_engine(void);
+
 /* Y = post(act(A W^T + bias)).  Replaces nn.Linear / GraphConv lin_l+lin_r / IndexLinear.forward
  * (gnn.py:57,63; jsmlp.py:15-20,32-40; mlp.py:22-25; critic.py:103). */
 int sard_linear_fwd(const SardGemm* g, sard_stream_t stream);

@@ -118,6 +118,8 @@ _PROTOS = {
     'sard_csr_aggregate': (ci, [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp]),
     'sard_concat_sorted': (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, vp, ci, vp]),
     'sard_unsort_grad': (ci, [vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp]),
+    'sard_set_gemm_engine': (ci, [ci]),
+    'sard_get_gemm_engine': (ci, []),
     'sard_linear_fwd': (ci, [P(SardGemm), vp]),
     'sard_linear_bwd_data': (ci, [P(SardGemm), vp]),
     'sard_linear_bwd_weight': (ci, [P(SardWGrad), vp]),
@@ -178,6 +180,8 @@ def check_struct_sizes():
 
 
 check_struct_sizes()
+if os.environ.get('SARD_GEMM_ENGINE') is not None:       # 0 = fp32 FFMA, 1 = tcgen05 3xTF32
+    lib.sard_set_gemm_engine(int(os.environ['SARD_GEMM_ENGINE']))
 
 
 def check(rc: int):

@@ -152,6 +152,11 @@ gemm_kernel(const SardGemm g) {
   }
 }
 
+int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st);   // umma.cu; -1 = shape not handled
+int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
+extern "C" int sard_set_gemm_engine(int engine) { g_sard_gemm_engine = engine; return 0; }
+extern "C" int sard_get_gemm_engine(void) { return g_sard_gemm_engine; }
+
 template <bool NT>
 static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   if (g->M <= 0 || g->N <= 0) return 0;
@@ -161,6 +166,10 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   const double groups = g->b_group_stride ? 13.0 : 1.0;   // weight slabs touched (live indices, nominal)
   ProfScope prof(st, 2.0 * g->M * (double)g->N * g->R,
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
+  if (g_sard_gemm_engine == 1) {
+    const int r = sard_umma_gemm(g, NT, st);
+    if (r >= 0) return r;
+  }
   if (g->N <= 16) {
     constexpr int BM = 128, BN = 16;
     const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);

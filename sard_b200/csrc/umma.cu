@@ -1,0 +1,292 @@
+// tcgen05 (5th-gen tensor core) engine for the linear layers: error-compensated 3xTF32.
+//
+//   D[128 x Nt] (fp32, TMEM) += A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T        per 8-wide k-step
+//
+// A and B tiles are read from global memory by all threads through the same operand accessors as the
+// SIMT engine (row gather, [lin_l|lin_r] split weights, per-body-index weight slabs, transposed
+// weights for backward-data), split into hi = top 19 bits and lo = v - hi, and written to shared
+// memory in the canonical K-major SWIZZLE_128B layout that the UMMA shared-memory descriptors
+// describe (8-row x 128-byte atoms, 16-byte chunk index XOR row&7).  One elected thread issues
+// tcgen05.mma.kind::tf32 (M=128, N=Nt, K=8); completion is tracked with tcgen05.commit on
+// mbarriers, two smem stages overlap the fill of chunk k+1 with the MMAs of chunk k; the epilogue
+// reads the accumulator with tcgen05.ld (32 lanes x 32 columns per warp) and applies the same
+// bias / activation / sin / act' / row-scatter epilogue as the SIMT engine.
+// hi*hi + lo*hi + hi*lo keeps ~2^-21 relative error, inside the rtol 1e-4 parity target that a
+// single TF32 pass (2^-11) would miss.
+#include "common.cuh"
+
+#define UMMA_BM 128
+#define UMMA_KC 32            // fp32 elements per 128-byte swizzle row
+#define UMMA_THREADS 256
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major SWIZZLE_128B descriptor: start address, LBO = 1 (unused for swizzled K-major), SBO = 1024 B
+// between 8-row groups, version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// store one 16-byte chunk (4 consecutive k) of tile row `row` as hi and lo parts
+__device__ __forceinline__ void store_split(float* hi_tile, float* lo_tile, int row, int chunk, float4 v) {
+  const int off = row * UMMA_KC + ((chunk ^ (row & 7)) << 2);
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+template <int NT_TILE, bool NT>
+__global__ void __launch_bounds__(UMMA_THREADS, 1) umma_gemm_kernel(const SardGemm g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_TILE = UMMA_BM * UMMA_KC;                // floats
+  constexpr int B_TILE = NT_TILE * UMMA_KC;
+  constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;           // A_hi, A_lo, B_hi, B_lo
+  // 1024-byte aligned base (dynamic smem is only guaranteed 16-byte aligned)
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_stage[2];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+
+  int row_start, row_end, group = 0;
+  if (g.tiles) {
+    const int nt = *g.num_tiles;
+    if ((int)blockIdx.x >= nt) return;
+    const int4 t = reinterpret_cast<const int4*>(g.tiles)[blockIdx.x];
+    row_start = t.x; row_end = t.y; group = t.z;
+  } else {
+    row_start = blockIdx.x * UMMA_BM;
+    row_end = min(g.M, row_start + UMMA_BM);
+    if (row_start >= g.M) return;
+  }
+  const int n0 = blockIdx.y * NT_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* B0 = g.B0 + (size_t)group * g.b_group_stride;
+  const float* B1 = g.B1 ? g.B1 + (size_t)group * g.b_group_stride : nullptr;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)NT_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(&bar_stage[0], 1);
+    mbar_init(&bar_stage[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  // A rows handled by this thread: chunk-fastest mapping (8 threads cover one 128-byte row)
+  constexpr int A_CH = UMMA_BM * 8 / UMMA_THREADS;          // 4 chunks per thread
+  long long a_off[A_CH];
+#pragma unroll
+  for (int i = 0; i < A_CH; ++i) {
+    const int m = (tid + i * UMMA_THREADS) >> 3;
+    const int grow = row_start + m;
+    a_off[i] = grow < row_end ? (long long)(g.a_rows ? g.a_rows[grow] : grow) * g.lda : -1;
+  }
+  const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+  const bool b_vec = NT && ((g.ldb0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(B0) & 15) == 0) && ((g.b_split & 3) == 0) &&
+                     (!B1 || (((g.ldb1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(B1) & 15) == 0)));
+  // instruction descriptor: D fp32, A/B tf32, both K-major, N, M
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT_TILE >> 3) << 17) | ((uint32_t)(UMMA_BM >> 4) << 24);
+
+  const int nkc = (g.R + UMMA_KC - 1) / UMMA_KC;
+  for (int kc = 0; kc < nkc; ++kc) {
+    const int s = kc & 1;
+    float* a_hi = base + s * STAGE;
+    float* a_lo = a_hi + A_TILE;
+    float* b_hi = a_lo + A_TILE;
+    float* b_lo = b_hi + B_TILE;
+    if (kc >= 2) mbar_wait(&bar_stage[s], ((kc >> 1) - 1) & 1);   // MMAs of chunk kc-2 have drained this stage
+    const int k0 = kc * UMMA_KC;
+    // ---- A tile ----
+#pragma unroll
+    for (int i = 0; i < A_CH; ++i) {
+      const int idx = tid + i * UMMA_THREADS;
+      const int m = idx >> 3, c = idx & 7;
+      const int kk = k0 + c * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_off[i] >= 0 && kk < g.R) {
+        const float* p = g.A + a_off[i] + kk;
+        if (a_vec && kk + 3 < g.R) v = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+          v.x = __ldg(p);
+          if (kk + 1 < g.R) v.y = __ldg(p + 1);
+          if (kk + 2 < g.R) v.z = __ldg(p + 2);
+          if (kk + 3 < g.R) v.w = __ldg(p + 3);
+        }
+      }
+      store_split(a_hi, a_lo, m, c, v);
+    }
+    // ---- B tile: B(n, k) ----
+    constexpr int B_CH = NT_TILE * 8 / UMMA_THREADS;         // chunks per thread
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int idx = tid + i * UMMA_THREADS;
+      int n, c;
+      if (NT) { n = idx >> 3; c = idx & 7; }                 // source contiguous along k
+      else    { n = idx % NT_TILE; c = idx / NT_TILE; }      // source contiguous along n
+      const int gc = n0 + n, kk = k0 + c * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gc < g.N && kk < g.R) {
+        if (NT) {
+          if (b_vec && kk + 3 < g.R) {
+            v = kk < g.b_split ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)gc * g.ldb0 + kk))
+                               : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)gc * g.ldb1 + (kk - g.b_split)));
+          } else {
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = kk + j;
+              if (k < g.R) e[j] = k < g.b_split ? __ldg(B0 + (size_t)gc * g.ldb0 + k) : __ldg(B1 + (size_t)gc * g.ldb1 + (k - g.b_split));
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+          }
+        } else {
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kk + j;
+            if (k < g.R) e[j] = gc < g.b_split ? __ldg(B0 + (size_t)k * g.ldb0 + gc) : __ldg(B1 + (size_t)k * g.ldb1 + (gc - g.b_split));
+          }
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      store_split(b_hi, b_lo, n, c, v);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (UMMA)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+      const int ksteps = min(4, (g.R - k0 + 7) >> 3);
+      for (int k = 0; k < ksteps; ++k) {
+        const uint32_t adv = k * 32;                               // 8 tf32 = 32 bytes inside the swizzle row
+        const uint64_t da_hi = umma_desc(sa_hi + adv), da_lo = umma_desc(sa_lo + adv);
+        const uint64_t db_hi = umma_desc(sb_hi + adv), db_lo = umma_desc(sb_lo + adv);
+        umma_tf32(tmem_d, da_hi, db_hi, idesc, (kc | k) ? 1u : 0u);
+        umma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+        umma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+      }
+      umma_commit(&bar_stage[s]);
+      if (kc == nkc - 1) umma_commit(&bar_done);
+    }
+  }
+  mbar_wait(&bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., warps w and w+4 split the columns ----
+  const int lane_grp = warp & 3;
+  const int grow = row_start + lane_grp * 32 + lane;
+  const bool row_ok = grow < row_end;
+  const long long yrow = row_ok ? (g.y_rows ? g.y_rows[grow] : grow) : 0;
+  const float* bias = g.bias ? g.bias + (size_t)group * g.bias_group_stride : nullptr;
+  constexpr int NCHUNK = NT_TILE / 32;
+  for (int cc = (warp >> 2); cc < NCHUNK; cc += 2) {
+    float v[32];
+    tmem_ld32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cc * 32), v);
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gc = n0 + cc * 32 + j;
+        if (gc >= g.N) break;
+        float x = v[j];
+        if (NT) {
+          if (bias) x += __ldg(bias + gc);
+          x = act_apply(x, g.act);
+          if (g.Ypre) g.Ypre[yrow * g.ldy + gc] = x;
+          if (g.post == SARD_POST_SIN_HALF_PI) x = sinf(x * 1.57079632679489662f);
+        } else if (g.Dact) {
+          x *= act_grad_from_output(g.Dact[yrow * g.ldd + gc], gc < g.dsplit ? g.dact0 : g.dact1);
+        }
+        g.Y[yrow * g.ldy + gc] = x;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)NT_TILE) : "memory");
+  }
+}
+
+template <int NT_TILE, bool NT>
+static int launch_umma_t(const SardGemm* g, cudaStream_t st) {
+  constexpr size_t smem = 2 * (2 * UMMA_BM * UMMA_KC + 2 * NT_TILE * UMMA_KC) * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SARD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<NT_TILE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, UMMA_BM);
+  if (tiles <= 0) return 0;
+  dim3 grid(tiles, ceil_div(g->N, NT_TILE));
+  umma_gemm_kernel<NT_TILE, NT><<<grid, UMMA_THREADS, smem, st>>>(*g);
+  SARD_LAUNCH_OK(NT ? "umma_gemm_kernel<fwd>" : "umma_gemm_kernel<bwd_data>");
+  return 0;
+}
+
+// returns -1 when the shape is not handled by this engine (caller falls through to the SIMT kernels)
+int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st) {
+  // long reductions stay on the FFMA engine: tensor-core fp32 accumulation truncates, and the bias grows
+  // with the number of accumulated k-steps (measured 5e-5 relative at R = 1410)
+  if (g->N <= 16 || g->R < 8 || g->R > 512) return -1;
+  if (g->N <= 64) return nt ? launch_umma_t<64, true>(g, st) : launch_umma_t<64, false>(g, st);
+  return nt ? launch_umma_t<128, true>(g, st) : launch_umma_t<128, false>(g, st);
+}

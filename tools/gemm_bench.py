@@ -1,0 +1,38 @@
+"""Micro-benchmark of sard_linear_fwd / bwd_data / bwd_weight at the bench workload's shapes, both engines."""
+import ctypes as C, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from sard_b200 import _lib as L
+torch.cuda.set_device(0)
+shapes = [('il1 fwd', 18432, 128, 256, True), ('il2 fwd', 18432, 128, 128, True), ('gconv fwd', 18432, 64, 128, True),
+          ('in_fc fwd', 18432, 64, 72, True), ('mlp1 fwd', 2048, 512, 64, True), ('mlp2 fwd', 2048, 256, 512, True),
+          ('il1 bwd_data', 18432, 256, 128, False), ('gconv bwd_data', 18432, 128, 64, False)]
+iters = int(os.environ.get('ITERS', '30'))
+only = os.environ.get('ONLY')
+for name, M, N, R, nt in shapes:
+    if only and only not in name:
+        continue
+    A = torch.randn(M, R, device='cuda'); W = torch.randn(N, R, device='cuda') / R ** 0.5 if nt else torch.randn(R, N, device='cuda') / R ** 0.5
+    b = torch.randn(N, device='cuda'); Y = torch.zeros(M, N, device='cuda')
+    g = L.SardGemm()
+    g.A, g.lda, g.B0 = L.ptr(A), R, L.ptr(W)
+    if nt:
+        g.ldb0, g.b_split, g.bias, g.act = R, R, L.ptr(b), 2
+    else:
+        g.ldb0, g.b_split, g.dsplit = N, N, N
+    g.Y, g.ldy, g.M, g.N, g.R = L.ptr(Y), N, M, N, R
+    fn = L.lib.sard_linear_fwd if nt else L.lib.sard_linear_bwd_data
+    ref = (torch.tanh(A.double() @ W.double().t() + b.double()) if nt else A.double() @ W.double())
+    for eng in (0, 1):
+        L.lib.sard_set_gemm_engine(eng)
+        for _ in range(3):
+            L.check(fn(C.byref(g), L.stream()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            L.check(fn(C.byref(g), L.stream()))
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        err = float((Y.double() - ref).abs().max())
+        print(f'{name:16s} M={M} N={N} R={R} engine={eng}: {us:7.1f} us  {2*M*N*R/us/1e6:7.2f} TFLOP/s  max|err|={err:.2e}')
