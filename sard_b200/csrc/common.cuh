@@ -68,6 +68,33 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Transcendental epilogues live in out-of-line functions: inlining tanhf/expf/sinf into 32-element
+// unrolled epilogues made every GEMM kernel > 64 KB of SASS, i.e. instruction-cache-miss bound.
+static __device__ __noinline__ float epi_slow(float v, int act, int post) {
+  if (act == SARD_ACT_TANH) v = tanhf(v);
+  else if (act == SARD_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+  else if (act == SARD_ACT_RELU) v = v > 0.f ? v : 0.f;
+  if (post == SARD_POST_SIN_HALF_PI) v = sinpif(0.5f * v);       // sin(pi/2 * v), exact argument reduction
+  return v;
+}
+// forward epilogue after the bias: activation; *pre receives the value before `post`
+__device__ __forceinline__ float epi_forward(float v, int act, int post, float* pre) {
+  if (act <= SARD_ACT_RELU && post == SARD_POST_NONE) {
+    v = (act == SARD_ACT_RELU && v < 0.f) ? 0.f : v;
+    if (pre) *pre = v;
+    return v;
+  }
+  if (pre) {                       // rare (attribute head): keep the pre-sin value
+    const float a = epi_slow(v, act, SARD_POST_NONE);
+    *pre = a;
+    return post == SARD_POST_SIN_HALF_PI ? epi_slow(a, SARD_ACT_NONE, post) : a;
+  }
+  return epi_slow(v, act, post);
+}
+static __device__ __noinline__ float act_grad_slow(float y, int act) {
+  return act == SARD_ACT_TANH ? 1.f - y * y : y * (1.f - y);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
     case SARD_ACT_RELU: return v > 0.f ? v : 0.f;
@@ -78,10 +105,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 // derivative of the activation expressed through its OUTPUT y
 __device__ __forceinline__ float act_grad_from_output(float y, int act) {
-  switch (act) {
-    case SARD_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case SARD_ACT_TANH: return 1.f - y * y;
-    case SARD_ACT_SIGMOID: return y * (1.f - y);
-    default: return 1.f;
-  }
+  if (act == SARD_ACT_NONE) return 1.f;
+  if (act == SARD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  return act == SARD_ACT_TANH ? 1.f - y * y : y * (1.f - y);
 }

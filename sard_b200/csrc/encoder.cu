@@ -1,0 +1,181 @@
+// Fused ObsEncoder chain (design_opt/models/jsmlp.py:7-20 + process_hfield_obj, policy.py:204-213):
+//   e1 = relu(x W1^T + b1),  ext[:, 64k:64k+64] = relu(e1 W2^T + b2)      for the encoders k with a small input
+// and its backward, one launch each instead of 6 + 15 GEMM launches per net and minibatch.  In most SARD
+// envs the hfield / obj / goal inputs are 1..12 wide, so these layers are launch-latency, not FLOP, bound.
+// Encoders with a wide input (hfield 1410 in locomotion_vt / escape) stay on the generic GEMM path.
+#include "common.cuh"
+#include "encoder.cuh"
+
+#define ENC_H 64
+#define ENC_KMAX 32
+#define ENC_ROWS 32
+#define ENC_BROWS 32
+
+__global__ void __launch_bounds__(256) enc_fwd_kernel(const EncFwdP p) {
+  __shared__ float W2s[ENC_H][ENC_H + 1];
+  __shared__ float h1[ENC_ROWS][ENC_H + 1];
+  __shared__ float xs[ENC_ROWS][ENC_KMAX];
+  const int k = p.enc_list[blockIdx.y];
+  const int K = p.K[k];
+  const int r0 = blockIdx.x * ENC_ROWS;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ENC_H * ENC_H; i += 256) W2s[i / ENC_H][i % ENC_H] = __ldg(p.w2[k] + i);
+  for (int i = tid; i < ENC_ROWS * K; i += 256) {
+    const int r = i / K, c = i - r * K;
+    xs[r][c] = (r0 + r < p.B) ? __ldg(p.src[k] + (size_t)p.ids[r0 + r] * K + c) : 0.f;
+  }
+  __syncthreads();
+  {
+    const int j = tid & 63, rg = tid >> 6;                 // 8 rows per thread
+    const float bj = __ldg(p.b1[k] + j);
+    float w[ENC_KMAX];
+#pragma unroll
+    for (int c = 0; c < ENC_KMAX; ++c) w[c] = c < K ? __ldg(p.w1[k] + (size_t)j * K + c) : 0.f;
+#pragma unroll 1
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = rg * 8 + rr;
+      float s = bj;
+#pragma unroll
+      for (int c = 0; c < ENC_KMAX; ++c) s = fmaf(xs[r][c < K ? c : 0], w[c], s);
+      s = s > 0.f ? s : 0.f;
+      h1[r][j] = s;
+      if (r0 + r < p.B) p.e1[k][(size_t)(r0 + r) * ENC_H + j] = s;
+    }
+  }
+  __syncthreads();
+  {
+    const int j = tid & 63, rg = tid >> 6;
+    const float bj = __ldg(p.b2[k] + j);
+    float acc[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) acc[rr] = bj;
+#pragma unroll 4
+    for (int i = 0; i < ENC_H; ++i) {
+      const float wv = W2s[j][i];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) acc[rr] = fmaf(h1[rg * 8 + rr][i], wv, acc[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = r0 + rg * 8 + rr;
+      if (r < p.B) p.ext[(size_t)r * p.ld_ext + k * ENC_H + j] = acc[rr] > 0.f ? acc[rr] : 0.f;
+    }
+  }
+}
+
+// per-chunk partial layout: dW2[64*64] | db2[64] | dW1[64*KMAX] | db1[64]
+#define ENC_PART (ENC_H * ENC_H + ENC_H + ENC_H * ENC_KMAX + ENC_H)
+
+__global__ void __launch_bounds__(256) enc_bwd_kernel(const EncBwdP p) {
+  __shared__ float dz[ENC_BROWS][ENC_H + 1];      // dext tile (relu' already applied by the producer)
+  __shared__ float es[ENC_BROWS][ENC_H + 1];      // e1 tile, later de1
+  __shared__ float W2s[ENC_H][ENC_H + 1];
+  __shared__ float xs[ENC_BROWS][ENC_KMAX];
+  const int k = p.enc_list[blockIdx.y];
+  const int K = p.K[k];
+  const int r0 = blockIdx.x * ENC_BROWS;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ENC_H * ENC_H; i += 256) W2s[i / ENC_H][i % ENC_H] = __ldg(p.w2[k] + i);
+  for (int i = tid; i < ENC_BROWS * ENC_H; i += 256) {
+    const int r = i / ENC_H, c = i % ENC_H;
+    const bool ok = r0 + r < p.B;
+    dz[r][c] = ok ? p.dext[(size_t)(r0 + r) * p.ld_dext + k * ENC_H + c] : 0.f;
+    es[r][c] = ok ? p.e1[k][(size_t)(r0 + r) * ENC_H + c] : 0.f;
+  }
+  for (int i = tid; i < ENC_BROWS * ENC_KMAX; i += 256) {
+    const int r = i / ENC_KMAX, c = i % ENC_KMAX;
+    xs[r][c] = (r0 + r < p.B && c < K) ? __ldg(p.src[k] + (size_t)p.ids[r0 + r] * K + c) : 0.f;
+  }
+  __syncthreads();
+  float* part = p.partials + ((size_t)blockIdx.x * p.n_enc + blockIdx.y) * ENC_PART;
+  const int j = tid & 63, g4 = tid >> 6;
+  {   // dW2[j][i] = sum_r dz[r][j] e1[r][i], i in [16 g4, 16 g4 + 16);  db2[j] = sum_r dz[r][j]
+    float acc[16], bs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < ENC_BROWS; ++r) {
+      const float d = dz[r][j];
+      bs += d;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(d, es[r][g4 * 16 + i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part[j * ENC_H + g4 * 16 + i] = acc[i];
+    if (g4 == 0) part[ENC_H * ENC_H + j] = bs;
+  }
+  __syncthreads();
+  {   // de1[r][i] = relu'(e1[r][i]) * sum_j dz[r][j] W2[j][i]; thread: i = tid&63, rows 8 g4 .. +8
+    const int i = j;
+    float acc[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) acc[rr] = 0.f;
+#pragma unroll 4
+    for (int jj = 0; jj < ENC_H; ++jj) {
+      const float wv = W2s[jj][i];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) acc[rr] = fmaf(dz[g4 * 8 + rr][jj], wv, acc[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = g4 * 8 + rr;
+      es[r][i] = es[r][i] > 0.f ? acc[rr] : 0.f;      // (r, i) is owned by exactly this thread; dW2 pass is behind the barrier above
+    }
+  }
+  __syncthreads();
+  {   // dW1[j][c] = sum_r de1[r][j] x[r][c], c in [8 g4, 8 g4 + 8);  db1[j] = sum_r de1[r][j]
+    float acc[8], bs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < ENC_BROWS; ++r) {
+      const float d = es[r][j];
+      bs += d;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(d, xs[r][g4 * 8 + c], acc[c]);
+    }
+    float* pw1 = part + ENC_H * ENC_H + ENC_H;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pw1[j * ENC_KMAX + g4 * 8 + c] = acc[c];
+    if (g4 == 0) pw1[ENC_H * ENC_KMAX + j] = bs;
+  }
+}
+
+__global__ void enc_bwd_reduce_kernel(const EncBwdP p, int n_chunks) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ENC_PART) return;
+  const int k = p.enc_list[blockIdx.y];
+  const int K = p.K[k];
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += p.partials[((size_t)c * p.n_enc + blockIdx.y) * ENC_PART + e];
+  if (e < ENC_H * ENC_H) p.gw2[k][e] += s;
+  else if (e < ENC_H * ENC_H + ENC_H) p.gb2[k][e - ENC_H * ENC_H] += s;
+  else if (e < ENC_H * ENC_H + ENC_H + ENC_H * ENC_KMAX) {
+    const int q = e - (ENC_H * ENC_H + ENC_H), jj = q / ENC_KMAX, c = q % ENC_KMAX;
+    if (c < K) p.gw1[k][(size_t)jj * K + c] += s;
+  } else p.gb1[k][e - (ENC_H * ENC_H + ENC_H + ENC_H * ENC_KMAX)] += s;
+}
+
+// ---- host entry points used by the schedules (engine.cu) ----
+int sard_enc_fused_ok(int K, int h1, int h2) { return K <= ENC_KMAX && h1 == ENC_H && h2 == ENC_H; }
+long long sard_enc_partials_floats(int B, int n_enc) { return (long long)ceil_div(B, ENC_BROWS) * n_enc * ENC_PART; }
+
+int sard_enc_fwd_launch(const EncFwdP& p, cudaStream_t st) {
+  if (p.n_enc <= 0 || p.B <= 0) return 0;
+  dim3 grid(ceil_div(p.B, ENC_ROWS), p.n_enc);
+  enc_fwd_kernel<<<grid, 256, 0, st>>>(p);
+  SARD_LAUNCH_OK("enc_fwd_kernel");
+  return 0;
+}
+
+int sard_enc_bwd_launch(const EncBwdP& p, cudaStream_t st) {
+  if (p.n_enc <= 0 || p.B <= 0) return 0;
+  const int n_chunks = ceil_div(p.B, ENC_BROWS);
+  dim3 grid(n_chunks, p.n_enc);
+  enc_bwd_kernel<<<grid, 256, 0, st>>>(p);
+  SARD_LAUNCH_OK("enc_bwd_kernel");
+  dim3 rgrid(ceil_div(ENC_PART, 256), p.n_enc);
+  enc_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(p, n_chunks);
+  SARD_LAUNCH_OK("enc_bwd_reduce_kernel");
+  return 0;
+}

@@ -7,6 +7,7 @@
 // All buffers come from a caller-provided workspace carved deterministically (bump allocation), so
 // the GATHER and COMPUTE phases of a data-parallel step can be separate calls.
 #include "common.cuh"
+#include "encoder.cuh"
 #include <string.h>
 
 thread_local char g_sard_err[1024] = "";
@@ -167,7 +168,20 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
 int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena* arena, const SardSel* sel,
                      float* const e1[3], float* ext, int ld_ext, sard_stream_t st) {
   site(K_ENC, 0);
+  EncFwdP fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.ids = sel->ids; fp.B = sel->B; fp.ext = ext; fp.ld_ext = ld_ext;
   for (int k = 0; k < 3; ++k) {
+    SARD_REQUIRE(enc[k][0].in == arena->ext_dim[k], "encoder input dim != arena ext dim");
+    if (sard_enc_fused_ok(enc[k][0].in, enc[k][0].out, enc[k][1].out)) {
+      fp.src[k] = arena->ext[k]; fp.K[k] = enc[k][0].in; fp.w1[k] = P + enc[k][0].w; fp.b1[k] = P + enc[k][0].b;
+      fp.w2[k] = P + enc[k][1].w; fp.b2[k] = P + enc[k][1].b; fp.e1[k] = e1[k];
+      fp.enc_list[fp.n_enc++] = k;
+    }
+  }
+  SARD_TRY(sard_enc_fwd_launch(fp, as_stream(st)));
+  for (int k = 0; k < 3; ++k) {
+    if (sard_enc_fused_ok(enc[k][0].in, enc[k][0].out, enc[k][1].out)) continue;
     SardGemm g = gemm0();
     g.A = arena->ext[k]; g.lda = arena->ext_dim[k]; g.a_rows = sel->ids;
     g.B0 = P + enc[k][0].w; g.ldb0 = enc[k][0].in; g.b_split = enc[k][0].in; g.bias = P + enc[k][0].b;
@@ -187,7 +201,19 @@ int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena*
 int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const SardArena* arena, const SardSel* sel,
                       float* const e1[3], const float* dext, int ld_dext, float* de1, float* wg_scratch,
                       sard_stream_t st) {
+  site(K_ENC, 2);
+  EncBwdP bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.ids = sel->ids; bp.B = sel->B; bp.dext = dext; bp.ld_dext = ld_dext; bp.partials = wg_scratch;
   for (int k = 0; k < 3; ++k) {
+    if (!sard_enc_fused_ok(enc[k][0].in, enc[k][0].out, enc[k][1].out)) continue;
+    bp.src[k] = arena->ext[k]; bp.K[k] = enc[k][0].in; bp.w2[k] = P + enc[k][1].w; bp.e1[k] = e1[k];
+    bp.gw1[k] = G + enc[k][0].w; bp.gb1[k] = G + enc[k][0].b; bp.gw2[k] = G + enc[k][1].w; bp.gb2[k] = G + enc[k][1].b;
+    bp.enc_list[bp.n_enc++] = k;
+  }
+  SARD_TRY(sard_enc_bwd_launch(bp, as_stream(st)));
+  for (int k = 0; k < 3; ++k) {
+    if (sard_enc_fused_ok(enc[k][0].in, enc[k][0].out, enc[k][1].out)) continue;
     const float* dz2 = dext + k * SARD_EXT_DIM;
     SardWGrad w = wgrad0();
     w.P = dz2; w.ldp = ld_dext; w.Q = e1[k]; w.ldq = enc[k][0].out; w.M = sel->B; w.N1 = enc[k][1].out; w.N2 = enc[k][1].in;
@@ -211,7 +237,7 @@ int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const
 }
 
 long long enc_wg_need(const SardDense enc[3][2], int B) {
-  long long need = 0;
+  long long need = sard_enc_partials_floats(B, 3);
   for (int k = 0; k < 3; ++k)
     for (int j = 0; j < 2; ++j) {
       long long v = wg_partials(B, enc[k][j].out, enc[k][j].in, WG_CHUNK);

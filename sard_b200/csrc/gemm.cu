@@ -12,6 +12,21 @@
 // for the tcgen05 3xTF32 plan.
 #include "common.cuh"
 
+// Shared epilogue of both engines, executed from a ROLLED loop over a tile staged in shared memory:
+// one copy of the bias / activation / sin / act' / scatter code per kernel (keeps the SASS small enough
+// for the instruction cache: the first version unrolled it 32x and every GEMM kernel exceeded 50 KB)
+// and coalesced global stores (consecutive threads -> consecutive output columns).
+template <bool NT>
+__device__ __forceinline__ void gemm_epilogue_store(const SardGemm& g, float v, long long yrow, int gc, const float* bias) {
+  if (NT) {
+    if (bias) v += __ldg(bias + gc);
+    v = epi_forward(v, g.act, g.post, g.Ypre ? g.Ypre + yrow * g.ldy + gc : nullptr);
+  } else if (g.Dact) {
+    v *= act_grad_from_output(g.Dact[yrow * g.ldd + gc], gc < g.dsplit ? g.dact0 : g.dact1);
+  }
+  g.Y[yrow * g.ldy + gc] = v;
+}
+
 template <int BM, int BN, int BK, int TM, int TN, bool NT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_kernel(const SardGemm g) {
@@ -19,9 +34,13 @@ gemm_kernel(const SardGemm g) {
   constexpr int EA = BM * BK / NTH;
   constexpr int EB = BN * BK / NTH;
   static_assert(BM * BK % NTH == 0 && BN * BK % NTH == 0, "tile/thread mismatch");
-  static_assert(TM % 4 == 0 || TM == 4, "TM");
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  static_assert(TM % 4 == 0, "TM");
+  constexpr int AS = BK * (BM + 4), BS = BK * (BN + 4);          // floats per buffer
+  constexpr int TILE_FLOATS = 2 * (AS + BS);
+  constexpr int C_FLOATS = BM * (BN + 1);
+  __shared__ __align__(16) float smem[TILE_FLOATS > C_FLOATS ? TILE_FLOATS : C_FLOATS];
+  float* As = smem;                 // [2][BK][BM+4]
+  float* Bs = smem + 2 * AS;        // [2][BK][BN+4]
 
   int row_start, row_end, group = 0;
   if (g.tiles) {
@@ -42,48 +61,9 @@ gemm_kernel(const SardGemm g) {
   long long a_off[EA];
 #pragma unroll
   for (int i = 0; i < EA; ++i) {
-    const int m = (tid + i * NTH) / BK;
-    const int grow = row_start + m;
-    if (grow < row_end) a_off[i] = (long long)(g.a_rows ? g.a_rows[grow] : grow) * g.lda;
-    else a_off[i] = -1;
+    const int grow = row_start + (tid + i * NTH) / BK;
+    a_off[i] = grow < row_end ? (long long)(g.a_rows ? g.a_rows[grow] : grow) * g.lda : -1;
   }
-
-  float ra[EA], rb[EB];
-  auto load_tile = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < EA; ++i) {
-      const int r = (tid + i * NTH) % BK;
-      const int kk = k0 + r;
-      ra[i] = (a_off[i] >= 0 && kk < g.R) ? __ldg(g.A + a_off[i] + kk) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < EB; ++i) {
-      const int idx = tid + i * NTH;
-      int r, c;
-      if (NT) { r = idx % BK; c = idx / BK; } else { c = idx % BN; r = idx / BN; }
-      const int kk = k0 + r, gc = n0 + c;
-      float v = 0.f;
-      if (kk < g.R && gc < g.N) {
-        if (NT) v = kk < g.b_split ? __ldg(B0 + (size_t)gc * g.ldb0 + kk) : __ldg(B1 + (size_t)gc * g.ldb1 + (kk - g.b_split));
-        else    v = gc < g.b_split ? __ldg(B0 + (size_t)kk * g.ldb0 + gc) : __ldg(B1 + (size_t)kk * g.ldb1 + (gc - g.b_split));
-      }
-      rb[i] = v;
-    }
-  };
-  auto store_tile = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < EA; ++i) {
-      const int idx = tid + i * NTH;
-      As[buf][idx % BK][idx / BK] = ra[i];
-    }
-#pragma unroll
-    for (int i = 0; i < EB; ++i) {
-      const int idx = tid + i * NTH;
-      if (NT) Bs[buf][idx % BK][idx / BK] = rb[i];
-      else    Bs[buf][idx / BN][idx % BN] = rb[i];
-    }
-  };
-
   const int ty = tid / (BN / TN), tx = tid % (BN / TN);
   float acc[TM][TN];
 #pragma unroll
@@ -91,64 +71,94 @@ gemm_kernel(const SardGemm g) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  float ra[EA], rb[EB];
   const int nkb = (g.R + BK - 1) / BK;
   int buf = 0;
-  load_tile(0);
-  store_tile(0);
-  __syncthreads();
-  for (int kb = 0; kb < nkb; ++kb) {
-    if (kb + 1 < nkb) load_tile((kb + 1) * BK);
+  // software pipeline with a single call site for load / compute / store: iteration kb loads tile kb into
+  // registers, computes tile kb-1 from smem[buf^1], then stores tile kb into smem[buf]
+#pragma unroll 1
+  for (int kb = 0; kb <= nkb; ++kb) {
+    if (kb < nkb) {
+      const int k0 = kb * BK;
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
-        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      for (int i = 0; i < EA; ++i) {
+        const int kk = k0 + (tid + i * NTH) % BK;
+        ra[i] = (a_off[i] >= 0 && kk < g.R) ? __ldg(g.A + a_off[i] + kk) : 0.f;
       }
-      if constexpr (TN % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < TN; j += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + j]);
-          b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+      for (int i = 0; i < EB; ++i) {
+        const int idx = tid + i * NTH;
+        const int r = NT ? idx % BK : idx / BN, c = NT ? idx / BK : idx % BN;
+        const int kk = k0 + r, gc = n0 + c;
+        float v = 0.f;
+        if (kk < g.R && gc < g.N) {
+          if (NT) v = kk < g.b_split ? __ldg(B0 + (size_t)gc * g.ldb0 + kk) : __ldg(B1 + (size_t)gc * g.ldb1 + (kk - g.b_split));
+          else    v = gc < g.b_split ? __ldg(B0 + (size_t)kk * g.ldb0 + gc) : __ldg(B1 + (size_t)kk * g.ldb1 + (gc - g.b_split));
         }
-      } else {
+        rb[i] = v;
+      }
+    }
+    if (kb > 0) {
+      const float* Ac = As + (buf ^ 1) * AS + ty * TM;
+      const float* Bc = Bs + (buf ^ 1) * BS + tx * TN;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = Bs[buf][k][tx * TN + j];
+      for (int k = 0; k < BK; ++k) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int i = 0; i < TM; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Ac + k * (BM + 4) + i);
+          a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+        }
+        if constexpr (TN % 4 == 0) {
+#pragma unroll
+          for (int j = 0; j < TN; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(Bc + k * (BN + 4) + j);
+            b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) b[j] = Bc[k * (BN + 4) + j];
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    if (kb < nkb) {
+#pragma unroll
+      for (int i = 0; i < EA; ++i) {
+        const int idx = tid + i * NTH;
+        As[buf * AS + (idx % BK) * (BM + 4) + idx / BK] = ra[i];
       }
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < EB; ++i) {
+        const int idx = tid + i * NTH;
+        if (NT) Bs[buf * BS + (idx % BK) * (BN + 4) + idx / BK] = rb[i];
+        else    Bs[buf * BS + (idx / BN) * (BN + 4) + idx % BN] = rb[i];
+      }
     }
-    if (kb + 1 < nkb) store_tile(buf ^ 1);
     __syncthreads();
     buf ^= 1;
   }
 
-  // epilogue
+  // stage the accumulators in shared memory (the operand tiles are dead), then a rolled, coalesced epilogue
+  float* Cs = smem;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) Cs[(ty * TM + i) * (BN + 1) + tx * TN + j] = acc[i][j];
+  __syncthreads();
   const float* bias = g.bias ? g.bias + (size_t)group * g.bias_group_stride : nullptr;
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int grow = row_start + ty * TM + i;
-    if (grow >= row_end) continue;
+  const int rows = row_end - row_start;
+#pragma unroll 1
+  for (int idx = tid; idx < rows * BN; idx += NTH) {
+    const int m = idx / BN, c = idx % BN;
+    const int gc = n0 + c;
+    if (gc >= g.N) continue;
+    const int grow = row_start + m;
     const long long yrow = g.y_rows ? g.y_rows[grow] : grow;
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int gc = n0 + tx * TN + j;
-      if (gc >= g.N) continue;
-      float v = acc[i][j];
-      if (NT) {
-        if (bias) v += __ldg(bias + gc);
-        v = act_apply(v, g.act);
-        if (g.Ypre) g.Ypre[yrow * g.ldy + gc] = v;
-        if (g.post == SARD_POST_SIN_HALF_PI) v = sinf(v * 1.57079632679489662f);
-      } else if (g.Dact) {
-        const float y = g.Dact[yrow * g.ldd + gc];
-        v *= act_grad_from_output(y, gc < g.dsplit ? g.dact0 : g.dact1);
-      }
-      g.Y[yrow * g.ldy + gc] = v;
-    }
+    gemm_epilogue_store<NT>(g, Cs[m * (BN + 1) + c], yrow, gc, bias);
   }
 }
 
@@ -166,7 +176,7 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   const double groups = g->b_group_stride ? 13.0 : 1.0;   // weight slabs touched (live indices, nominal)
   ProfScope prof(st, 2.0 * g->M * (double)g->N * g->R,
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
-  if (g_sard_gemm_engine == 1) {
+  if (g_sard_gemm_engine >= 1) {
     const int r = sard_umma_gemm(g, NT, st);
     if (r >= 0) return r;
   }
@@ -296,10 +306,15 @@ wgrad_kernel(const SardWGrad w) {
   }
 }
 
-__global__ void wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
+// Ordered reduction of the per-chunk partial products.  A block owns 32 consecutive output elements;
+// its 8 warps each sum every 8th chunk (8 independent load streams instead of one serial chain), then
+// the 8 slice sums are added in slice order -> deterministic, ~8x shorter latency chain.
+#define WR_SLICES 8
+__global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
+  __shared__ float part[WR_SLICES][33];
   const int ldpart = w.N2 + 1;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= w.N1 * ldpart) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int total = w.N1 * ldpart;
   int k0, k1, slot = 0;
   if (w.grp_chunk_ptr) {
     const int u = blockIdx.y;
@@ -310,15 +325,36 @@ __global__ void wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
   } else {
     k0 = 0; k1 = nchunks_plain;
   }
-  float s = 0.f;
-  for (int k = k0; k < k1; ++k) s += w.partials[(size_t)k * w.N1 * ldpart + e];
-  const int c1 = e / ldpart, c2 = e - c1 * ldpart;
-  if (c2 == w.N2) {
-    if (w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
-  } else if (c2 < w.w_split) {
-    w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c2] += s;
-  } else {
-    w.dW1[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw1 + (c2 - w.w_split)] += s;
+  // grid-stride over 32-element blocks (grouped launches keep the grid small: most groups are empty)
+  for (int eb = blockIdx.x; eb * 32 < total; eb += gridDim.x) {
+    const int e = eb * 32 + lane;
+    float s = 0.f;
+    if (e < total) {
+      const float* p = w.partials + (size_t)e;
+      const size_t stride = (size_t)w.N1 * ldpart;
+      int k = k0 + slice;
+      for (; k + 3 * WR_SLICES < k1; k += 4 * WR_SLICES) {
+        const float a0 = p[(size_t)k * stride], a1 = p[(size_t)(k + WR_SLICES) * stride];
+        const float a2 = p[(size_t)(k + 2 * WR_SLICES) * stride], a3 = p[(size_t)(k + 3 * WR_SLICES) * stride];
+        s += a0; s += a1; s += a2; s += a3;
+      }
+      for (; k < k1; k += WR_SLICES) s += p[(size_t)k * stride];
+    }
+    __syncthreads();                    // previous iteration's readers of `part` are done
+    part[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && e < total) {
+#pragma unroll
+      for (int j = 1; j < WR_SLICES; ++j) s += part[j][lane];
+      const int c1 = e / ldpart, c2 = e - c1 * ldpart;
+      if (c2 == w.N2) {
+        if (w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
+      } else if (c2 < w.w_split) {
+        w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c2] += s;
+      } else {
+        w.dW1[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw1 + (c2 - w.w_split)] += s;
+      }
+    }
   }
 }
 
@@ -361,8 +397,10 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
     wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
   }
   SARD_LAUNCH_OK("wgrad_kernel");
-  dim3 rgrid(ceil_div((long long)w->N1 * (w->N2 + 1), 256), w->grp_chunk_ptr ? w->n_groups : 1);
-  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(*w, w->chunks ? 0 : nchunks);
+  int rblocks = ceil_div((long long)w->N1 * (w->N2 + 1), 32);
+  if (w->grp_chunk_ptr && rblocks > 64) rblocks = 64;
+  dim3 rgrid(rblocks, w->grp_chunk_ptr ? w->n_groups : 1);
+  wgrad_reduce_kernel<<<rgrid, 32 * WR_SLICES, 0, st>>>(*w, w->chunks ? 0 : nchunks);
   SARD_LAUNCH_OK("wgrad_reduce_kernel");
   return 0;
 }

@@ -80,27 +80,38 @@ extern "C" int sard_concat_sorted(const float* h, int ld_h, int Fh, const float*
   return 0;
 }
 
-// one warp per graph: per-node rows go back to unsorted order, the ext part is summed over the
-// graph's nodes in node order (deterministic segment sum)
+// (Fh+Fe)/4 threads per graph, one float4 column each: per-node rows go back to unsorted order, the ext
+// part is summed over the graph's nodes in node order (deterministic segment sum)
 __global__ void unsort_grad_kernel(const float* __restrict__ dxs, int ld_dxs, const int* __restrict__ spos,
                                    const int* __restrict__ cum, int node_base, int B,
                                    const float* __restrict__ h, int ld_h, int Fh, int h_act,
                                    float* __restrict__ dh, int ld_dh,
                                    const float* __restrict__ ext, int ld_ext, int Fe,
                                    float* __restrict__ dext, int ld_dext) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int W4 = (Fh + Fe) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(idx / W4), c = (int)(idx - (long long)g * W4) * 4;
   if (g >= B) return;
   const int r0 = cum[g] - node_base, r1 = cum[g + 1] - node_base;
-  for (int c = lane; c < Fh; c += 32) {
+  if (c < Fh) {
     for (int r = r0; r < r1; ++r) {
-      const float v = dxs[(size_t)__ldg(spos + r) * ld_dxs + c];
-      dh[(size_t)r * ld_dh + c] = v * act_grad_from_output(h[(size_t)r * ld_h + c], h_act);
+      float4 v = *reinterpret_cast<const float4*>(dxs + (size_t)__ldg(spos + r) * ld_dxs + c);
+      const float4 y = *reinterpret_cast<const float4*>(h + (size_t)r * ld_h + c);
+      v.x *= act_grad_from_output(y.x, h_act); v.y *= act_grad_from_output(y.y, h_act);
+      v.z *= act_grad_from_output(y.z, h_act); v.w *= act_grad_from_output(y.w, h_act);
+      *reinterpret_cast<float4*>(dh + (size_t)r * ld_dh + c) = v;
     }
-  }
-  for (int c = lane; c < Fe; c += 32) {
-    float acc = 0.f;
-    for (int r = r0; r < r1; ++r) acc += dxs[(size_t)__ldg(spos + r) * ld_dxs + Fh + c];
-    dext[(size_t)g * ld_dext + c] = ext[(size_t)g * ld_ext + c] > 0.f ? acc : 0.f;
+  } else {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(dxs + (size_t)__ldg(spos + r) * ld_dxs + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int ce = c - Fh;
+    const float4 e = *reinterpret_cast<const float4*>(ext + (size_t)g * ld_ext + ce);
+    acc.x = e.x > 0.f ? acc.x : 0.f; acc.y = e.y > 0.f ? acc.y : 0.f;
+    acc.z = e.z > 0.f ? acc.z : 0.f; acc.w = e.w > 0.f ? acc.w : 0.f;
+    *reinterpret_cast<float4*>(dext + (size_t)g * ld_dext + ce) = acc;
   }
 }
 
@@ -109,7 +120,9 @@ extern "C" int sard_unsort_grad(const float* dxs, int ld_dxs, const int* spos, c
                                 const float* ext, int ld_ext, int Fe, float* dext, int ld_dext,
                                 sard_stream_t stream) {
   if (B <= 0) return 0;
-  unsort_grad_kernel<<<ceil_div((long long)B * 32, 256), 256, 0, as_stream(stream)>>>(
+  SARD_REQUIRE(Fh % 4 == 0 && Fe % 4 == 0 && ld_dxs % 4 == 0 && ld_h % 4 == 0 && ld_dh % 4 == 0 && ld_ext % 4 == 0 && ld_dext % 4 == 0,
+               "unsort_grad: widths / strides must be multiples of 4");
+  unsort_grad_kernel<<<ceil_div((long long)B * ((Fh + Fe) / 4), 256), 256, 0, as_stream(stream)>>>(
       dxs, ld_dxs, spos, cum, node_base, B, h, ld_h, Fh, h_act, dh, ld_dh, ext, ld_ext, Fe, dext, ld_dext);
   SARD_LAUNCH_OK("unsort_grad_kernel");
   return 0;

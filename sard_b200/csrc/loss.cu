@@ -92,7 +92,7 @@ __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
       } else {
         dmu = coef * (__ldg(a.actions + (size_t)an * SARD_ACTION_DIM + a.act_col + c) - mu) * ivar[c];
       }
-      if (a.pre) dmu *= 1.57079632679489662f * cosf(1.57079632679489662f * a.pre[(size_t)row * a.ld_out + c]);
+      if (a.pre) dmu *= 1.57079632679489662f * cospif(0.5f * a.pre[(size_t)row * a.ld_out + c]);
       a.dout[(size_t)row * a.ld_dout + c] = dmu;
     }
   }

@@ -8,22 +8,53 @@
 
 #define NORM_CHUNK 128
 
+// one block per 128-row chunk; threadIdx.y splits the chunk into 4 sub-chunks of 32 rows that are merged in
+// sub-chunk order (pairwise formula), so the partial layout stays one {mean, M2} pair per chunk and column
+#define NORM_SUB 4
 __global__ void norm_moments_kernel(const float* __restrict__ x, int ldx, int n, int D,
                                     float* __restrict__ partials) {
+  extern __shared__ float sm[];                    // [NORM_SUB][3][blockDim.x]  (count, mean, M2)
   const int chunk = blockIdx.x;
-  const int r0 = chunk * NORM_CHUNK, r1 = min(n, r0 + NORM_CHUNK);
-  const float cnt = (float)(r1 - r0);
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    const float shift = x[(size_t)r0 * ldx + c];
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const float d = x[(size_t)r * ldx + c] - shift;
-      s1 += d;
-      s2 = fmaf(d, d, s2);
+  const int sub = threadIdx.y;
+  const int rows_per_sub = NORM_CHUNK / NORM_SUB;
+  const int r0 = min(n, chunk * NORM_CHUNK + sub * rows_per_sub), r1 = min(n, r0 + rows_per_sub);
+  const int W = blockDim.x;
+  for (int c0 = 0; c0 < D; c0 += W) {
+    const int c = c0 + threadIdx.x;
+    float cnt = (float)(r1 - r0), mean = 0.f, m2 = 0.f;
+    if (c < D && r1 > r0) {
+      const float shift = x[(size_t)r0 * ldx + c];
+      float s1 = 0.f, s2 = 0.f;
+      for (int r = r0; r < r1; ++r) {
+        const float d = x[(size_t)r * ldx + c] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+      const float m = s1 / cnt;
+      mean = shift + m;
+      m2 = fmaxf(s2 - s1 * m, 0.f);
     }
-    const float m = s1 / cnt;
-    partials[((size_t)chunk * 2 + 0) * D + c] = shift + m;
-    partials[((size_t)chunk * 2 + 1) * D + c] = fmaxf(s2 - s1 * m, 0.f);
+    sm[(sub * 3 + 0) * W + threadIdx.x] = cnt;
+    sm[(sub * 3 + 1) * W + threadIdx.x] = mean;
+    sm[(sub * 3 + 2) * W + threadIdx.x] = m2;
+    __syncthreads();
+    if (sub == 0 && c < D) {
+      float na = sm[0 * W + threadIdx.x], ma = sm[1 * W + threadIdx.x], qa = sm[2 * W + threadIdx.x];
+#pragma unroll
+      for (int j = 1; j < NORM_SUB; ++j) {
+        const float nb = sm[(j * 3 + 0) * W + threadIdx.x];
+        if (nb > 0.f) {
+          const float mb = sm[(j * 3 + 1) * W + threadIdx.x], qb = sm[(j * 3 + 2) * W + threadIdx.x];
+          const float nn = na + nb, d = mb - ma;
+          ma = ma + d * (nb / nn);
+          qa = qa + qb + d * d * (na * nb / nn);
+          na = nn;
+        }
+      }
+      partials[((size_t)chunk * 2 + 0) * D + c] = ma;
+      partials[((size_t)chunk * 2 + 1) * D + c] = qa;
+    }
+    __syncthreads();
   }
 }
 
@@ -76,7 +107,8 @@ extern "C" int sard_norm_moments(const float* x, int ldx, int n, int D, float* p
   if (n > 0) {
     int threads = ((D + 31) / 32) * 32;
     if (threads > 256) threads = 256;
-    norm_moments_kernel<<<nchunks, threads, 0, st>>>(x, ldx, n, D, partials);
+    dim3 block(threads, NORM_SUB);
+    norm_moments_kernel<<<nchunks, block, NORM_SUB * 3 * threads * sizeof(float), st>>>(x, ldx, n, D, partials);
     SARD_LAUNCH_OK("norm_moments_kernel");
   }
   norm_merge_chunks_kernel<<<ceil_div((long long)D * 32, 256), 256, 0, st>>>(partials, n, D, nchunks, record);

@@ -147,34 +147,45 @@ __global__ void sort_hist_kernel(const int* __restrict__ body, int n, int max_in
   for (int u = threadIdx.x; u < max_index; u += blockDim.x) blockhist[(size_t)blockIdx.x * max_index + u] = hist[u];
 }
 
-__global__ void sort_scan_kernel(int nb, int n, int max_index, int tile_rows, int chunk_rows,
+// one block of 1024 threads, thread u owns body index u: per-index totals, then block-wide exclusive
+// scans give the row / tile / chunk offsets and every thread writes its own tile and chunk entries
+__global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_index, int tile_rows, int chunk_rows,
                                  int* __restrict__ blockhist, int* __restrict__ cnt, int* __restrict__ grp_ptr,
                                  int4* __restrict__ tiles, int4* __restrict__ chunks, int* __restrict__ grp_chunk_ptr,
                                  int* __restrict__ counts) {
-  for (int u = threadIdx.x; u < max_index; u += blockDim.x) {
-    int total = 0;
+  __shared__ int sc[3][1024];
+  const int u = threadIdx.x;
+  int total = 0;
+  if (u < max_index) {
     for (int b = 0; b < nb; ++b) {
-      int t = blockhist[(size_t)b * max_index + u];
+      const int t = blockhist[(size_t)b * max_index + u];
       blockhist[(size_t)b * max_index + u] = total;
       total += t;
     }
     cnt[u] = total;
   }
+  const int my_t = (total + tile_rows - 1) / tile_rows, my_c = (total + chunk_rows - 1) / chunk_rows;
+  sc[0][u] = total; sc[1][u] = my_t; sc[2][u] = my_c;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0, nt = 0, nc = 0;
-    for (int u = 0; u < max_index; ++u) {
-      const int c = cnt[u];
-      grp_ptr[u] = run;
-      grp_chunk_ptr[u] = nc;
-      for (int s = 0; s < c; s += tile_rows) tiles[nt++] = make_int4(run + s, run + min(s + tile_rows, c), u, 0);
-      for (int s = 0; s < c; s += chunk_rows) chunks[nc++] = make_int4(run + s, run + min(s + chunk_rows, c), u, 0);
-      run += c;
+  for (int o = 1; o < 1024; o <<= 1) {          // inclusive Hillis-Steele scan of the three counters
+    int v0 = 0, v1 = 0, v2 = 0;
+    if (u >= o) { v0 = sc[0][u - o]; v1 = sc[1][u - o]; v2 = sc[2][u - o]; }
+    __syncthreads();
+    sc[0][u] += v0; sc[1][u] += v1; sc[2][u] += v2;
+    __syncthreads();
+  }
+  if (u < max_index) {
+    const int run = sc[0][u] - total, t0 = sc[1][u] - my_t, c0 = sc[2][u] - my_c;
+    grp_ptr[u] = run;
+    grp_chunk_ptr[u] = c0;
+    for (int k = 0; k < my_t; ++k) tiles[t0 + k] = make_int4(run + k * tile_rows, run + min((k + 1) * tile_rows, total), u, 0);
+    for (int k = 0; k < my_c; ++k) chunks[c0 + k] = make_int4(run + k * chunk_rows, run + min((k + 1) * chunk_rows, total), u, 0);
+    if (u == max_index - 1) {
+      grp_ptr[max_index] = sc[0][u];
+      grp_chunk_ptr[max_index] = sc[2][u];
+      counts[0] = sc[1][u];
+      counts[1] = sc[2][u];
     }
-    grp_ptr[max_index] = run;
-    grp_chunk_ptr[max_index] = nc;
-    counts[0] = nt;
-    counts[1] = nc;
   }
 }
 
@@ -205,7 +216,7 @@ __global__ void sort_scatter_kernel(const int* __restrict__ body, int n, int max
 extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int tile_rows, int chunk_rows,
                                   int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
                                   int* counts, int* scratch, sard_stream_t stream) {
-  SARD_REQUIRE(max_index > 0 && max_index <= 4096, "max_index");
+  SARD_REQUIRE(max_index > 0 && max_index <= 1024, "max_index");
   SARD_REQUIRE(tile_rows > 0 && chunk_rows > 0, "tile/chunk rows");
   cudaStream_t st = as_stream(stream);
   SARD_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
@@ -216,7 +227,7 @@ extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int til
     sort_hist_kernel<<<nb, SORT_BLOCK, max_index * sizeof(int), st>>>(body, n, max_index, blockhist, counts);
     SARD_LAUNCH_OK("sort_hist_kernel");
   }
-  sort_scan_kernel<<<1, 256, 0, st>>>(nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
+  sort_scan_kernel<<<1, 1024, 0, st>>>(nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
                                       reinterpret_cast<int4*>(tiles), reinterpret_cast<int4*>(chunks),
                                       grp_chunk_ptr, counts);
   SARD_LAUNCH_OK("sort_scan_kernel");

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from sard_b200 import _lib as L
 torch.cuda.set_device(0)
-shapes = [('il1 fwd', 18432, 128, 256, True), ('il2 fwd', 18432, 128, 128, True), ('gconv fwd', 18432, 64, 128, True),
+shapes = [('x tiny', 128, 64, 8, True), ('x onetile', 128, 128, 256, True), ('x 18k r8', 18432, 128, 8, True), ('x 18k n64 r8', 18432, 64, 8, True), ('x 2k n128 r64', 2048, 128, 64, True),
+          ('il1 fwd', 18432, 128, 256, True), ('il2 fwd', 18432, 128, 128, True), ('gconv fwd', 18432, 64, 128, True),
           ('in_fc fwd', 18432, 64, 72, True), ('mlp1 fwd', 2048, 512, 64, True), ('mlp2 fwd', 2048, 256, 512, True),
           ('il1 bwd_data', 18432, 256, 128, False), ('gconv bwd_data', 18432, 128, 64, False)]
 iters = int(os.environ.get('ITERS', '30'))
@@ -23,7 +24,7 @@ for name, M, N, R, nt in shapes:
     g.Y, g.ldy, g.M, g.N, g.R = L.ptr(Y), N, M, N, R
     fn = L.lib.sard_linear_fwd if nt else L.lib.sard_linear_bwd_data
     ref = (torch.tanh(A.double() @ W.double().t() + b.double()) if nt else A.double() @ W.double())
-    for eng in (0, 1):
+    for eng in [int(e) for e in os.environ.get('ENGINES', '0,1,2').split(',')]:
         L.lib.sard_set_gemm_engine(eng)
         for _ in range(3):
             L.check(fn(C.byref(g), L.stream()))
