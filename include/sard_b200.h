@@ -348,6 +348,7 @@ typedef struct {                       /* one stage of Transform2ActPolicy (tran
   long long log_std;                   /* offset in flat params, -1 for the categorical stage */
   int tie_c0, tie_c1;
   int max_index;
+  int n_live;                          /* number of body indices with a slot (bounds the grouped tile / chunk grids) */
   const int* slot_of_index;            /* [max_index] compact gradient slot per body index */
   float* GT;                           /* compact table gradients of this stage */
 } SardPolicyStage;

@@ -91,7 +91,7 @@ class SardPolicyStage(C.Structure):
     _fields_ = [('stage', ci), ('tower', SardTower), ('lead', ci), ('tail', ci),
                 ('n_il', ci), ('il', SardIndexLinear * MAX_IL), ('il_act', ci),
                 ('out_dim', ci), ('post', ci), ('log_std', cll), ('tie_c0', ci), ('tie_c1', ci),
-                ('max_index', ci), ('slot_of_index', vp), ('GT', vp)]
+                ('max_index', ci), ('n_live', ci), ('slot_of_index', vp), ('GT', vp)]
 
 
 class SardPolicyNet(C.Structure):

@@ -19,6 +19,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HOSTPACK = os.path.join(HERE, '_hostpack.so')
+
+
+def build_hostpack() -> str:
+    """Native host packer (CPython extension, no CUDA): g++ only."""
+    import sysconfig
+    inc = sysconfig.get_paths()['include']
+    subprocess.check_call(['g++', '-O3', '-std=c++17', '-shared', '-fPIC', '-pthread', f'-I{inc}',
+                           os.path.join(CSRC, 'hostpack.cpp'), '-o', HOSTPACK])
+    return HOSTPACK
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -38,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{out}')
     subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    build_hostpack()
     with open(os.path.join(HERE, 'build', 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
     if verbose:

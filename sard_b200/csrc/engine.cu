@@ -408,8 +408,10 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
   sb.rec = reinterpret_cast<double*>(b.f(2 * (1 + 2 * s.tower.D) + 2));
   for (int k = 0; k < 3; ++k) sb.e1[k] = b.f((long long)B * net.enc[k][0].out);
   sb.ext = b.f((long long)B * 3 * SARD_EXT_DIM);
-  sb.max_tiles = ceil_div(n, IL_TILE) + s.max_index;
-  sb.max_chunks = ceil_div(n, WG_CHUNK) + s.max_index;
+  // every present body index adds at most one partial tile / chunk
+  const int live = s.n_live > 0 && s.n_live < s.max_index ? s.n_live : s.max_index;
+  sb.max_tiles = n / IL_TILE + live;
+  sb.max_chunks = n / WG_CHUNK + live;
   sb.srow = b.i(n); sb.spos = b.i(n); sb.grp_ptr = b.i(s.max_index + 1);
   sb.tiles = b.i(4LL * sb.max_tiles); sb.chunks = b.i(4LL * sb.max_chunks);
   sb.grp_chunk_ptr = b.i(s.max_index + 1); sb.counts = b.i(4);

@@ -163,6 +163,7 @@ gemm_kernel(const SardGemm g) {
 }
 
 int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st);   // umma.cu; -1 = shape not handled
+int sard_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st);
 int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
 extern "C" int sard_set_gemm_engine(int engine) { g_sard_gemm_engine = engine; return 0; }
 extern "C" int sard_get_gemm_engine(void) { return g_sard_gemm_engine; }
@@ -389,14 +390,21 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
   const double wgroups = w->grp_chunk_ptr ? 13.0 : 1.0;
   ProfScope prof(st, 2.0 * w->M * (double)w->N1 * w->N2,
                  4.0 * ((double)w->M * w->N1 + (double)w->M * w->N2 + wgroups * (double)w->N1 * w->N2));
-  if (w->N1 <= 16) {
+  int umma_rc = -1;
+  if (g_sard_gemm_engine >= 1) {
+    umma_rc = sard_umma_wgrad(w, nchunks, st);
+    if (umma_rc > 0) return umma_rc;
+  }
+  if (umma_rc == 0) {
+    // partial products done on the tensor cores
+  } else if (w->N1 <= 16) {
     dim3 grid(nchunks, 1, ceil_div(w->N2, 64));
     wgrad_kernel<16, 64, 16, 4, 4><<<grid, 64, 0, st>>>(*w);
   } else {
     dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
     wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
   }
-  SARD_LAUNCH_OK("wgrad_kernel");
+  if (umma_rc != 0) SARD_LAUNCH_OK("wgrad_kernel");
   int rblocks = ceil_div((long long)w->N1 * (w->N2 + 1), 32);
   if (w->grp_chunk_ptr && rblocks > 64) rblocks = 64;
   dim3 rgrid(rblocks, w->grp_chunk_ptr ? w->n_groups : 1);

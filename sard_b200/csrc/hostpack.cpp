@@ -1,0 +1,199 @@
+// Native host packer: flattens the reference's list-of-states rollout batch (TrajBatchDisc:
+// design_opt/utils/tools.py:4-16; state layout design_opt/envs/derl_envs/derl_env.py:377-396) into the
+// flat fp32 / int32 arrays of the device arena, writing straight into caller-provided (pinned) buffers.
+// Replaces the per-state Python work of tensorfy (transform2act_agent.py:20-24) and batch_data
+// (transform2act_policy.py:183-202).  Pure CPython C-API + buffer protocol (no numpy headers needed).
+//
+//   scan(states)  -> (T, n_total, e_total, d_obs, H, O, G)
+//   fill(states, actions_or_None, obs, act, node_ptr, edge_ptr, esrc, edst, stage, body, hf, ob, go, nthreads)
+// where the outputs are writable buffers (numpy arrays / torch pinned tensors via .numpy()).
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Src {
+  const void* ptr; Py_ssize_t n0, n1; Py_ssize_t s0, s1; char kind; int itemsize;   // kind: 'f' float, 'i' signed int
+};
+
+bool get_src(PyObject* o, Src& s, std::vector<Py_buffer>& keep) {
+  Py_buffer b;
+  if (PyObject_GetBuffer(o, &b, PyBUF_STRIDES | PyBUF_FORMAT) != 0) return false;
+  const char* f = b.format ? b.format : "B";
+  while (*f == '<' || *f == '=' || *f == '@' || *f == '|') ++f;
+  char k = 0;
+  if (*f == 'd' || *f == 'f') k = 'f';
+  else if (*f == 'l' || *f == 'q' || *f == 'i' || *f == 'b' || *f == 'h') k = 'i';
+  else if (*f == 'L' || *f == 'Q' || *f == 'I' || *f == 'B' || *f == 'H' || *f == '?') k = 'i';
+  if (!k || b.ndim > 2) { PyBuffer_Release(&b); PyErr_SetString(PyExc_TypeError, "hostpack: unsupported array dtype / rank"); return false; }
+  s.ptr = b.buf; s.kind = k; s.itemsize = (int)b.itemsize;
+  if (b.ndim == 0) { s.n0 = 1; s.n1 = 1; s.s0 = s.s1 = b.itemsize; }
+  else if (b.ndim == 1) { s.n0 = 1; s.n1 = b.shape[0]; s.s0 = 0; s.s1 = b.strides ? b.strides[0] : b.itemsize; }
+  else { s.n0 = b.shape[0]; s.n1 = b.shape[1]; s.s0 = b.strides[0]; s.s1 = b.strides[1]; }
+  keep.push_back(b);
+  return true;
+}
+
+inline double load_f(const Src& s, Py_ssize_t i, Py_ssize_t j) {
+  const char* p = (const char*)s.ptr + i * s.s0 + j * s.s1;
+  if (s.kind == 'f') return s.itemsize == 8 ? *(const double*)p : (double)*(const float*)p;
+  switch (s.itemsize) { case 8: return (double)*(const int64_t*)p; case 4: return (double)*(const int32_t*)p;
+                        case 2: return (double)*(const int16_t*)p; default: return (double)*(const int8_t*)p; }
+}
+inline long long load_i(const Src& s, Py_ssize_t i, Py_ssize_t j) {
+  const char* p = (const char*)s.ptr + i * s.s0 + j * s.s1;
+  if (s.kind == 'f') return (long long)(s.itemsize == 8 ? *(const double*)p : (double)*(const float*)p);
+  switch (s.itemsize) { case 8: return *(const int64_t*)p; case 4: return *(const int32_t*)p;
+                        case 2: return *(const int16_t*)p; default: return *(const int8_t*)p; }
+}
+
+void copy_f32(const Src& s, float* dst, Py_ssize_t ld) {
+  if (s.kind == 'f' && s.itemsize == 8 && s.s1 == 8) {
+    for (Py_ssize_t i = 0; i < s.n0; ++i) {
+      const double* p = (const double*)((const char*)s.ptr + i * s.s0);
+      float* d = dst + i * ld;
+      for (Py_ssize_t j = 0; j < s.n1; ++j) d[j] = (float)p[j];
+    }
+  } else if (s.kind == 'f' && s.itemsize == 4 && s.s1 == 4) {
+    for (Py_ssize_t i = 0; i < s.n0; ++i) memcpy(dst + i * ld, (const char*)s.ptr + i * s.s0, (size_t)s.n1 * 4);
+  } else {
+    for (Py_ssize_t i = 0; i < s.n0; ++i)
+      for (Py_ssize_t j = 0; j < s.n1; ++j) dst[i * ld + j] = (float)load_f(s, i, j);
+  }
+}
+
+struct Out { void* ptr; Py_ssize_t len; Py_buffer b; };
+bool get_out(PyObject* o, Out& out, int itemsize, std::vector<Py_buffer>& keep) {
+  Py_buffer b;
+  if (PyObject_GetBuffer(o, &b, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) != 0) return false;
+  if (b.itemsize != itemsize) { PyBuffer_Release(&b); PyErr_SetString(PyExc_TypeError, "hostpack: output buffer itemsize"); return false; }
+  out.ptr = b.buf; out.len = b.len / itemsize;
+  keep.push_back(b);
+  return true;
+}
+
+struct Item { Src obs, edges, stage, nn, body, hf, ob, go, act; bool has_act; };
+
+bool collect(PyObject* states, PyObject* actions, std::vector<Item>& items, std::vector<Py_buffer>& keep) {
+  const Py_ssize_t T = PySequence_Size(states);
+  if (T < 0) return false;
+  items.resize((size_t)T);
+  const bool has_act = actions && actions != Py_None;
+  for (Py_ssize_t t = 0; t < T; ++t) {
+    PyObject* st = PySequence_GetItem(states, t);
+    if (!st) return false;
+    if (PySequence_Size(st) != 8) { Py_DECREF(st); PyErr_SetString(PyExc_ValueError, "hostpack: a state must have 8 slots"); return false; }
+    Item& it = items[(size_t)t];
+    Src* slots[8] = {&it.obs, &it.edges, &it.stage, &it.nn, &it.body, &it.hf, &it.ob, &it.go};
+    for (int k = 0; k < 8; ++k) {
+      PyObject* o = PySequence_GetItem(st, k);
+      const bool ok = o && get_src(o, *slots[k], keep);
+      Py_XDECREF(o);
+      if (!ok) { Py_DECREF(st); return false; }
+    }
+    Py_DECREF(st);
+    it.has_act = has_act;
+    if (has_act) {
+      PyObject* a = PySequence_GetItem(actions, t);
+      const bool ok = a && get_src(a, it.act, keep);
+      Py_XDECREF(a);
+      if (!ok) return false;
+    }
+  }
+  return true;
+}
+
+void release(std::vector<Py_buffer>& keep) { for (auto& b : keep) PyBuffer_Release(&b); keep.clear(); }
+
+PyObject* py_scan(PyObject*, PyObject* args) {
+  PyObject* states;
+  if (!PyArg_ParseTuple(args, "O", &states)) return nullptr;
+  std::vector<Item> items; std::vector<Py_buffer> keep;
+  if (!collect(states, nullptr, items, keep)) { release(keep); return nullptr; }
+  long long n = 0, e = 0;
+  for (auto& it : items) { n += it.obs.n0; e += it.edges.n1; }
+  const long long d_obs = items.empty() ? 0 : (long long)items[0].obs.n1;
+  const long long H = items.empty() ? 0 : (long long)items[0].hf.n1, O = items.empty() ? 0 : (long long)items[0].ob.n1,
+                  G = items.empty() ? 0 : (long long)items[0].go.n1;
+  release(keep);
+  return Py_BuildValue("(LLLLLLL)", (long long)items.size(), n, e, d_obs, H, O, G);
+}
+
+PyObject* py_fill(PyObject*, PyObject* args) {
+  PyObject *states, *actions, *o_obs, *o_act, *o_np, *o_ep, *o_es, *o_ed, *o_st, *o_body, *o_hf, *o_ob, *o_go;
+  int nthreads = 4;
+  if (!PyArg_ParseTuple(args, "OOOOOOOOOOOOO|i", &states, &actions, &o_obs, &o_act, &o_np, &o_ep, &o_es, &o_ed, &o_st, &o_body,
+                        &o_hf, &o_ob, &o_go, &nthreads)) return nullptr;
+  std::vector<Item> items; std::vector<Py_buffer> keep;
+  Out obs, act, np_, ep, es, ed, stg, body, hf, ob, go;
+  if (!collect(states, actions, items, keep) || !get_out(o_obs, obs, 4, keep) || !get_out(o_act, act, 4, keep) ||
+      !get_out(o_np, np_, 4, keep) || !get_out(o_ep, ep, 4, keep) || !get_out(o_es, es, 4, keep) || !get_out(o_ed, ed, 4, keep) ||
+      !get_out(o_st, stg, 4, keep) || !get_out(o_body, body, 4, keep) || !get_out(o_hf, hf, 4, keep) || !get_out(o_ob, ob, 4, keep) ||
+      !get_out(o_go, go, 4, keep)) { release(keep); return nullptr; }
+  const size_t T = items.size();
+  if (T == 0) { release(keep); Py_RETURN_NONE; }
+  const Py_ssize_t D = items[0].obs.n1, H = items[0].hf.n1, O = items[0].ob.n1, G = items[0].go.n1;
+  int32_t* node_ptr = (int32_t*)np_.ptr; int32_t* edge_ptr = (int32_t*)ep.ptr;
+  long long n = 0, e = 0;
+  const char* err = nullptr;
+  for (size_t t = 0; t < T; ++t) {
+    node_ptr[t] = (int32_t)n; edge_ptr[t] = (int32_t)e;
+    const Item& it = items[t];
+    if (it.obs.n1 != D || it.hf.n1 != H || it.ob.n1 != O || it.go.n1 != G || it.edges.n0 != 2 || it.body.n1 != it.obs.n0 ||
+        (it.has_act && (it.act.n0 != it.obs.n0 || it.act.n1 != 8)))
+      err = "hostpack: inconsistent state shapes";
+    n += it.obs.n0; e += it.edges.n1;
+  }
+  node_ptr[T] = (int32_t)n; edge_ptr[T] = (int32_t)e;
+  if (!err && (obs.len < n * D || act.len < n * 8 || es.len < e || ed.len < e || body.len < n || (Py_ssize_t)T > stg.len ||
+               hf.len < (Py_ssize_t)T * H || ob.len < (Py_ssize_t)T * O || go.len < (Py_ssize_t)T * G))
+    err = "hostpack: output buffers too small";
+  if (err) { release(keep); PyErr_SetString(PyExc_ValueError, err); return nullptr; }
+
+  auto work = [&](size_t lo, size_t hi) {
+    for (size_t t = lo; t < hi; ++t) {
+      const Item& it = items[t];
+      const long long n0 = node_ptr[t], e0 = edge_ptr[t];
+      copy_f32(it.obs, (float*)obs.ptr + n0 * D, D);
+      if (it.has_act) copy_f32(it.act, (float*)act.ptr + n0 * 8, 8);
+      else memset((float*)act.ptr + n0 * 8, 0, (size_t)it.obs.n0 * 8 * 4);
+      for (Py_ssize_t j = 0; j < it.edges.n1; ++j) {
+        ((int32_t*)es.ptr)[e0 + j] = (int32_t)load_i(it.edges, 0, j);
+        ((int32_t*)ed.ptr)[e0 + j] = (int32_t)load_i(it.edges, 1, j);
+      }
+      for (Py_ssize_t j = 0; j < it.body.n1; ++j) ((int32_t*)body.ptr)[n0 + j] = (int32_t)load_i(it.body, 0, j);
+      ((int32_t*)stg.ptr)[t] = (int32_t)load_i(it.stage, 0, 0);
+      copy_f32(it.hf, (float*)hf.ptr + (long long)t * H, H);
+      copy_f32(it.ob, (float*)ob.ptr + (long long)t * O, O);
+      copy_f32(it.go, (float*)go.ptr + (long long)t * G, G);
+    }
+  };
+  Py_BEGIN_ALLOW_THREADS
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > T) nthreads = (int)T;
+  std::vector<std::thread> th;
+  const size_t per = (T + nthreads - 1) / nthreads;
+  for (int k = 1; k < nthreads; ++k) {
+    const size_t lo = k * per, hi = lo + per < T ? lo + per : T;
+    if (lo < hi) th.emplace_back(work, lo, hi);
+  }
+  work(0, per < T ? per : T);
+  for (auto& x : th) x.join();
+  Py_END_ALLOW_THREADS
+  release(keep);
+  Py_RETURN_NONE;
+}
+
+PyMethodDef methods[] = {
+    {"scan", py_scan, METH_VARARGS, "scan(states) -> (T, n_total, e_total, d_obs, H, O, G)"},
+    {"fill", py_fill, METH_VARARGS, "fill(states, actions, obs, act, node_ptr, edge_ptr, esrc, edst, stage, body, hf, ob, go[, nthreads])"},
+    {nullptr, nullptr, 0, nullptr}};
+PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_hostpack", "native rollout packer for sard_b200", -1, methods};
+
+}  // namespace
+
+PyMODINIT_FUNC PyInit__hostpack(void) { return PyModule_Create(&moddef); }

@@ -528,6 +528,188 @@ static int launch_umma_ts(const SardGemm* g, cudaStream_t st) {
 
 extern int g_sard_gemm_engine;
 
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  partial[chunk][n1][n2] = sum_{rows of chunk} dZ[row][n1] * X[row][n2].
+// The reduction runs over rows, so the UMMA "M" dimension is n1 (<= 128 per tile) and "K" is the row index:
+//   A(m = n1, k = row) = dZ[row][n1]   -> every thread owns one n1 (TMEM lane), loads 16 rows per 32-row step
+//                                          (coalesced across the warp along n1) and stores hi/lo with tcgen05.st
+//   B(n = n2, k = row) = X[row][n2]    -> consecutive threads take consecutive n2 (coalesced), 4 rows per 16-byte
+//                                          chunk, hi/lo written K-major SWIZZLE_128B (conflict-free: the XOR
+//                                          swizzle spreads the 8 rows of an atom over all banks)
+// TMEM map: [0,256) accumulator (N2 tile up to 256), [256,512) two stages of {A_hi[32], A_lo[32]} (+pad).
+// The bias gradient (column sums of dZ) is accumulated in registers from the same A values.
+// ------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(UMMA_THREADS, 1) umma_wgrad_kernel(const SardWGrad w) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int B_TILE = NB * UMMA_KC;                     // floats
+  constexpr int STAGE = 2 * B_TILE;
+  constexpr uint32_t TMEM_COLS = 512;
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_stage[2];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bsum_s[UMMA_BM];
+
+  int rs, re;
+  if (w.chunks) {
+    if ((int)blockIdx.x >= *w.num_chunks) return;
+    const int4 t = reinterpret_cast<const int4*>(w.chunks)[blockIdx.x];
+    rs = t.x; re = t.y;
+  } else {
+    rs = blockIdx.x * w.chunk_rows;
+    re = min(w.M, rs + w.chunk_rows);
+    if (rs >= w.M) return;
+  }
+  const int c10 = blockIdx.y * UMMA_BM, c20 = blockIdx.z * NB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane_grp = warp & 3, half = warp >> 2;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(&bar_stage[0], 1);
+    mbar_init(&bar_stage[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+  const uint32_t tmem_lane = (uint32_t)(lane_grp * 32) << 16;
+
+  const int n1 = c10 + lane_grp * 32 + lane;               // this thread's output row (TMEM lane)
+  const bool n1_ok = n1 < w.N1;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(UMMA_BM >> 4) << 24);
+  constexpr int B_CH = NB * 8 / UMMA_THREADS;
+
+  float ra[16];
+  float4 rb[B_CH];
+  float bsum = 0.f;
+  auto load_regs = [&](int step) {
+    const int r0 = rs + step * UMMA_KC;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = r0 + half * 16 + i;
+      float v = 0.f;
+      if (n1_ok && r < re) v = __ldg(w.P + (size_t)(w.p_rows ? w.p_rows[r] : r) * w.ldp + n1);
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int idx = tid + i * UMMA_THREADS;
+      const int n = idx % NB, c = idx / NB;
+      const int n2 = c20 + n;
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      if (n2 < w.N2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = r0 + c * 4 + j;
+          if (r < re) e[j] = __ldg(w.Q + (size_t)(w.q_rows ? w.q_rows[r] : r) * w.ldq + n2);
+        }
+      }
+      rb[i] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+  };
+
+  const int nsteps = (re - rs + UMMA_KC - 1) / UMMA_KC;
+  load_regs(0);
+  for (int st = 0; st < nsteps; ++st) {
+    const int s = st & 1;
+    float* b_hi = base + s * STAGE;
+    float* b_lo = b_hi + B_TILE;
+    const uint32_t ta_hi = tmem_d + 256u + (uint32_t)s * 128u;     // A_hi columns [0,32), A_lo at +64
+    if (st >= 2) {
+      mbar_wait(&bar_stage[s], ((st >> 1) - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        bsum += ra[j];
+        hi[j] = __uint_as_float(__float_as_uint(ra[j]) & 0xffffe000u);
+        lo[j] = ra[j] - hi[j];
+      }
+      tmem_st16(ta_hi + tmem_lane + (uint32_t)(half * 16), hi);
+      tmem_st16(ta_hi + 64u + tmem_lane + (uint32_t)(half * 16), lo);
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int idx = tid + i * UMMA_THREADS;
+      store_split(b_hi, b_lo, idx % NB, idx / NB, rb[i]);
+    }
+    if (st + 1 < nsteps) load_regs(st + 1);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+      const int ksteps = min(4, (re - rs - st * UMMA_KC + 7) >> 3);
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t db_hi = umma_desc(sb_hi + k * 32), db_lo = umma_desc(sb_lo + k * 32);
+        const uint32_t a_hi = ta_hi + (uint32_t)(k * 8), a_lo = ta_hi + 64u + (uint32_t)(k * 8);
+        umma_tf32_ts(tmem_d, a_hi, db_hi, idesc, (st | k) ? 1u : 0u);
+        umma_tf32_ts(tmem_d, a_lo, db_hi, idesc, 1u);
+        umma_tf32_ts(tmem_d, a_hi, db_lo, idesc, 1u);
+      }
+      umma_commit(&bar_stage[s]);
+      if (st == nsteps - 1) umma_commit(&bar_done);
+    }
+  }
+  // bias gradient: the two halves of a lane group hold the two 16-row halves of every step
+  if (half == 1) bsum_s[lane_grp * 32 + lane] = bsum;
+  mbar_wait(&bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  const int ldpart = w.N2 + 1;
+  float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
+  constexpr int NCHUNK = NB / 32;
+  for (int cc = half; cc < NCHUNK; cc += 2) {
+    float v[32];
+    tmem_ld32(tmem_d + tmem_lane + (uint32_t)(cc * 32), v);
+    if (!n1_ok) continue;
+    float* pp = part + (size_t)n1 * ldpart + c20 + cc * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (c20 + cc * 32 + j < w.N2) pp[j] = v[j];
+  }
+  if (half == 0 && n1_ok && blockIdx.z == 0) part[(size_t)n1 * ldpart + w.N2] = bsum + bsum_s[lane_grp * 32 + lane];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int NB>
+static int launch_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st) {
+  constexpr size_t smem = 2 * (2 * NB * UMMA_KC) * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SARD_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(nchunks, ceil_div(w->N1, UMMA_BM), ceil_div(w->N2, NB));
+  umma_wgrad_kernel<NB><<<grid, UMMA_THREADS, smem, st>>>(*w);
+  SARD_LAUNCH_OK("umma_wgrad_kernel");
+  return 0;
+}
+
+// partial products of the weight gradient on the tensor cores; -1 = shape not handled (caller uses the SIMT kernel)
+int sard_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st) {
+  if (w->N1 < 32 || w->N2 < 8) return -1;
+  if (w->N2 <= 64) return launch_umma_wgrad<64>(w, nchunks, st);
+  if (w->N2 <= 128) return launch_umma_wgrad<128>(w, nchunks, st);
+  return launch_umma_wgrad<256>(w, nchunks, st);
+}
+
 // returns -1 when the shape is not handled by this engine (caller falls through to the SIMT kernels)
 int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st) {
   // long reductions stay on the FFMA engine: tensor-core fp32 accumulation truncates, and the bias grows

@@ -265,6 +265,7 @@ class PolicyEngine(_EngineBase):
             st.log_std = -1 if s == 0 else self.store.off(m.attr_action_log_std if s == 1 else m.control_action_log_std)
             st.tie_c0, st.tie_c1 = m.tie_columns(s)
             st.max_index = self.max_index
+            st.n_live = max(int(self.ever_live[s].sum()), 1)
             st.slot_of_index = self.slot_of_index.data_ptr() + 4 * self.max_index * s
             st.GT = self.GA.data_ptr() + 4 * self.gt_off[s]
         self.net = net

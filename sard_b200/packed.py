@@ -54,43 +54,79 @@ def host_rollout_from_lists(states: Sequence[list], actions: Optional[Sequence] 
         exps=z(exps))
 
 
+try:                                    # native list walker (sard_b200/csrc/hostpack.cpp); pure-Python packing otherwise
+    from . import _hostpack
+except ImportError:                     # pragma: no cover
+    _hostpack = None
+
+_F32 = ('obs', 'actions', 'hfield', 'obj', 'goal', 'rewards', 'masks')
+_I32 = ('node_ptr', 'edge_ptr', 'esrc', 'edst', 'stage', 'body_ind')
+
+
+def host_tensors_from_rollout(host: HostRollout, pin: bool = True) -> dict:
+    """fp32 / int32 host tensors (pinned when asked) of a flat ``HostRollout``."""
+    src = {'obs': host.obs, 'actions': host.actions, 'hfield': host.hfield, 'obj': host.obj, 'goal': host.goal,
+           'rewards': host.rewards, 'masks': host.masks, 'node_ptr': host.node_ptr, 'edge_ptr': host.edge_ptr,
+           'esrc': host.edges[0], 'edst': host.edges[1], 'stage': host.stage, 'body_ind': host.body_ind}
+    out = {}
+    for k, a in src.items():
+        a = np.asarray(a)
+        dt = torch.float32 if k in _F32 else torch.int32
+        t = torch.empty(a.shape, dtype=dt, pin_memory=pin)
+        np.copyto(t.numpy(), a, casting='unsafe')          # one pass: cast straight into the (pinned) staging buffer
+        out[k] = t
+    return out
+
+
+def host_tensors_from_lists(states, actions=None, rewards=None, masks=None, pin: bool = True, nthreads: int = 8):
+    """Same from the reference's list-of-states batch; uses the native packer when it is built."""
+    if _hostpack is None or isinstance(states[0][0], torch.Tensor):
+        return host_tensors_from_rollout(host_rollout_from_lists(states, actions, rewards, masks), pin)
+    T, n, e, d, H, O, G = _hostpack.scan(states)
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
+    out = {'obs': mk((n, d), torch.float32), 'actions': mk((n, 8), torch.float32), 'node_ptr': mk((T + 1,), torch.int32),
+           'edge_ptr': mk((T + 1,), torch.int32), 'esrc': mk((e,), torch.int32), 'edst': mk((e,), torch.int32),
+           'stage': mk((T,), torch.int32), 'body_ind': mk((n,), torch.int32), 'hfield': mk((T, H), torch.float32),
+           'obj': mk((T, O), torch.float32), 'goal': mk((T, G), torch.float32)}
+    _hostpack.fill(states, actions, *[out[k].numpy() for k in ('obs', 'actions', 'node_ptr', 'edge_ptr', 'esrc', 'edst', 'stage',
+                                                                'body_ind', 'hfield', 'obj', 'goal')], nthreads)
+    for k, v in (('rewards', rewards), ('masks', masks)):
+        t = mk((T,), torch.float32)
+        if v is None:
+            t.zero_()
+        else:
+            np.copyto(t.numpy(), _np(v).reshape(-1), casting='unsafe')
+        out[k] = t
+    return out
+
+
 class PackedRollout:
     """One rollout batch resident on the device (the ``SardArena`` of include/sard_b200.h)."""
 
-    def __init__(self, host: HostRollout, device, pin: bool = True):
+    def __init__(self, host, device, pin: bool = True):
         device = torch.device(device)
         if device.type != 'cuda':
             raise _lib.SardError('PackedRollout needs a CUDA device: the SARD B200 path has no CPU implementation')
         self.device = device
-        self.T = int(host.stage.shape[0])
-        self.n_total = int(host.node_ptr[-1])
-        self.e_total = int(host.edge_ptr[-1])
-        self.d_obs = int(host.obs.shape[1])
+        ht = host if isinstance(host, dict) else host_tensors_from_rollout(host, pin)
+        self.T = int(ht['stage'].shape[0])
+        self.n_total = int(ht['node_ptr'][-1])
+        self.e_total = int(ht['edge_ptr'][-1])
+        self.d_obs = int(ht['obs'].shape[1])
         # host-side integer copies used for planning (no device round trips in the update loop)
-        self.stage_np = host.stage.astype(np.int64, copy=False)
-        self.num_nodes_np = np.diff(host.node_ptr).astype(np.int64)
-        self.node_ptr_np = host.node_ptr.astype(np.int64, copy=False)
-        self.body_np = host.body_ind.astype(np.int64, copy=False)
-        self.h2d_bytes = 0
-
-        def up(a, dtype):
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
-            if pin:
-                t = t.pin_memory()
-            self.h2d_bytes += t.numel() * t.element_size()
-            return t.to(device, non_blocking=True)
-
-        self.obs = up(host.obs, np.float32)
-        self.actions = up(host.actions, np.float32)
-        self.node_ptr = up(host.node_ptr, np.int32)
-        self.edge_ptr = up(host.edge_ptr, np.int32)
-        self.esrc = up(host.edges[0], np.int32)
-        self.edst = up(host.edges[1], np.int32)
-        self.stage = up(host.stage, np.int32)
-        self.body_ind = up(host.body_ind, np.int32)
-        self.ext = [up(host.hfield, np.float32), up(host.obj, np.float32), up(host.goal, np.float32)]
-        self.rewards = up(host.rewards, np.float32)
-        self.masks = up(host.masks, np.float32)
+        self.stage_np = ht['stage'].numpy().astype(np.int64)
+        self.node_ptr_np = ht['node_ptr'].numpy().astype(np.int64)
+        self.num_nodes_np = np.diff(self.node_ptr_np)
+        self.body_np = ht['body_ind'].numpy().astype(np.int64)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in ht.values())
+        up = lambda k: ht[k].to(device, non_blocking=True)
+        self._host = ht                                     # keep the pinned staging alive until the copies finish
+        self.obs, self.actions = up('obs'), up('actions')
+        self.node_ptr, self.edge_ptr = up('node_ptr'), up('edge_ptr')
+        self.esrc, self.edst = up('esrc'), up('edst')
+        self.stage, self.body_ind = up('stage'), up('body_ind')
+        self.ext = [up('hfield'), up('obj'), up('goal')]
+        self.rewards, self.masks = up('rewards'), up('masks')
         i32 = dict(dtype=torch.int32, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.in_ptr = torch.empty(self.n_total + 1, **i32)
@@ -110,7 +146,7 @@ class PackedRollout:
 
     @classmethod
     def from_lists(cls, states, actions=None, rewards=None, masks=None, exps=None, device='cuda', pin=False):
-        return cls(host_rollout_from_lists(states, actions, rewards, masks, exps), device, pin=pin)
+        return cls(host_tensors_from_lists(states, actions, rewards, masks, pin=pin), device, pin=pin)
 
     def _make_struct(self) -> SardArena:
         a = SardArena()

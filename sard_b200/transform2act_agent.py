@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from .engine import Comm
 from .nets import AdamState
-from .packed import EpochPlan, Ordering, PackedRollout, host_rollout_from_lists, stage_partition
+from .packed import EpochPlan, Ordering, PackedRollout, host_tensors_from_lists, stage_partition
 from .rl_core import estimate_advantages
 from .synthetic import HostRollout
 from .transform2act_critic import Transform2ActValue
@@ -177,9 +177,10 @@ class Transform2ActAgent:
     # ---- the hot path ------------------------------------------------------------------------------
     def pack(self, batch) -> PackedRollout:
         """``TrajBatchDisc`` (or a ``HostRollout``) -> device arena: one packed upload instead of tensorfy."""
-        host = batch if isinstance(batch, HostRollout) else host_rollout_from_lists(
-            batch.states, batch.actions, batch.rewards, batch.masks, getattr(batch, 'exps', None))
-        return PackedRollout(host, self.device, pin=True)
+        if isinstance(batch, HostRollout):
+            return PackedRollout(batch, self.device, pin=True)
+        return PackedRollout(host_tensors_from_lists(batch.states, batch.actions, batch.rewards, batch.masks, pin=True),
+                             self.device, pin=True)
 
     def _prepare(self, arena: PackedRollout):
         self.policy_net.prepare(arena, self.optimizer_policy)

@@ -37,3 +37,30 @@ for name, M, N, R, nt in shapes:
         us = e0.elapsed_time(e1) / iters * 1e3
         err = float((Y.double() - ref).abs().max())
         print(f'{name:16s} M={M} N={N} R={R} engine={eng}: {us:7.1f} us  {2*M*N*R/us/1e6:7.2f} TFLOP/s  max|err|={err:.2e}')
+
+# ---- weight gradient (ungrouped) ----
+for name, M, N1, N2 in [('gconv wgrad', 18432, 64, 128), ('il1 wgrad', 18432, 128, 256), ('in_fc wgrad', 18432, 64, 82)]:
+    if only and only not in name:
+        continue
+    dZ = torch.randn(M, N1, device='cuda'); X = torch.randn(M, N2, device='cuda')
+    dW = torch.zeros(N1, N2, device='cuda'); db = torch.zeros(N1, device='cuda')
+    rows = L.lib.sard_wgrad_chunk_rows(M, N1, N2)
+    part = torch.zeros(((M + rows - 1) // rows) * N1 * (N2 + 1), device='cuda')
+    w = L.SardWGrad()
+    w.P, w.ldp, w.Q, w.ldq, w.M, w.N1, w.N2, w.chunk_rows = L.ptr(dZ), N1, L.ptr(X), N2, M, N1, N2, 0
+    w.dW0, w.ldw0, w.w_split, w.db, w.partials = L.ptr(dW), N2, N2, L.ptr(db), L.ptr(part)
+    ref = dZ.double().t() @ X.double()
+    for eng in [int(e) for e in os.environ.get('ENGINES', '0,1,2').split(',')]:
+        L.lib.sard_set_gemm_engine(eng)
+        for _ in range(3):
+            L.check(L.lib.sard_linear_bwd_weight(C.byref(w), L.stream()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dW.zero_()
+        e0.record()
+        for _ in range(iters):
+            L.check(L.lib.sard_linear_bwd_weight(C.byref(w), L.stream()))
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        err = float((dW.double() / iters - ref).abs().max())
+        print(f'{name:16s} M={M} N1={N1} N2={N2} engine={eng}: {us:7.1f} us  {2*M*N1*N2/us/1e6:7.2f} TFLOP/s  max|err|={err:.2e}')
