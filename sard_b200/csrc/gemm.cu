@@ -164,6 +164,8 @@ gemm_kernel(const SardGemm g) {
 
 int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st);   // umma.cu; -1 = shape not handled
 int sard_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st);
+int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st);      // gemm_fast.cu; -1 = not covered
+int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st);
 int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
 extern "C" int sard_set_gemm_engine(int engine) { g_sard_gemm_engine = engine; return 0; }
 extern "C" int sard_get_gemm_engine(void) { return g_sard_gemm_engine; }
@@ -179,6 +181,10 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
   if (g_sard_gemm_engine >= 1) {
     const int r = sard_umma_gemm(g, NT, st);
+    if (r >= 0) return r;
+  }
+  {
+    const int r = sard_gemm_fast(g, NT, st);
     if (r >= 0) return r;
   }
   if (g->N <= 16) {
@@ -362,7 +368,9 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
 // Rows per chunk for an ungrouped weight gradient: enough chunks to put ~2 CTAs on every SM, at least
 // 16 rows each (the partial products are reduced in chunk order afterwards).
 extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
-  const long long tiles = (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
+  const bool fast = N1 % 64 == 0 && N2 % 128 == 0;          // wgrad_fast_kernel tiles: (64|128) x 128
+  const long long tiles = fast ? (long long)(N1 % 128 == 0 ? N1 / 128 : N1 / 64) * (N2 / 128)
+                               : (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
   long long chunks = (2 * 148 + tiles - 1) / tiles;
   if (chunks < 1) chunks = 1;
   long long rows = (M + chunks - 1) / chunks;
@@ -395,8 +403,12 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
     umma_rc = sard_umma_wgrad(w, nchunks, st);
     if (umma_rc > 0) return umma_rc;
   }
+  if (umma_rc != 0) {
+    umma_rc = sard_wgrad_fast(w, nchunks, st);          // aligned shapes: 8x8 register tiles, 16-byte loads
+    if (umma_rc > 0) return umma_rc;
+  }
   if (umma_rc == 0) {
-    // partial products done on the tensor cores
+    // partial products already launched (tensor cores or the fast SIMT kernel)
   } else if (w->N1 <= 16) {
     dim3 grid(nchunks, 1, ceil_div(w->N2, 64));
     wgrad_kernel<16, 64, 16, 4, 4><<<grid, 64, 0, st>>>(*w);

@@ -1,0 +1,296 @@
+// Fast paths of the fp32 SIMT GEMMs for the aligned shapes that dominate the update (GraphConv, JSMLP,
+// critic MLP): 16-byte global loads with per-thread base pointers (no per-element index math or
+// bounds branches: out-of-range rows are clamped to a valid row and discarded in the epilogue), 8x8 /
+// 8x4 register tiles, register-prefetch double buffering, shared-memory-staged rolled epilogue.
+// ncu on the generic kernels showed them issue-bound with only 37-46 % of issued instructions being
+// FFMA; these variants are ~90 % FFMA in the main loop.  Anything unaligned falls back to gemm.cu.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ forward / backward-data
+template <int BN, int TN, bool NT>
+__global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
+  constexpr int BM = 128, BK = 16, TM = 8;
+  constexpr int AS = BK * (BM + 4), BS = BK * (BN + 4);
+  constexpr int A_LD = BM * BK / 4 / 256;                  // float4 loads per thread: 2
+  constexpr int B_LD = BN * BK / 4 / 256;                  // 1 (BN=64) or 2 (BN=128)
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = smem + 2 * AS;
+
+  int row_start, row_end, group = 0;
+  if (g.tiles) {
+    if ((int)blockIdx.x >= *g.num_tiles) return;
+    const int4 t = reinterpret_cast<const int4*>(g.tiles)[blockIdx.x];
+    row_start = t.x; row_end = t.y; group = t.z;
+  } else {
+    row_start = blockIdx.x * BM;
+    row_end = min(g.M, row_start + BM);
+    if (row_start >= g.M) return;
+  }
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x;
+  const float* B0 = g.B0 + (size_t)group * g.b_group_stride;
+  const float* B1 = g.B1 ? g.B1 + (size_t)group * g.b_group_stride : nullptr;
+
+  const float* a_ptr[A_LD];
+#pragma unroll
+  for (int i = 0; i < A_LD; ++i) {
+    const int idx = tid + i * 256;
+    const int grow = min(row_start + (idx >> 2), row_end - 1);         // clamp: extra rows are never stored
+    a_ptr[i] = g.A + (size_t)(g.a_rows ? g.a_rows[grow] : grow) * g.lda + (idx & 3) * 4;
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[A_LD], rb[B_LD];
+  const int nkb = g.R / BK;
+  int buf = 0;
+#pragma unroll 1
+  for (int kb = 0; kb <= nkb; ++kb) {
+    if (kb < nkb) {
+      const int k0 = kb * BK;
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) ra[i] = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + k0));
+#pragma unroll
+      for (int i = 0; i < B_LD; ++i) {
+        const int idx = tid + i * 256;
+        if (NT) {            // W[n][k]: 4 consecutive k of output column n
+          const int n = idx >> 2, kk = k0 + (idx & 3) * 4;
+          rb[i] = kk < g.b_split ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(n0 + n) * g.ldb0 + kk))
+                                 : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(n0 + n) * g.ldb1 + (kk - g.b_split)));
+        } else {             // W[k][c]: 4 consecutive output columns of reduction row k
+          const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
+          rb[i] = n0 < g.b_split ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(k0 + r) * g.ldb0 + n0 + c))
+                                 : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(k0 + r) * g.ldb1 + (n0 - g.b_split) + c));
+        }
+      }
+    }
+    if (kb > 0) {
+      const float* Ac = As + (buf ^ 1) * AS + ty * TM;
+      const float* Bc = Bs + (buf ^ 1) * BS + tx * TN;
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int i = 0; i < TM; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Ac + k * (BM + 4) + i);
+          a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Bc + k * (BN + 4) + j);
+          b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    if (kb < nkb) {
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int idx = tid + i * 256;
+        float* d = As + buf * AS + ((idx & 3) * 4) * (BM + 4) + (idx >> 2);
+        d[0] = ra[i].x; d[BM + 4] = ra[i].y; d[2 * (BM + 4)] = ra[i].z; d[3 * (BM + 4)] = ra[i].w;
+      }
+#pragma unroll
+      for (int i = 0; i < B_LD; ++i) {
+        const int idx = tid + i * 256;
+        if (NT) {
+          float* d = Bs + buf * BS + ((idx & 3) * 4) * (BN + 4) + (idx >> 2);
+          d[0] = rb[i].x; d[BN + 4] = rb[i].y; d[2 * (BN + 4)] = rb[i].z; d[3 * (BN + 4)] = rb[i].w;
+        } else {
+          *reinterpret_cast<float4*>(Bs + buf * BS + (idx / (BN / 4)) * (BN + 4) + (idx % (BN / 4)) * 4) = rb[i];
+        }
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  float* Cs = smem;                                          // [BM][BN+1]; the operand tiles are dead
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) Cs[(ty * TM + i) * (BN + 1) + tx * TN + j] = acc[i][j];
+  __syncthreads();
+  const float* bias = g.bias ? g.bias + (size_t)group * g.bias_group_stride : nullptr;
+  const int rows = row_end - row_start;
+#pragma unroll 1
+  for (int idx = tid; idx < rows * BN; idx += 256) {
+    const int m = idx / BN, c = idx % BN;
+    const int gc = n0 + c;
+    const int grow = row_start + m;
+    const long long yrow = g.y_rows ? g.y_rows[grow] : grow;
+    float v = Cs[m * (BN + 1) + c];
+    if (NT) {
+      if (bias) v += __ldg(bias + gc);
+      v = epi_forward(v, g.act, g.post, g.Ypre ? g.Ypre + yrow * g.ldy + gc : nullptr);
+    } else if (g.Dact) {
+      v *= act_grad_from_output(g.Dact[yrow * g.ldd + gc], gc < g.dsplit ? g.dact0 : g.dact1);
+    }
+    g.Y[yrow * g.ldy + gc] = v;
+  }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, int TN, bool NT>
+static int launch_fast(const SardGemm* g, cudaStream_t st) {
+  constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
+  constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
+  static bool configured = false;
+  if (!configured) {
+    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
+  if (tiles <= 0) return 0;
+  dim3 grid(tiles, g->N / BN);
+  gemm_fast_kernel<BN, TN, NT><<<grid, 256, smem, st>>>(*g);
+  SARD_LAUNCH_OK(NT ? "gemm_fast_kernel<fwd>" : "gemm_fast_kernel<bwd_data>");
+  return 0;
+}
+
+// -1: the shape / alignment is not covered, use the generic kernel
+int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
+  if (g->R < 16 || g->R % 16 || g->N % 64 || g->lda % 4 || !al16(g->A) || g->ldb0 % 4 || !al16(g->B0)) return -1;
+  if (g->b_group_stride % 4) return -1;
+  const bool split = g->B1 != nullptr;
+  if (split && (g->ldb1 % 4 || !al16(g->B1))) return -1;
+  if (nt) {
+    if (split && g->b_split % 16) return -1;
+    if (!split && g->b_split < g->R) return -1;
+    if (g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, true>(g, st);
+    return launch_fast<64, 4, true>(g, st);
+  }
+  if (split) {
+    if (g->b_split % 64) return -1;
+    return launch_fast<64, 4, false>(g, st);               // every 64-column block lies in one weight matrix
+  }
+  if (g->b_split < g->N) return -1;
+  if (g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, false>(g, st);
+  return launch_fast<64, 4, false>(g, st);
+}
+
+// ------------------------------------------------------------------------------------------ weight gradient
+template <int BN1>
+__global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) {
+  constexpr int BN2 = 128, BKM = 16, NTH = BN1 * 2;         // 8x8 register tile: (BN1/8) x 16 threads
+  constexpr int PS = BKM * (BN1 + 4), QS = BKM * (BN2 + 4);
+  constexpr int P_LD = BKM * BN1 / 4 / NTH, Q_LD = BKM * BN2 / 4 / NTH;
+  __shared__ __align__(16) float Ps[2 * PS];
+  __shared__ __align__(16) float Qs[2 * QS];
+  int rs, re;
+  if (w.chunks) {
+    if ((int)blockIdx.x >= *w.num_chunks) return;
+    const int4 t = reinterpret_cast<const int4*>(w.chunks)[blockIdx.x];
+    rs = t.x; re = t.y;
+  } else {
+    rs = blockIdx.x * w.chunk_rows;
+    re = min(w.M, rs + w.chunk_rows);
+    if (rs >= w.M) return;
+  }
+  const int c10 = blockIdx.y * BN1, c20 = blockIdx.z * BN2;
+  const int tid = threadIdx.x;
+  const int t1 = tid >> 4, t2 = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = blockIdx.z == 0 && tid < BN1;
+
+  float4 rp[P_LD], rq[Q_LD];
+  const int nsteps = (re - rs + BKM - 1) / BKM;
+  int buf = 0;
+#pragma unroll 1
+  for (int s = 0; s <= nsteps; ++s) {
+    if (s < nsteps) {
+      const int m0 = rs + s * BKM;
+#pragma unroll
+      for (int i = 0; i < P_LD; ++i) {
+        const int idx = tid + i * NTH;
+        const int row = m0 + idx / (BN1 / 4), c = (idx % (BN1 / 4)) * 4;
+        rp[i] = row < re ? __ldg(reinterpret_cast<const float4*>(w.P + (size_t)(w.p_rows ? w.p_rows[row] : row) * w.ldp + c10 + c))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < Q_LD; ++i) {
+        const int idx = tid + i * NTH;
+        const int row = m0 + idx / (BN2 / 4), c = (idx % (BN2 / 4)) * 4;
+        rq[i] = row < re ? __ldg(reinterpret_cast<const float4*>(w.Q + (size_t)(w.q_rows ? w.q_rows[row] : row) * w.ldq + c20 + c))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (s > 0) {
+      const float* Pc = Ps + (buf ^ 1) * PS;
+      const float* Qc = Qs + (buf ^ 1) * QS;
+#pragma unroll
+      for (int k = 0; k < BKM; ++k) {
+        float p[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Pc + k * (BN1 + 4) + t1 * 8 + i);
+          p[i] = v.x; p[i + 1] = v.y; p[i + 2] = v.z; p[i + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Qc + k * (BN2 + 4) + t2 * 8 + j);
+          q[j] = v.x; q[j + 1] = v.y; q[j + 2] = v.z; q[j + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p[i], q[j], acc[i][j]);
+      }
+      if (do_bias) {
+#pragma unroll
+        for (int k = 0; k < BKM; ++k) bsum += Pc[k * (BN1 + 4) + tid];
+      }
+    }
+    if (s < nsteps) {
+#pragma unroll
+      for (int i = 0; i < P_LD; ++i) {
+        const int idx = tid + i * NTH;
+        *reinterpret_cast<float4*>(Ps + buf * PS + (idx / (BN1 / 4)) * (BN1 + 4) + (idx % (BN1 / 4)) * 4) = rp[i];
+      }
+#pragma unroll
+      for (int i = 0; i < Q_LD; ++i) {
+        const int idx = tid + i * NTH;
+        *reinterpret_cast<float4*>(Qs + buf * QS + (idx / (BN2 / 4)) * (BN2 + 4) + (idx % (BN2 / 4)) * 4) = rq[i];
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int ldpart = w.N2 + 1;
+  float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pp[j] = acc[i][j];
+  }
+  if (do_bias) part[(size_t)(c10 + tid) * ldpart + w.N2] = bsum;
+}
+
+// partial products for aligned shapes; -1 = not covered (caller uses the generic kernel)
+int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st) {
+  if (w->N1 % 64 || w->N2 % 128 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
+  if (w->N1 % 128 == 0) {
+    dim3 grid(nchunks, w->N1 / 128, w->N2 / 128);
+    wgrad_fast_kernel<128><<<grid, 256, 0, st>>>(*w);
+  } else {
+    dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
+    wgrad_fast_kernel<64><<<grid, 128, 0, st>>>(*w);
+  }
+  SARD_LAUNCH_OK("wgrad_fast_kernel");
+  return 0;
+}
