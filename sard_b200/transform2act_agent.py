@@ -78,6 +78,8 @@ class Transform2ActAgent:
         self.enable_infer = cfg.enable_infer
         self.total_time_steps = 0
         self.last_update_stats = {}
+        self.overlap_nets = True          # critic and policy updates of a minibatch on two CUDA streams
+        self._streams = None
         if checkpoint != 0:
             self.load_checkpoint(checkpoint)
 
@@ -251,11 +253,20 @@ class Transform2ActAgent:
         batch_design = bool(self.cfg.agent_specs.get('batch_design', False))
         n_mb = T // M
         n_steps = self.opt_num_epochs * n_mb
+        plans_alive = []
         plog = torch.zeros(max(n_steps, 1), 8, dtype=torch.float32, device=self.device)
         vlog = torch.zeros(max(n_steps, 1), 8, dtype=torch.float32, device=self.device)
         step = 0
         h2d = 0
         cur_perm = np.arange(T)
+        # The critic update and the policy update of a minibatch are independent (disjoint parameters,
+        # workspaces and gradient buckets; the arena is read-only), and each one alone launches grids of
+        # only ~150-300 CTAs on 148 SMs: run them on two streams so their kernels share the machine.
+        main = torch.cuda.current_stream(self.device)
+        if self._streams is None or self._streams[0].device != self.device:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        sv, sp = self._streams
+        sv.wait_stream(main); sp.wait_stream(main)
         for ep in range(self.opt_num_epochs):
             # like the reference, each epoch permutes the already permuted lists (agent :331-342)
             p = perms[ep] if perms is not None else self.draw_perm(T)
@@ -263,6 +274,7 @@ class Transform2ActAgent:
             plan = EpochPlan(arena, cur_perm, M, batch_design)
             cur_perm = plan.perm
             h2d += plan.h2d_bytes
+            sv.wait_stream(main); sp.wait_stream(main)       # the ordering upload happened on the main stream
             counts = np.concatenate([plan.stage_graphs, plan.stage_nodes], axis=1)      # [n_mb, 6]
             if world > 1:
                 ct = torch.from_numpy(counts).to(self.device)
@@ -271,10 +283,21 @@ class Transform2ActAgent:
             for k in range(plan.n_mb):
                 B_glob = int(counts[k, :3].sum())
                 active = [bool(counts[k, s] > 0) for s in range(3)]
-                veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
-                peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
-                                40.0, self.clip_first_step_only, plog[step], comm)
+                if self.overlap_nets and comm is None:
+                    with torch.cuda.stream(sv):
+                        veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
+                    with torch.cuda.stream(sp):
+                        peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
+                                        40.0, self.clip_first_step_only, plog[step], comm)
+                else:
+                    veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
+                    peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
+                                    40.0, self.clip_first_step_only, plog[step], comm)
                 step += 1
+            if self.overlap_nets and comm is None:
+                # the next epoch's plan replaces the ordering tensors the in-flight kernels read
+                plans_alive.append(plan)
+        main.wait_stream(sv); main.wait_stream(sp)
         logs = plog[:step].cpu().numpy()
         vlogs = vlog[:step].cpu().numpy()
         self.last_update_stats = {'h2d_bytes': arena.h2d_bytes + h2d, 'd2h_bytes': int(logs.nbytes + vlogs.nbytes),
