@@ -138,14 +138,41 @@ class ValueEngine(_EngineBase):
             check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), mode, PHASE_ALL,
                                      inv_B, ptr(ml), None, 1, sq, ptr(ws), ws.numel(), st))
 
+    # -- data-parallel phases: the agent interleaves them with the policy's so that the two nets' collectives
+    #    are issued back to back (NCCL executes them in issue order) and their compute overlaps on two streams
+    def _call(self, arena, run, mode, phase, inv_B, ma, world):
+        net = self.net
+        ws = self._workspace('v', lib.sard_value_workspace(C.byref(net), run.n, run.B))
+        ml, _ = self._moments('v', net.tower.D, world)
+        check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), mode, phase, inv_B, ptr(ml), ptr(ma), world,
+                                 self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+
+    def dp_gather(self, arena, run, world):
+        self.GA.zero_()
+        self._call(arena, run, 1, PHASE_GATHER, 0.0, None, 1)
+
+    def dp_allgather(self, comm):
+        ml, ma = self._moments('v', self.net.tower.D, comm.world)
+        comm.allgather(ml, ma)
+
+    def dp_compute(self, arena, run, B_global, world):
+        _, ma = self._moments('v', self.net.tower.D, world)
+        self._call(arena, run, 1, PHASE_COMPUTE, 1.0 / B_global, ma, world)
+
+    def dp_allreduce(self, comm):
+        comm.allreduce(self.GA)
+
     def train_step(self, arena: PackedRollout, run: Run, B_global: int, log_row: Optional[torch.Tensor] = None,
                    comm: Optional[Comm] = None):
         """AgentPG.update_value (agent_pg.py:18-25): forward, MSE, backward, Adam."""
-        opt = self.opt
         self.GA.zero_()
         self.run(arena, run, True, 1.0 / B_global, comm)
         if comm is not None and comm.world > 1:
             comm.allreduce(self.GA)
+        self.adam(B_global, log_row)
+
+    def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None):
+        opt = self.opt
         st = stream()
         check(lib.sard_adam_prepare(ptr(self.GA), 1.0 / B_global, 1.0, 0.0, None, -1.0, 0, 0, 1, opt.betas[0], opt.betas[1],
                                     ptr(opt.ctl_f), ptr(opt.ctl_i), ptr(log_row), st))
@@ -311,11 +338,42 @@ class PolicyEngine(_EngineBase):
         else:
             check(lib.sard_policy_run(*args, phase, clip_eps, inv_B, ptr(ml), None, 1, *tail))
 
+    def dp_gather(self, arena, runs, active_global, world):
+        self.GA.zero_()
+        for s in (2, 1, 0):
+            if runs[s] is not None:
+                self.run_stage(s, arena, runs[s], True, phase=PHASE_GATHER)
+            elif active_global[s]:
+                ml, _ = self._moments(s, self.net.stage[s].tower.D, world)
+                ml.zero_()                # empty record: another rank has graphs of this stage
+
+    def dp_allgather(self, active_global, comm):
+        for s in (2, 1, 0):
+            if active_global[s]:
+                ml, ma = self._moments(s, self.net.stage[s].tower.D, comm.world)
+                comm.allgather(ml, ma)
+
+    def dp_compute(self, arena, runs, active_global, B_global, clip_eps, world):
+        net = self.net
+        for s in (2, 1, 0):
+            if runs[s] is not None:
+                run = runs[s]
+                ws = self._workspace(s, lib.sard_policy_workspace(C.byref(net), s, run.n, run.B))
+                ml, ma = self._moments(s, net.stage[s].tower.D, world)
+                check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, clip_eps,
+                                          1.0 / B_global, ptr(ml), ptr(ma), world, ptr(self.GA), None, None, ptr(ws),
+                                          ws.numel(), stream()))
+            elif active_global[s]:
+                _, ma = self._moments(s, net.stage[s].tower.D, world)
+                self._empty_norm_update(s, ma, world)
+
+    def dp_allreduce(self, comm):
+        comm.allreduce(self.GA)
+
     def train_step(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
                    active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
                    log_row: Optional[torch.Tensor] = None, comm: Optional[Comm] = None):
         """ppo_loss + backward + clip + Adam (transform2act_agent.py:351-358), gated on device (:404-407)."""
-        opt = self.opt
         self.GA.zero_()
         for s in (2, 1, 0):                       # the reference evaluates execution, attribute, skeleton
             if runs[s] is not None:
@@ -330,6 +388,10 @@ class PolicyEngine(_EngineBase):
         if comm is not None and comm.world > 1:
             comm.allreduce(self.GA)
             world = comm.world
+        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row)
+
+    def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None):
+        opt = self.opt
         mask = (1 if any(active_global) else 0) | sum((1 << (1 + s)) for s in range(3) if active_global[s])
         st = stream()
         check(lib.sard_sqnorm(self.GA.data_ptr() + 4 * N_STATS, self.GA.numel() - N_STATS, ptr(self.sq_scratch),

@@ -283,18 +283,41 @@ class Transform2ActAgent:
             for k in range(plan.n_mb):
                 B_glob = int(counts[k, :3].sum())
                 active = [bool(counts[k, s] > 0) for s in range(3)]
-                if self.overlap_nets and comm is None:
+                vrun, pruns = plan.value_run(k), plan.policy_runs(k)
+                skel_nodes = int(counts[k, 3])
+                if world > 1 and self.overlap_nets:
+                    # phases interleaved so both nets' collectives are issued back to back (NCCL runs them in
+                    # issue order) while their compute overlaps on the two streams
                     with torch.cuda.stream(sv):
-                        veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
+                        veng.dp_gather(arena, vrun, world)
                     with torch.cuda.stream(sp):
-                        peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
+                        peng.dp_gather(arena, pruns, active, world)
+                    with torch.cuda.stream(sv):
+                        veng.dp_allgather(comm)
+                    with torch.cuda.stream(sp):
+                        peng.dp_allgather(active, comm)
+                    with torch.cuda.stream(sv):
+                        veng.dp_compute(arena, vrun, B_glob, world)
+                    with torch.cuda.stream(sp):
+                        peng.dp_compute(arena, pruns, active, B_glob, self.clip_epsilon, world)
+                    with torch.cuda.stream(sv):
+                        veng.dp_allreduce(comm)
+                        veng.adam(B_glob, vlog[step])
+                    with torch.cuda.stream(sp):
+                        peng.dp_allreduce(comm)
+                        peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step])
+                elif self.overlap_nets:
+                    with torch.cuda.stream(sv):
+                        veng.train_step(arena, vrun, B_glob, vlog[step], comm)
+                    with torch.cuda.stream(sp):
+                        peng.train_step(arena, pruns, B_glob, skel_nodes, active, self.clip_epsilon,
                                         40.0, self.clip_first_step_only, plog[step], comm)
                 else:
-                    veng.train_step(arena, plan.value_run(k), B_glob, vlog[step], comm)
-                    peng.train_step(arena, plan.policy_runs(k), B_glob, int(counts[k, 3]), active, self.clip_epsilon,
+                    veng.train_step(arena, vrun, B_glob, vlog[step], comm)
+                    peng.train_step(arena, pruns, B_glob, skel_nodes, active, self.clip_epsilon,
                                     40.0, self.clip_first_step_only, plog[step], comm)
                 step += 1
-            if self.overlap_nets and comm is None:
+            if self.overlap_nets:
                 # the next epoch's plan replaces the ordering tensors the in-flight kernels read
                 plans_alive.append(plan)
         main.wait_stream(sv); main.wait_stream(sp)
