@@ -206,7 +206,7 @@ class Transform2ActPolicy(nn.Module):
 
     def select_action(self, x, mean_action=False):
         """Rollout-side sampling (policy.py:339-381); returns ``(action, action_env)`` as float64 numpy."""
-        control_dist, attr_dist, skel_dist, node_design_mask, _, total_num_nodes, _, _, _, device = self.forward(x)
+        control_dist, attr_dist, skel_dist, node_design_mask, _, total_num_nodes, _, cum_attr, _, device = self.forward(x)
         action = torch.zeros(total_num_nodes, self.action_dim, device=device)
         action_env = torch.zeros(total_num_nodes, self.action_dim, device=device)
         cad = self.control_action_dim
@@ -220,14 +220,17 @@ class Transform2ActPolicy(nn.Module):
             a = torch.clamp(a, -1, 1)
             a_env = a
             if self.enable_infer:
-                a_env, a = self.transform_policy_output(a, self.body_ind_attribute, attr=True, attr_select=True)
+                a_env, a = self.transform_policy_output(a, self.body_ind_attribute, attr=True, attr_select=True,
+                                                        num_nodes_cum=cum_attr)
                 self.is_new_morphology = False
             m = node_design_mask['attr_trans'].to(device)
             action[m, cad:-1] = a
             action_env[m, cad:-1] = a_env
         if skel_dist is not None:
             a = skel_dist.mean_sample() if mean_action else skel_dist.sample()
-            a[0] = 0
+            # the reference zeroes a[0] (policy.py:362) and is only ever called with one graph; for a batch the
+            # root of every graph is forced to the no-op
+            a[(self.body_ind_skeleleton == 0).to(a.device)] = 0
             a_env = a
             if self.enable_infer:
                 a_env, a = self.transform_policy_output(a, self.body_ind_skeleleton)
@@ -254,7 +257,7 @@ class Transform2ActPolicy(nn.Module):
                 rep[rows_orb] = np.repeat(rows_rep, len(members))
         return rep
 
-    def transform_policy_output(self, outputs, body_ind, attr=False, attr_select=False):
+    def transform_policy_output(self, outputs, body_ind, attr=False, attr_select=False, num_nodes_cum=None):
         """Orbit tie (+ subgroup symmetrizer on the xy offsets when ``attr_select``), policy.py:421-498.
 
         Host-side utility for rollouts and inspection; the training path applies the tie inside the
@@ -271,8 +274,13 @@ class Transform2ActPolicy(nn.Module):
         if attr_select:
             levels, legs = body_levels_and_legs(body, self.index_base)
             sym = self.group.get_cur_subgroup_symmetrizer()
-            for l in range(1, int(levels.max(initial=0)) + 1):
-                rows = np.flatnonzero(levels == l)
+            # the reference symmetrises all rows of a level at once and is only called with one graph;
+            # with several graphs (num_nodes_cum given) each graph is symmetrised on its own
+            bounds = [0, len(body)] if num_nodes_cum is None else [0] + [int(c) for c in num_nodes_cum]
+            graph_of = np.repeat(np.arange(len(bounds) - 1), np.diff(bounds))
+            work = [(g, l) for g in range(len(bounds) - 1) for l in range(1, int(levels.max(initial=0)) + 1)]
+            for g, l in work:
+                rows = np.flatnonzero((levels == l) & (graph_of == g))
                 if len(rows) == 0:
                     continue
                 leg0 = legs[rows] - 1

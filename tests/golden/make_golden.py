@@ -312,12 +312,39 @@ def make_case(tag, subgroup_name, orbits_key, seed, shape, T=96, mini_batch=32, 
     print(f'case_{tag}.npz written: {len(out)} arrays, valid={valid}, kl={log["approx_kl"]:.4f}')
 
 
+def symmetrizer_cases():
+    """transform_policy_output with attr_select=True (orbit tie + subgroup symmetrizer, policy.py:421-498)."""
+    from design_opt.models.transform2act_policy import Transform2ActPolicy
+    from sard_b200 import synthetic
+    shape = synthetic.EnvShape('golden_b', sim_obs_dim=4, hfield_dim=1, obj_dim=1, goal_dim=3)
+    pol_specs, _ = small_cfg()
+    out = {}
+    names = ['H_4>0>H_4>4', 'H_2>1>H_1>4', 'H_2>2>H_1>4', 'K_1>0>K_1>4', 'H_1_0>0>H_1_0>4', 'K_0>1>H_2_0>4']
+    for i, name in enumerate(names):
+        torch.manual_seed(100 + i)
+        np.random.seed(100 + i)
+        agent = StubAgent(StubCfg(name, pol_specs, None), shape)
+        policy = Transform2ActPolicy(pol_specs, agent)
+        _, body, _, _ = synthetic.make_ant_graph((2, 2, 2, 2), shape)       # symmetric under every subgroup of D_4
+        x = torch.randn(len(body), 6)
+        env_out, orbit_out = policy.transform_policy_output(x.clone(), body, attr=True, attr_select=True)
+        tie_only, _ = policy.transform_policy_output(x.clone(), body, attr=True)
+        sk = torch.randint(0, 3, (len(body),))
+        sk_out, _ = policy.transform_policy_output(sk.clone(), body)
+        out[f'{i}.x'] = x.numpy(); out[f'{i}.body'] = body; out[f'{i}.env'] = env_out.numpy(); out[f'{i}.orbit'] = orbit_out.numpy()
+        out[f'{i}.tie'] = tie_only.numpy(); out[f'{i}.skel_in'] = sk.numpy(); out[f'{i}.skel_out'] = sk_out.numpy()
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, 'symmetrizer.npz'), **out)
+    print('symmetrizer.npz written')
+
+
 def main():
     install_shims()
     torch.set_default_dtype(torch.float64)      # design_opt/train.py:51
     torch.set_num_threads(1)
     from sard_b200 import synthetic
     group_tables()
+    symmetrizer_cases()
     shp_a = synthetic.EnvShape('golden_a', sim_obs_dim=5, hfield_dim=7, obj_dim=3, goal_dim=2)
     shp_b = synthetic.EnvShape('golden_b', sim_obs_dim=4, hfield_dim=1, obj_dim=1, goal_dim=3)
     make_case('trivial', 'H_4>0>H_4>4', 'H_4', 11, shp_a)

@@ -1,0 +1,141 @@
+"""GPU: drop-in API behaviour around the hot path -- every env's observation shape, batched
+select_action, device round trips of the modules (the reference moves the nets to the CPU for
+sampling) and checkpoint interchange."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+def make_agent(shape, subgroup='H_4>0>H_4>4', seed=0, T=96, M=32):
+    from sard_b200 import synthetic
+    from sard_b200.transform2act_agent import Transform2ActAgent
+    torch.manual_seed(seed)
+    ag = Transform2ActAgent(small_config(subgroup, M, 2, T), torch.float32, 'cuda', 0, 1, env=synthetic.SyntheticEnv(shape))
+    with torch.no_grad():
+        for nm in ('skel', 'attr', 'control'):
+            lin = getattr(ag.policy_net, f'{nm}_ind_mlp').linear
+            lin.b.add_(0.05 * torch.randn_like(lin.b))
+    return ag
+
+
+def oracle_of(ag, shape):
+    from oracle import sard_oracle as O
+    psd = {k: v.detach().cpu().double().clone() for k, v in ag.policy_net.state_dict().items()}
+    vsd = {k: v.detach().cpu().double().clone() for k, v in ag.value_net.state_dict().items()}
+    spec = O.Spec(attr_fixed_dim=shape.attr_fixed_dim, index_base=shape.index_base,
+                  embeds=ag.policy_net.group.get_cur_subgroup_embeds().double(),
+                  orbits={int(k): [int(x) for x in v] for k, v in ag.policy_net.group.get_cur_orbits().items()})
+    return O, psd, vsd, spec
+
+
+def lists_of(roll):
+    b = roll.to_traj_batch()
+    states = [[torch.tensor(x) if i in (0, 1, 5, 6, 7) else x for i, x in enumerate(s)] for s in b.states]
+    return b, states, [torch.tensor(a) for a in b.actions]
+
+
+@pytest.mark.parametrize('env', ['point_nav', 'patrol', 'locomotion_ft', 'locomotion_vt', 'escape', 'manipulation_box'])
+def test_all_six_env_shapes_forward_parity(env, cuda_device):
+    """Values and log-probs for every SARD env's observation layout (hfield 1410, obj 12, goal 3, S 41/54)."""
+    from sard_b200 import synthetic
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES[env]
+    ag = make_agent(shape)
+    roll = synthetic.generate_rollout(shape, 96, seed=21, min_exec=8, max_exec=25, dtype=np.float32)
+    for f in ('obs', 'hfield', 'obj', 'goal', 'actions', 'rewards', 'masks'):
+        setattr(roll, f, getattr(roll, f).astype(np.float64))
+    O, psd, vsd, spec = oracle_of(ag, shape)
+    b, states, actions = lists_of(roll)
+    ag.policy_net.train(); ag.value_net.train()        # train mode: RunningNorm update, then normalised forward
+    with torch.no_grad():
+        want_lp = O.policy_log_prob(psd, spec, states, actions, training=True)
+        want_v = O.value_forward(vsd, spec, states, training=True)
+    got_lp = ag.policy_net.get_log_prob(b.states, b.actions)
+    got_v = ag.value_net(b.states)
+    assert_close(got_lp.cpu(), want_lp, rtol=1e-4, atol=3e-4, what=f'{env} log_prob')
+    assert_close(got_v.cpu(), want_v, rtol=1e-4, atol=5e-5, what=f'{env} value')
+    for k in ('control_norm.mean', 'control_norm.var'):
+        assert_close(ag.policy_net.state_dict()[k].cpu(), psd[k], rtol=1e-4, atol=1e-6, what=k)
+
+
+def test_select_action_batched_equals_per_state(cuda_device):
+    from sard_b200 import synthetic
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['point_nav']
+    ag = make_agent(shape, 'K_1>0>K_1>4')
+    roll = synthetic.generate_rollout(shape, 40, seed=8, orbits=synthetic.SYMMETRIC_ORBITS['K_1'], min_exec=4, max_exec=10)
+    b = roll.to_traj_batch()
+    ag.policy_net.eval()
+    act, act_env = ag.policy_net.select_action(b.states, mean_action=True)
+    assert act.shape == (roll.obs.shape[0], 8) and act.dtype == np.float64
+    at = 0
+    for t, s in enumerate(b.states):
+        a1, e1 = ag.policy_net.select_action([s], mean_action=True)
+        n = a1.shape[0]
+        assert_close(act[at:at + n], a1, rtol=1e-5, atol=1e-6, what=f'state {t} action')
+        assert_close(act_env[at:at + n], e1, rtol=1e-5, atol=1e-6, what=f'state {t} action_env')
+        st = int(s[2][0])
+        if st == 2:
+            assert np.all(a1[:, 1:] == 0)
+        elif st == 1:
+            assert np.all(np.abs(a1[:, 1:7]) <= 1) and np.all(a1[:, 0] == 0) and np.all(a1[:, 7] == 0)
+            # tied columns (offset_z, gear, size) are equal inside an orbit of K_1: legs {1,2} and {3,4}
+            body = np.asarray(s[4])
+            for lvl_legs in ((1, 2), (3, 4), (6, 7), (8, 9)):
+                rows = [int(np.flatnonzero(body == x)[0]) for x in lvl_legs if np.any(body == x)]
+                if len(rows) == 2:
+                    assert_close(a1[rows[0], 3:6], a1[rows[1], 3:6], rtol=0, atol=1e-7, what='orbit tie')
+        at += n
+
+
+def test_modules_survive_cpu_round_trip(cuda_device):
+    from sard_b200 import synthetic
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['manipulation_box']
+    ag = make_agent(shape)
+    roll = synthetic.generate_rollout(shape, 48, seed=2, min_exec=5, max_exec=12)
+    b = roll.to_traj_batch()
+    ag.policy_net.eval(); ag.value_net.eval()
+    lp0, v0 = ag.policy_net.get_log_prob(b.states, b.actions).clone(), ag.value_net(b.states).clone()
+    ag.policy_net.to('cpu'); ag.value_net.to('cpu')            # khrylib/utils/torch.py:15-29 (to_cpu for samplers)
+    with pytest.raises(Exception):
+        ag.policy_net.get_log_prob(b.states, b.actions)        # no CPU implementation: must fail loudly
+    ag.policy_net.to('cuda'); ag.value_net.to('cuda')
+    assert torch.equal(ag.policy_net.get_log_prob(b.states, b.actions), lp0)
+    assert torch.equal(ag.value_net(b.states), v0)
+    secs, log = ag.update_params(roll)                          # and the training path still works afterwards
+    assert np.isfinite(log['surr_loss'])
+
+
+def test_checkpoint_interchange(tmp_path, cuda_device):
+    from sard_b200 import synthetic
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['point_nav']
+    ag = make_agent(shape, seed=1)
+    roll = synthetic.generate_rollout(shape, 96, seed=5, min_exec=6, max_exec=20)
+    ag.update_params(roll)
+    path = os.path.join(tmp_path, 'cp.p')
+    ag.save_checkpoint_to(path, epoch=3)
+    cp = pickle.load(open(path, 'rb'))
+    assert set(cp) == {'policy_dict', 'value_dict', 'running_state', 'loss_iter', 'best_rewards', 'epoch', 'symmetry'}
+    keys = set(cp['policy_dict'])
+    for k in ('control_action_log_std', 'attr_action_log_std', 'hfield_enc.enc.0.weight', 'goal_enc.enc.2.bias', 'skel_norm.n',
+              'control_gnn.in_fc.weight', 'attr_gnn.gconv_layers.2.lin_l.bias', 'attr_gnn.gconv_layers.0.lin_r.weight',
+              'control_ind_mlp.affine_layers.1.W', 'skel_ind_mlp.linear.b'):
+        assert k in keys, k
+    assert not any(k.endswith('.inv') for k in keys)            # scratch buffers are not persisted
+    assert set(cp['value_dict']) >= {'norm.mean', 'gnn.in_fc.bias', 'mlp.affine_layers.1.weight', 'value_head.weight'}
+    ag2 = make_agent(shape, seed=9)
+    ag2.load_checkpoint(path)
+    b = roll.to_traj_batch()
+    for a in (ag, ag2):
+        a.policy_net.eval(); a.value_net.eval()
+    assert torch.equal(ag.policy_net.get_log_prob(b.states, b.actions), ag2.policy_net.get_log_prob(b.states, b.actions))
+    assert torch.equal(ag.value_net(b.states), ag2.value_net(b.states))

@@ -75,3 +75,34 @@ def test_survey_known_answers():
     G.set_cur_subgroup_name('H_2>1>H_1>4')
     np.testing.assert_allclose(G.get_cur_subgroup_embeds().numpy(), [1 / 3, 1 / 6, 1 / 3, 1 / 6, 0, 0, 0, 0], atol=1e-6)
     assert G.leg_representatives(5).tolist() == [0, 1, 1, 1, 1]
+
+
+def test_transform_policy_output_matches_reference_goldens():
+    """Orbit tie + subgroup symmetrizer of the rollout path (policy.py:421-498), host utility (CPU tensors)."""
+    import torch
+    from sard_b200 import synthetic
+    from sard_b200.transform2act_policy import Transform2ActPolicy
+    from tests.util import small_config
+    z = np.load(os.path.join(GOLDEN, 'symmetrizer.npz'))
+    shape = synthetic.EnvShape('golden_b', sim_obs_dim=4, hfield_dim=1, obj_dim=1, goal_dim=3)
+
+    class A:
+        pass
+    for i, name in enumerate(z['names']):
+        cfg = small_config(str(name))
+        agent = A()
+        agent.cfg = cfg
+        agent.env = synthetic.SyntheticEnv(shape)
+        for k in ('attr_fixed_dim', 'sim_obs_dim', 'attr_design_dim', 'control_action_dim', 'skel_num_action',
+                  'sim_obs_hfield_dim', 'sim_obs_obj_dim', 'sim_obs_goal_dim'):
+            setattr(agent, k, getattr(agent.env, k))
+        agent.state_dim = shape.state_dim
+        policy = Transform2ActPolicy(cfg.policy_specs, agent)
+        x, body = torch.from_numpy(z[f'{i}.x']), z[f'{i}.body']
+        env_out, orbit_out = policy.transform_policy_output(x.clone(), body, attr=True, attr_select=True)
+        np.testing.assert_allclose(env_out.numpy(), z[f'{i}.env'], atol=1e-12, err_msg=str(name))
+        np.testing.assert_allclose(orbit_out.numpy(), z[f'{i}.orbit'], atol=1e-12, err_msg=str(name))
+        tie, _ = policy.transform_policy_output(x.clone(), body, attr=True)
+        np.testing.assert_allclose(tie.numpy(), z[f'{i}.tie'], atol=0, err_msg=str(name))
+        sk, _ = policy.transform_policy_output(torch.from_numpy(z[f'{i}.skel_in']), body)
+        assert np.array_equal(sk.numpy(), z[f'{i}.skel_out']), name
