@@ -43,6 +43,12 @@ int sard_struct_sizes(int* out, int capacity);
 /* Kernels launched by the library since load (monotonic; host counter). */
 long long sard_launch_count(void);
 
+/* Programmatic dependent launch for every kernel of the library (default 1): a kernel's CTAs may be
+ * scheduled while its predecessor on the stream drains; they wait for its completion before touching
+ * memory, so results are unchanged.  0 = plain stream-ordered launches. */
+int sard_set_pdl(int enabled);
+int sard_get_pdl(void);
+
 /* Per-call-site kernel timing for the roofline numbers (CUDA events on the launching stream).
  * Sites label the GEMM / aggregate launches of the network schedules: site = 3*kind + pass with
  * kind in {0 in_fc, 1 graphconv, 2 index-linear, 3 obs-encoder, 4 critic mlp, 5 value head, 6 csr aggregate}

@@ -105,6 +105,8 @@ _PROTOS = {
     'sard_last_error_string': (C.c_char_p, []),
     'sard_struct_sizes': (ci, [P(ci), ci]),
     'sard_launch_count': (cll, []),
+    'sard_set_pdl': (ci, [ci]),
+    'sard_get_pdl': (ci, []),
     'sard_prof_enable': (ci, [C.c_uint, ci]),
     'sard_prof_collect': (ci, [P(cd), ci]),
     'sard_build_csr': (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
@@ -180,6 +182,8 @@ def check_struct_sizes():
 
 
 check_struct_sizes()
+if os.environ.get('SARD_PDL') is not None:               # 1 = programmatic dependent launch (default), 0 = off
+    lib.sard_set_pdl(int(os.environ['SARD_PDL']))
 if os.environ.get('SARD_GEMM_ENGINE') is not None:       # 0 = fp32 FFMA, 1 = tcgen05 3xTF32
     lib.sard_set_gemm_engine(int(os.environ['SARD_GEMM_ENGINE']))
 

@@ -34,6 +34,35 @@ struct ProfScope {
       return sard_set_error("launch %s failed: %s", name, cudaGetErrorString(e__));          \
   } while (0)
 
+// Programmatic dependent launch (sm_90+): every kernel of this library is launched with the programmatic
+// stream-serialization attribute and opens with pdl_sync() = griddepcontrol.wait, so the launch of kernel
+// k+1 is processed while kernel k drains and its CTAs start the moment k's last CTA exits (the implicit
+// trigger).  Measured on the 50 k-transition update (two streams): 319 -> 296 ms.  An EARLY trigger
+// (griddepcontrol.launch_dependents at kernel entry) was measured too and is worse (376 ms): the parked
+// CTAs of k+1 hold shared memory and registers that the other stream's kernels need.
+// Launched without the attribute (sard_set_pdl(0)) the wait is a no-op.
+extern int g_sard_pdl;
+__device__ __forceinline__ void pdl_sync() {
+#ifdef SARD_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... P, typename... A>
+static inline void sard_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_sard_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);   // errors surface through SARD_LAUNCH_OK
+}
+
 #define SARD_REQUIRE(cond, msg)                                                              \
   do {                                                                                       \
     if (!(cond)) return sard_set_error("%s:%d requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \

@@ -12,6 +12,7 @@
 #define ENC_BROWS 32
 
 __global__ void __launch_bounds__(256) enc_fwd_kernel(const EncFwdP p) {
+  pdl_sync();
   __shared__ float W2s[ENC_H][ENC_H + 1];
   __shared__ float h1[ENC_ROWS][ENC_H + 1];
   __shared__ float xs[ENC_ROWS][ENC_KMAX];
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) enc_fwd_kernel(const EncFwdP p) {
 #define ENC_PART (ENC_H * ENC_H + ENC_H + ENC_H * ENC_KMAX + ENC_H)
 
 __global__ void __launch_bounds__(256) enc_bwd_kernel(const EncBwdP p) {
+  pdl_sync();
   __shared__ float dz[ENC_BROWS][ENC_H + 1];      // dext tile (relu' already applied by the producer)
   __shared__ float es[ENC_BROWS][ENC_H + 1];      // e1 tile, later de1
   __shared__ float W2s[ENC_H][ENC_H + 1];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) enc_bwd_kernel(const EncBwdP p) {
 }
 
 __global__ void enc_bwd_reduce_kernel(const EncBwdP p, int n_chunks) {
+  pdl_sync();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ENC_PART) return;
   const int k = p.enc_list[blockIdx.y];
@@ -163,7 +166,7 @@ long long sard_enc_partials_floats(int B, int n_enc) { return (long long)ceil_di
 int sard_enc_fwd_launch(const EncFwdP& p, cudaStream_t st) {
   if (p.n_enc <= 0 || p.B <= 0) return 0;
   dim3 grid(ceil_div(p.B, ENC_ROWS), p.n_enc);
-  enc_fwd_kernel<<<grid, 256, 0, st>>>(p);
+  sard_launch(enc_fwd_kernel, grid, 256, 0, st, p);
   SARD_LAUNCH_OK("enc_fwd_kernel");
   return 0;
 }
@@ -172,10 +175,10 @@ int sard_enc_bwd_launch(const EncBwdP& p, cudaStream_t st) {
   if (p.n_enc <= 0 || p.B <= 0) return 0;
   const int n_chunks = ceil_div(p.B, ENC_BROWS);
   dim3 grid(n_chunks, p.n_enc);
-  enc_bwd_kernel<<<grid, 256, 0, st>>>(p);
+  sard_launch(enc_bwd_kernel, grid, 256, 0, st, p);
   SARD_LAUNCH_OK("enc_bwd_kernel");
   dim3 rgrid(ceil_div(ENC_PART, 256), p.n_enc);
-  enc_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(p, n_chunks);
+  sard_launch(enc_bwd_reduce_kernel, rgrid, 256, 0, st, p, n_chunks);
   SARD_LAUNCH_OK("enc_bwd_reduce_kernel");
   return 0;
 }

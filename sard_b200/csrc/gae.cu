@@ -48,6 +48,7 @@ __device__ __forceinline__ Aff block_suffix_scan(Aff mine, Aff* sh) {
 
 template <typename T>
 __global__ void gae_block_maps(const T* r, const T* m, const T* v, int Tn, double gamma, double gt, double* blk) {
+  pdl_sync();
   __shared__ Aff sh[GAE_THREADS];
   const int s = blockIdx.x * GAE_PER_BLOCK + threadIdx.x * GAE_PER_THREAD;
   const int e = min(Tn, s + GAE_PER_THREAD);
@@ -57,6 +58,7 @@ __global__ void gae_block_maps(const T* r, const T* m, const T* v, int Tn, doubl
 }
 
 __global__ void gae_block_carry(int nblk, const double* blk, double* carry) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double c = 0.0;
   for (int b = nblk - 1; b >= 0; --b) {
@@ -68,6 +70,7 @@ __global__ void gae_block_carry(int nblk, const double* blk, double* carry) {
 template <typename T>
 __global__ void gae_apply(const T* r, const T* m, const T* v, int Tn, double gamma, double gt, const double* carry,
                           T* adv, T* ret, double* blk_sum) {
+  pdl_sync();
   __shared__ Aff sh[GAE_THREADS];
   __shared__ double red[GAE_THREADS];
   const int s0 = blockIdx.x * GAE_PER_BLOCK + threadIdx.x * GAE_PER_THREAD;
@@ -99,6 +102,7 @@ __global__ void gae_apply(const T* r, const T* m, const T* v, int Tn, double gam
 
 template <typename T>
 __global__ void gae_var_partial(const T* adv, int Tn, int nblk, const double* blk_sum, double* blk_sq) {
+  pdl_sync();
   __shared__ double red[GAE_THREADS];
   __shared__ double mean_s;
   if (threadIdx.x == 0) {
@@ -125,6 +129,7 @@ __global__ void gae_var_partial(const T* adv, int Tn, int nblk, const double* bl
 
 template <typename T>
 __global__ void gae_normalise(T* adv, int Tn, int nblk, const double* blk_sum, const double* blk_sq) {
+  pdl_sync();
   __shared__ double mean_s, inv_std_s;
   if (threadIdx.x == 0) {
     double s = 0.0, q = 0.0;
@@ -149,15 +154,15 @@ static int gae_impl(const T* rewards, const T* masks, const T* values, int Tn, d
   double* blk_sum = carry + nblk;        // [nblk]  (blk is dead after gae_block_carry and is reused for blk_sq)
   double* blk_sq = blk;
   const double gt = gamma * tau;
-  gae_block_maps<T><<<nblk, GAE_THREADS, 0, st>>>(rewards, masks, values, Tn, gamma, gt, blk);
+  sard_launch(gae_block_maps<T>, nblk, GAE_THREADS, 0, st, rewards, masks, values, Tn, gamma, gt, blk);
   SARD_LAUNCH_OK("gae_block_maps");
-  gae_block_carry<<<1, 32, 0, st>>>(nblk, blk, carry);
+  sard_launch(gae_block_carry, 1, 32, 0, st, nblk, blk, carry);
   SARD_LAUNCH_OK("gae_block_carry");
-  gae_apply<T><<<nblk, GAE_THREADS, 0, st>>>(rewards, masks, values, Tn, gamma, gt, carry, advantages, returns, blk_sum);
+  sard_launch(gae_apply<T>, nblk, GAE_THREADS, 0, st, rewards, masks, values, Tn, gamma, gt, carry, advantages, returns, blk_sum);
   SARD_LAUNCH_OK("gae_apply");
-  gae_var_partial<T><<<nblk, GAE_THREADS, 0, st>>>(advantages, Tn, nblk, blk_sum, blk_sq);
+  sard_launch(gae_var_partial<T>, nblk, GAE_THREADS, 0, st, advantages, Tn, nblk, blk_sum, blk_sq);
   SARD_LAUNCH_OK("gae_var_partial");
-  gae_normalise<T><<<nblk, GAE_THREADS, 0, st>>>(advantages, Tn, nblk, blk_sum, blk_sq);
+  sard_launch(gae_normalise<T>, nblk, GAE_THREADS, 0, st, advantages, Tn, nblk, blk_sum, blk_sq);
   SARD_LAUNCH_OK("gae_normalise");
   return 0;
 }

@@ -11,6 +11,7 @@
 // fp32 FFMA is used because the parity target is rtol 1e-4 against an fp64 oracle; see DESIGN.md
 // for the tcgen05 3xTF32 plan.
 #include "common.cuh"
+#include <stdlib.h>
 
 // Shared epilogue of both engines, executed from a ROLLED loop over a tile staged in shared memory:
 // one copy of the bias / activation / sin / act' / scatter code per kernel (keeps the SASS small enough
@@ -30,6 +31,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const SardGemm& g, float v, 
 template <int BM, int BN, int BK, int TM, int TN, bool NT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_kernel(const SardGemm g) {
+  pdl_sync();
   constexpr int NTH = (BM / TM) * (BN / TN);
   constexpr int EA = BM * BK / NTH;
   constexpr int EB = BN * BK / NTH;
@@ -192,18 +194,18 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
     const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
     if (tiles <= 0) return 0;
     dim3 grid(tiles, ceil_div(g->N, BN));
-    gemm_kernel<BM, BN, 16, 4, 2, NT><<<grid, 256, 0, st>>>(*g);
+    sard_launch(gemm_kernel<BM, BN, 16, 4, 2, NT>, grid, 256, 0, st, *g);
   } else if (!g->tiles && (long long)ceil_div(g->M, 128) * ceil_div(g->N, 64) < 2 * 148) {
     // few large tiles would leave most of the 148 SMs idle: use 64x64 tiles (4x the CTAs)
     constexpr int BM = 64, BN = 64;
     dim3 grid(ceil_div(g->M, BM), ceil_div(g->N, BN));
-    gemm_kernel<BM, BN, 16, 4, 4, NT><<<grid, 256, 0, st>>>(*g);
+    sard_launch(gemm_kernel<BM, BN, 16, 4, 4, NT>, grid, 256, 0, st, *g);
   } else {
     constexpr int BM = 128, BN = 64;
     const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, BM);
     if (tiles <= 0) return 0;
     dim3 grid(tiles, ceil_div(g->N, BN));
-    gemm_kernel<BM, BN, 16, 8, 4, NT><<<grid, 256, 0, st>>>(*g);
+    sard_launch(gemm_kernel<BM, BN, 16, 8, 4, NT>, grid, 256, 0, st, *g);
   }
   SARD_LAUNCH_OK(NT ? "gemm_kernel<fwd>" : "gemm_kernel<bwd_data>");
   return 0;
@@ -218,6 +220,7 @@ extern "C" int sard_linear_bwd_data(const SardGemm* g, sard_stream_t stream) { r
 template <int B1, int B2, int BKM, int T1, int T2>
 __global__ void __launch_bounds__((B1 / T1) * (B2 / T2))
 wgrad_kernel(const SardWGrad w) {
+  pdl_sync();
   constexpr int NTH = (B1 / T1) * (B2 / T2);
   constexpr int EP = B1 * BKM / NTH, EQ = B2 * BKM / NTH;
   __shared__ __align__(16) float Ps[2][BKM][B1 + 4];
@@ -318,6 +321,7 @@ wgrad_kernel(const SardWGrad w) {
 // the 8 slice sums are added in slice order -> deterministic, ~8x shorter latency chain.
 #define WR_SLICES 8
 __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
+  pdl_sync();
   __shared__ float part[WR_SLICES][33];
   const int ldpart = w.N2 + 1;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -369,9 +373,15 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
 // 16 rows each (the partial products are reduced in chunk order afterwards).
 extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
   const bool fast = N1 % 64 == 0 && N2 % 128 == 0;          // wgrad_fast_kernel tiles: (64|128) x 128
+  if (N1 <= 8) {                                             // wgrad_skinny_kernel: rows are streamed once per 128 columns
+    long long rows = ((long long)M * ceil_div(N2, 128) + 591) / 592;
+    rows = (rows + 15) / 16 * 16;
+    return (int)(rows < 32 ? 32 : (rows > 1024 ? 1024 : rows));
+  }
   const long long tiles = fast ? (long long)(N1 % 128 == 0 ? N1 / 128 : N1 / 64) * (N2 / 128)
                                : (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
-  long long chunks = (2 * 148 + tiles - 1) / tiles;
+  static const int waves = getenv("SARD_WG_WAVES") ? atoi(getenv("SARD_WG_WAVES")) : 2;   // tuning knob
+  long long chunks = ((long long)waves * 148 + tiles - 1) / tiles;
   if (chunks < 1) chunks = 1;
   long long rows = (M + chunks - 1) / chunks;
   rows = (rows + 15) / 16 * 16;
@@ -411,16 +421,16 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
     // partial products already launched (tensor cores or the fast SIMT kernel)
   } else if (w->N1 <= 16) {
     dim3 grid(nchunks, 1, ceil_div(w->N2, 64));
-    wgrad_kernel<16, 64, 16, 4, 4><<<grid, 64, 0, st>>>(*w);
+    sard_launch(wgrad_kernel<16, 64, 16, 4, 4>, grid, 64, 0, st, *w);
   } else {
     dim3 grid(nchunks, ceil_div(w->N1, 64), ceil_div(w->N2, 64));
-    wgrad_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(*w);
+    sard_launch(wgrad_kernel<64, 64, 16, 4, 4>, grid, 256, 0, st, *w);
   }
   if (umma_rc != 0) SARD_LAUNCH_OK("wgrad_kernel");
   int rblocks = ceil_div((long long)w->N1 * (w->N2 + 1), 32);
   if (w->grp_chunk_ptr && rblocks > 64) rblocks = 64;
   dim3 rgrid(rblocks, w->grp_chunk_ptr ? w->n_groups : 1);
-  wgrad_reduce_kernel<<<rgrid, 32 * WR_SLICES, 0, st>>>(*w, w->chunks ? 0 : nchunks);
+  sard_launch(wgrad_reduce_kernel, rgrid, 32 * WR_SLICES, 0, st, *w, w->chunks ? 0 : nchunks);
   SARD_LAUNCH_OK("wgrad_reduce_kernel");
   return 0;
 }

@@ -11,6 +11,7 @@ struct AggP {
 };
 
 __global__ void csr_aggregate_kernel(const AggP p) {
+  pdl_sync();
   const long long total = (long long)p.n * p.F4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -47,7 +48,7 @@ extern "C" int sard_csr_aggregate(const float* in, int ld_in, float* out, int ld
   // algorithmic bytes: read the feature rows once, write them once, plus the index arrays (2 n F 4 + (n+1+e) 4,
   // e = 2(n - graphs) for trees ~ 2n)
   ProfScope prof(as_stream(stream), (double)n * F, 4.0 * ((2.0 + (base ? 1.0 : 0.0) + (yprev ? 1.0 : 0.0)) * (double)n * F + 5.0 * n));
-  csr_aggregate_kernel<<<grid_for((long long)n * (F / 4), 256, 16), 256, 0, as_stream(stream)>>>(p);
+  sard_launch(csr_aggregate_kernel, grid_for((long long)n * (F / 4), 256, 16), 256, 0, as_stream(stream), p);
   SARD_LAUNCH_OK("csr_aggregate_kernel");
   return 0;
 }
@@ -56,6 +57,7 @@ extern "C" int sard_csr_aggregate(const float* in, int ld_in, float* out, int ld
 __global__ void concat_sorted_kernel(const float* __restrict__ h, int ld_h, int Fh4, const float* __restrict__ ext,
                                      int ld_ext, int Fe4, const int* __restrict__ srow,
                                      const int* __restrict__ nd_graph, int n, float* __restrict__ xs, int ld_xs) {
+  pdl_sync();
   const int W4 = Fh4 + Fe4;
   const long long total = (long long)n * W4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -74,7 +76,7 @@ extern "C" int sard_concat_sorted(const float* h, int ld_h, int Fh, const float*
                                   sard_stream_t stream) {
   if (n <= 0) return 0;
   SARD_REQUIRE(Fh % 4 == 0 && Fe % 4 == 0 && ld_h % 4 == 0 && ld_ext % 4 == 0 && ld_xs % 4 == 0, "concat: multiples of 4");
-  concat_sorted_kernel<<<grid_for((long long)n * ((Fh + Fe) / 4), 256, 16), 256, 0, as_stream(stream)>>>(
+  sard_launch(concat_sorted_kernel, grid_for((long long)n * ((Fh + Fe) / 4), 256, 16), 256, 0, as_stream(stream), 
       h, ld_h, Fh / 4, ext, ld_ext, Fe / 4, srow, nd_graph, n, xs, ld_xs);
   SARD_LAUNCH_OK("concat_sorted_kernel");
   return 0;
@@ -88,6 +90,7 @@ __global__ void unsort_grad_kernel(const float* __restrict__ dxs, int ld_dxs, co
                                    float* __restrict__ dh, int ld_dh,
                                    const float* __restrict__ ext, int ld_ext, int Fe,
                                    float* __restrict__ dext, int ld_dext) {
+  pdl_sync();
   const int W4 = (Fh + Fe) >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int g = (int)(idx / W4), c = (int)(idx - (long long)g * W4) * 4;
@@ -122,7 +125,7 @@ extern "C" int sard_unsort_grad(const float* dxs, int ld_dxs, const int* spos, c
   if (B <= 0) return 0;
   SARD_REQUIRE(Fh % 4 == 0 && Fe % 4 == 0 && ld_dxs % 4 == 0 && ld_h % 4 == 0 && ld_dh % 4 == 0 && ld_ext % 4 == 0 && ld_dext % 4 == 0,
                "unsort_grad: widths / strides must be multiples of 4");
-  unsort_grad_kernel<<<ceil_div((long long)B * ((Fh + Fe) / 4), 256), 256, 0, as_stream(stream)>>>(
+  sard_launch(unsort_grad_kernel, ceil_div((long long)B * ((Fh + Fe) / 4), 256), 256, 0, as_stream(stream), 
       dxs, ld_dxs, spos, cum, node_base, B, h, ld_h, Fh, h_act, dh, ld_dh, ext, ld_ext, Fe, dext, ld_dext);
   SARD_LAUNCH_OK("unsort_grad_kernel");
   return 0;

@@ -23,6 +23,7 @@ __device__ __forceinline__ float ppo_dlp(float lp, float fixed, float adv, float
 }
 
 __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
+  pdl_sync();
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= a.B) return;
   const int gid = a.ids[g];
@@ -102,12 +103,13 @@ extern "C" int sard_gauss_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   if (a->B <= 0) return 0;
   SARD_REQUIRE(a->d >= 1 && a->d <= MAXD, "gauss loss: action dims");
   SARD_REQUIRE(a->log_std != nullptr, "gauss loss: log_std");
-  gauss_loss_kernel<<<ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream)>>>(*a);
+  sard_launch(gauss_loss_kernel, ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream), *a);
   SARD_LAUNCH_OK("gauss_loss_kernel");
   return 0;
 }
 
 __global__ void cat_loss_kernel(const SardPolicyLoss a) {
+  pdl_sync();
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= a.B) return;
   const int gid = a.ids[g];
@@ -205,7 +207,7 @@ __global__ void cat_loss_kernel(const SardPolicyLoss a) {
 extern "C" int sard_cat_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   if (a->B <= 0) return 0;
   SARD_REQUIRE(a->d >= 2 && a->d <= MAXD, "cat loss: number of actions");
-  cat_loss_kernel<<<ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream)>>>(*a);
+  sard_launch(cat_loss_kernel, ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream), *a);
   SARD_LAUNCH_OK("cat_loss_kernel");
   return 0;
 }
@@ -213,6 +215,7 @@ extern "C" int sard_cat_loss(const SardPolicyLoss* a, sard_stream_t stream) {
 // one block per column, rows strided over threads, fixed-order tree: deterministic
 __global__ void loss_reduce_kernel(const float* __restrict__ gstat, int B, int W, float* __restrict__ stats,
                                    float* __restrict__ dlogstd, int d, const float* __restrict__ log_std) {
+  pdl_sync();
   __shared__ float red[256];
   const int c = blockIdx.x;
   float s = 0.f;
@@ -237,7 +240,7 @@ __global__ void loss_reduce_kernel(const float* __restrict__ gstat, int B, int W
 extern "C" int sard_loss_reduce(const float* gstat, int B, int W, float* stats, float* dlogstd, int d,
                                 const float* log_std_for_entropy, sard_stream_t stream) {
   if (W <= 0) return 0;
-  loss_reduce_kernel<<<W, 256, 0, as_stream(stream)>>>(gstat, B, W, stats, dlogstd, d, log_std_for_entropy);
+  sard_launch(loss_reduce_kernel, W, 256, 0, as_stream(stream), gstat, B, W, stats, dlogstd, d, log_std_for_entropy);
   SARD_LAUNCH_OK("loss_reduce_kernel");
   return 0;
 }
@@ -245,6 +248,7 @@ extern "C" int sard_loss_reduce(const float* gstat, int B, int W, float* stats, 
 __global__ void value_loss_kernel(const float* __restrict__ v, const int* __restrict__ ids, int B,
                                   const float* __restrict__ returns, float inv_B, float* __restrict__ dv,
                                   float* __restrict__ sq_err, float* __restrict__ values_out) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int gid = ids[b];
@@ -260,7 +264,7 @@ __global__ void value_loss_kernel(const float* __restrict__ v, const int* __rest
 extern "C" int sard_value_loss(const float* v, const int* ids, int B, const float* returns, float inv_B,
                                float* dv, float* sq_err, float* values_out, sard_stream_t stream) {
   if (B <= 0) return 0;
-  value_loss_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(v, ids, B, returns, inv_B, dv, sq_err, values_out);
+  sard_launch(value_loss_kernel, ceil_div(B, 256), 256, 0, as_stream(stream), v, ids, B, returns, inv_B, dv, sq_err, values_out);
   SARD_LAUNCH_OK("value_loss_kernel");
   return 0;
 }

@@ -13,6 +13,7 @@
 #define NORM_SUB 4
 __global__ void norm_moments_kernel(const float* __restrict__ x, int ldx, int n, int D,
                                     float* __restrict__ partials) {
+  pdl_sync();
   extern __shared__ float sm[];                    // [NORM_SUB][3][blockDim.x]  (count, mean, M2)
   const int chunk = blockIdx.x;
   const int sub = threadIdx.y;
@@ -73,6 +74,7 @@ __device__ __forceinline__ Mom mom_merge(Mom a, Mom b) {
 // one warp per column: lanes take chunks round-robin, then a fixed shuffle tree
 __global__ void norm_merge_chunks_kernel(const float* __restrict__ partials, int n, int D, int nchunks,
                                          double* __restrict__ record) {
+  pdl_sync();
   const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (col >= D) return;
   Mom acc = {0.0, 0.0, 0.0};
@@ -108,10 +110,10 @@ extern "C" int sard_norm_moments(const float* x, int ldx, int n, int D, float* p
     int threads = ((D + 31) / 32) * 32;
     if (threads > 256) threads = 256;
     dim3 block(threads, NORM_SUB);
-    norm_moments_kernel<<<nchunks, block, NORM_SUB * 3 * threads * sizeof(float), st>>>(x, ldx, n, D, partials);
+    sard_launch(norm_moments_kernel, nchunks, block, NORM_SUB * 3 * threads * sizeof(float), st, x, ldx, n, D, partials);
     SARD_LAUNCH_OK("norm_moments_kernel");
   }
-  norm_merge_chunks_kernel<<<ceil_div((long long)D * 32, 256), 256, 0, st>>>(partials, n, D, nchunks, record);
+  sard_launch(norm_merge_chunks_kernel, ceil_div((long long)D * 32, 256), 256, 0, st, partials, n, D, nchunks, record);
   SARD_LAUNCH_OK("norm_merge_chunks_kernel");
   return 0;
 }
@@ -119,6 +121,7 @@ extern "C" int sard_norm_moments(const float* x, int ldx, int n, int D, float* p
 __global__ void norm_update_kernel(const double* __restrict__ records, int n_records, int D,
                                    float* __restrict__ mean, float* __restrict__ var, float* __restrict__ std,
                                    long long* __restrict__ count, float* __restrict__ inv) {
+  pdl_sync();
   const long long n_old = *count;
   const int stride = 1 + 2 * D;
   double m_total = 0.0;
@@ -155,24 +158,26 @@ __global__ void norm_update_kernel(const double* __restrict__ records, int n_rec
 extern "C" int sard_norm_update(const double* records, int n_records, int D, float* mean, float* var, float* std,
                                 long long* count, float* inv, sard_stream_t stream) {
   SARD_REQUIRE(n_records >= 1, "n_records");
-  norm_update_kernel<<<1, 256, 0, as_stream(stream)>>>(records, n_records, D, mean, var, std, count, inv);
+  sard_launch(norm_update_kernel, 1, 256, 0, as_stream(stream), records, n_records, D, mean, var, std, count, inv);
   SARD_LAUNCH_OK("norm_update_kernel");
   return 0;
 }
 
 __global__ void norm_prepare_eval_kernel(const float* __restrict__ std, int D, float* __restrict__ inv) {
+  pdl_sync();
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x)
     inv[c] = 1.0f / (std[c] + 1e-8f);
 }
 
 extern "C" int sard_norm_prepare_eval(const float* std, int D, float* inv, sard_stream_t stream) {
-  norm_prepare_eval_kernel<<<ceil_div(D, 256), 256, 0, as_stream(stream)>>>(std, D, inv);
+  sard_launch(norm_prepare_eval_kernel, ceil_div(D, 256), 256, 0, as_stream(stream), std, D, inv);
   SARD_LAUNCH_OK("norm_prepare_eval_kernel");
   return 0;
 }
 
 __global__ void norm_apply_kernel(float* __restrict__ x, int ldx, int n, int D, const float* __restrict__ mean,
                                   const float* __restrict__ inv, const long long* __restrict__ count, float clip) {
+  pdl_sync();
   if (*count <= 0) return;
   const long long total = (long long)n * D;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -187,7 +192,7 @@ __global__ void norm_apply_kernel(float* __restrict__ x, int ldx, int n, int D, 
 extern "C" int sard_norm_apply(float* x, int ldx, int n, int D, const float* mean, const float* inv,
                                const long long* count, float clip, sard_stream_t stream) {
   if (n <= 0) return 0;
-  norm_apply_kernel<<<grid_for((long long)n * D, 256), 256, 0, as_stream(stream)>>>(x, ldx, n, D, mean, inv, count, clip);
+  sard_launch(norm_apply_kernel, grid_for((long long)n * D, 256), 256, 0, as_stream(stream), x, ldx, n, D, mean, inv, count, clip);
   SARD_LAUNCH_OK("norm_apply_kernel");
   return 0;
 }

@@ -9,6 +9,7 @@
 #define SQ_BLOCKS 1024
 
 __global__ void sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ scratch) {
+  pdl_sync();
   __shared__ float red[256];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -25,6 +26,7 @@ __global__ void sqnorm_partial_kernel(const float* __restrict__ g, long long n, 
 }
 
 __global__ void sqnorm_final_kernel(const float* __restrict__ scratch, int nb, float* __restrict__ out) {
+  pdl_sync();
   __shared__ double red[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < nb; i += 256) s += (double)scratch[i];
@@ -42,9 +44,9 @@ extern "C" int sard_sqnorm(const float* g, long long n, float* scratch, float* o
   int nb = (int)((n + 1023) / 1024);
   if (nb > SQ_BLOCKS) nb = SQ_BLOCKS;
   if (nb < 1) nb = 1;
-  sqnorm_partial_kernel<<<nb, 256, 0, st>>>(g, n, scratch);
+  sard_launch(sqnorm_partial_kernel, nb, 256, 0, st, g, n, scratch);
   SARD_LAUNCH_OK("sqnorm_partial_kernel");
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(scratch, nb, out);
+  sard_launch(sqnorm_final_kernel, 1, 256, 0, st, scratch, nb, out);
   SARD_LAUNCH_OK("sqnorm_final_kernel");
   return 0;
 }
@@ -53,6 +55,7 @@ __global__ void adam_prepare_kernel(const float* stats, float inv_B, float inv_w
                                     const float* sqnorm, float max_norm, int first_only, int use_gate,
                                     int active_mask, double beta1, double beta2, float* ctl_f, int* ctl_i,
                                     float* log_row) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float surr_loss = 0.f, kl = 0.f, entropy = 0.f, extra = 0.f;
   if (stats) {
@@ -92,7 +95,7 @@ extern "C" int sard_adam_prepare(const float* stats, float inv_B, float inv_worl
                                  const float* sqnorm, float max_norm, int first_only, int use_gate, int active_mask,
                                  double beta1, double beta2, float* ctl_f, int* ctl_i, float* log_row,
                                  sard_stream_t stream) {
-  adam_prepare_kernel<<<1, 32, 0, as_stream(stream)>>>(stats, inv_B, inv_world, inv_cat_nodes, sqnorm, max_norm,
+  sard_launch(adam_prepare_kernel, 1, 32, 0, as_stream(stream), stats, inv_B, inv_world, inv_cat_nodes, sqnorm, max_norm,
                                                       first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i,
                                                       log_row);
   SARD_LAUNCH_OK("adam_prepare_kernel");
@@ -101,6 +104,7 @@ extern "C" int sard_adam_prepare(const float* stats, float inv_B, float inv_worl
 
 __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr, float beta1, float beta2, float eps,
                                   int active_mask, const float* __restrict__ ctl_f, const int* __restrict__ ctl_i) {
+  pdl_sync();
   if (ctl_i[0] == 0) return;
   const SardAdamSeg s = segs[blockIdx.y];
   if (!((active_mask >> s.group) & 1)) return;
@@ -126,7 +130,7 @@ extern "C" int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max
   int gx = (int)((max_seg_len + 255) / 256);
   if (gx > 256) gx = 256;
   dim3 grid(gx, n_seg);
-  adam_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i);
+  sard_launch(adam_apply_kernel, grid, 256, 0, as_stream(stream), segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i);
   SARD_LAUNCH_OK("adam_apply_kernel");
   return 0;
 }

@@ -10,6 +10,7 @@
 __global__ void csr_kernel(const int* __restrict__ node_ptr, const int* __restrict__ edge_ptr,
                            const int* __restrict__ key, const int* __restrict__ val, int T,
                            int* __restrict__ ptr, int* __restrict__ nbr) {
+  pdl_sync();
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= T) return;
   const int gn = node_ptr[g], N = node_ptr[g + 1] - gn;
@@ -28,9 +29,9 @@ extern "C" int sard_build_csr(const int* node_ptr, const int* edge_ptr, const in
                               int* in_ptr, int* in_nbr, int* out_ptr, int* out_nbr, sard_stream_t stream) {
   if (T <= 0) return 0;
   const int threads = 128, blocks = ceil_div(T, threads);
-  csr_kernel<<<blocks, threads, 0, as_stream(stream)>>>(node_ptr, edge_ptr, edst, esrc, T, in_ptr, in_nbr);
+  sard_launch(csr_kernel, blocks, threads, 0, as_stream(stream), node_ptr, edge_ptr, edst, esrc, T, in_ptr, in_nbr);
   SARD_LAUNCH_OK("csr_kernel(in)");
-  csr_kernel<<<blocks, threads, 0, as_stream(stream)>>>(node_ptr, edge_ptr, esrc, edst, T, out_ptr, out_nbr);
+  sard_launch(csr_kernel, blocks, threads, 0, as_stream(stream), node_ptr, edge_ptr, esrc, edst, T, out_ptr, out_nbr);
   SARD_LAUNCH_OK("csr_kernel(out)");
   return 0;
 }
@@ -41,6 +42,7 @@ extern "C" int sard_build_csr(const int* node_ptr, const int* edge_ptr, const in
 __global__ void orbit_rep_kernel(const int* __restrict__ node_ptr, const int* __restrict__ body, int T,
                                  const int* __restrict__ leg_rep, int base, int* __restrict__ rep_local,
                                  int* __restrict__ err_flag) {
+  pdl_sync();
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= T) return;
   const int gn = node_ptr[g], N = node_ptr[g + 1] - gn;
@@ -65,7 +67,7 @@ extern "C" int sard_orbit_rep(const int* node_ptr, const int* body_ind, int T, c
                               int* rep_local, int* err_flag, sard_stream_t stream) {
   if (T <= 0) return 0;
   SARD_REQUIRE(index_base >= 2, "index_base");
-  orbit_rep_kernel<<<ceil_div(T, 128), 128, 0, as_stream(stream)>>>(node_ptr, body_ind, T, leg_rep, index_base,
+  sard_launch(orbit_rep_kernel, ceil_div(T, 128), 128, 0, as_stream(stream), node_ptr, body_ind, T, leg_rep, index_base,
                                                                    rep_local, err_flag);
   SARD_LAUNCH_OK("orbit_rep_kernel");
   return 0;
@@ -82,6 +84,7 @@ struct GatherP {
 };
 
 __global__ void gather_kernel(const GatherP p) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= p.B) return;
   const int gid = p.ids[warp];
@@ -122,7 +125,7 @@ extern "C" int sard_gather_nodes(const SardArena* arena, const SardSel* sel, con
   p.x = out->x; p.ldx = out->ldx; p.nd_graph = out->nd_graph; p.nd_arena = out->nd_arena; p.body = out->body;
   p.root_row = out->root_row;
   const int threads = 256;
-  gather_kernel<<<ceil_div((long long)sel->B * 32, threads), threads, 0, as_stream(stream)>>>(p);
+  sard_launch(gather_kernel, ceil_div((long long)sel->B * 32, threads), threads, 0, as_stream(stream), p);
   SARD_LAUNCH_OK("gather_kernel");
   return 0;
 }
@@ -134,6 +137,7 @@ extern "C" int sard_gather_nodes(const SardArena* arena, const SardSel* sel, con
 
 __global__ void sort_hist_kernel(const int* __restrict__ body, int n, int max_index, int* __restrict__ blockhist,
                                  int* __restrict__ counts) {
+  pdl_sync();
   extern __shared__ int hist[];
   for (int u = threadIdx.x; u < max_index; u += blockDim.x) hist[u] = 0;
   __syncthreads();
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_
                                  int* __restrict__ blockhist, int* __restrict__ cnt, int* __restrict__ grp_ptr,
                                  int4* __restrict__ tiles, int4* __restrict__ chunks, int* __restrict__ grp_chunk_ptr,
                                  int* __restrict__ counts) {
+  pdl_sync();
   __shared__ int sc[3][1024];
   const int u = threadIdx.x;
   int total = 0;
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_
 __global__ void sort_scatter_kernel(const int* __restrict__ body, int n, int max_index,
                                     const int* __restrict__ blockhist, const int* __restrict__ grp_ptr,
                                     int* __restrict__ srow, int* __restrict__ spos) {
+  pdl_sync();
   extern __shared__ int warp_cnt[];   // [SORT_BLOCK/32][max_index]
   const int nwarp = SORT_BLOCK / 32;
   for (int i = threadIdx.x; i < nwarp * max_index; i += blockDim.x) warp_cnt[i] = 0;
@@ -224,15 +230,15 @@ extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int til
   int* blockhist = scratch;
   int* cnt = scratch + (size_t)nb * max_index;
   if (nb > 0) {
-    sort_hist_kernel<<<nb, SORT_BLOCK, max_index * sizeof(int), st>>>(body, n, max_index, blockhist, counts);
+    sard_launch(sort_hist_kernel, nb, SORT_BLOCK, max_index * sizeof(int), st, body, n, max_index, blockhist, counts);
     SARD_LAUNCH_OK("sort_hist_kernel");
   }
-  sort_scan_kernel<<<1, 1024, 0, st>>>(nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
+  sard_launch(sort_scan_kernel, 1, 1024, 0, st, nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
                                       reinterpret_cast<int4*>(tiles), reinterpret_cast<int4*>(chunks),
                                       grp_chunk_ptr, counts);
   SARD_LAUNCH_OK("sort_scan_kernel");
   if (nb > 0) {
-    sort_scatter_kernel<<<nb, SORT_BLOCK, (SORT_BLOCK / 32) * max_index * sizeof(int), st>>>(
+    sard_launch(sort_scatter_kernel, nb, SORT_BLOCK, (SORT_BLOCK / 32) * max_index * sizeof(int), st, 
         body, n, max_index, blockhist, grp_ptr, srow, spos);
     SARD_LAUNCH_OK("sort_scatter_kernel");
   }

@@ -3,6 +3,9 @@
 #include <vector>
 
 long long g_sard_launches = 0;
+int g_sard_pdl = 1;
+extern "C" int sard_set_pdl(int enabled) { g_sard_pdl = enabled ? 1 : 0; return 0; }
+extern "C" int sard_get_pdl(void) { return g_sard_pdl; }
 thread_local int g_sard_site = -1;
 
 namespace {

@@ -89,6 +89,7 @@ __device__ __forceinline__ void store_split(float* hi_tile, float* lo_tile, int 
 
 template <int NT_TILE, bool NT>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_gemm_kernel(const SardGemm g) {
+  pdl_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_TILE = UMMA_BM * UMMA_KC;                // floats
   constexpr int B_TILE = NT_TILE * UMMA_KC;
@@ -275,7 +276,7 @@ static int launch_umma_t(const SardGemm* g, cudaStream_t st) {
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, UMMA_BM);
   if (tiles <= 0) return 0;
   dim3 grid(tiles, ceil_div(g->N, NT_TILE));
-  umma_gemm_kernel<NT_TILE, NT><<<grid, UMMA_THREADS, smem, st>>>(*g);
+  sard_launch(umma_gemm_kernel<NT_TILE, NT>, grid, UMMA_THREADS, smem, st, *g);
   SARD_LAUNCH_OK(NT ? "umma_gemm_kernel<fwd>" : "umma_gemm_kernel<bwd_data>");
   return 0;
 }
@@ -309,6 +310,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 template <int NT_TILE, bool NT>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_gemm_ts_kernel(const SardGemm g) {
+  pdl_sync();
   // one pipeline step covers KSTEP = 64 k-values: two 128-byte swizzle sub-tiles of B in smem, 64 TMEM
   // columns each for A_hi and A_lo.  Each thread then reads exactly one 128-byte line of its A row per step.
   constexpr int KSUB = 2, KSTEP = KSUB * UMMA_KC;
@@ -521,7 +523,7 @@ static int launch_umma_ts(const SardGemm* g, cudaStream_t st) {
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, UMMA_BM);
   if (tiles <= 0) return 0;
   dim3 grid(tiles, ceil_div(g->N, NT_TILE));
-  umma_gemm_ts_kernel<NT_TILE, NT><<<grid, UMMA_THREADS, smem, st>>>(*g);
+  sard_launch(umma_gemm_ts_kernel<NT_TILE, NT>, grid, UMMA_THREADS, smem, st, *g);
   SARD_LAUNCH_OK(NT ? "umma_gemm_ts_kernel<fwd>" : "umma_gemm_ts_kernel<bwd_data>");
   return 0;
 }
@@ -542,6 +544,7 @@ extern int g_sard_gemm_engine;
 // ------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_wgrad_kernel(const SardWGrad w) {
+  pdl_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_TILE = NB * UMMA_KC;                     // floats
   constexpr int STAGE = 2 * B_TILE;
@@ -697,7 +700,7 @@ static int launch_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(nchunks, ceil_div(w->N1, UMMA_BM), ceil_div(w->N2, NB));
-  umma_wgrad_kernel<NB><<<grid, UMMA_THREADS, smem, st>>>(*w);
+  sard_launch(umma_wgrad_kernel<NB>, grid, UMMA_THREADS, smem, st, *w);
   SARD_LAUNCH_OK("umma_wgrad_kernel");
   return 0;
 }
