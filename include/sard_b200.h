@@ -49,6 +49,12 @@ long long sard_launch_count(void);
 int sard_set_pdl(int enabled);
 int sard_get_pdl(void);
 
+/* Weight gradients of sard_value_run / sard_policy_run on a low-priority side stream owned by the library
+ * (default 1): forked after each layer's output gradient, joined before the call returns, so the
+ * caller's stream semantics are unchanged.  0 = everything on the caller's stream. */
+int sard_set_wgrad_overlap(int enabled);
+int sard_get_wgrad_overlap(void);
+
 /* Per-call-site kernel timing for the roofline numbers (CUDA events on the launching stream).
  * Sites label the GEMM / aggregate launches of the network schedules: site = 3*kind + pass with
  * kind in {0 in_fc, 1 graphconv, 2 index-linear, 3 obs-encoder, 4 critic mlp, 5 value head, 6 csr aggregate}

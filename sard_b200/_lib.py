@@ -107,6 +107,8 @@ _PROTOS = {
     'sard_launch_count': (cll, []),
     'sard_set_pdl': (ci, [ci]),
     'sard_get_pdl': (ci, []),
+    'sard_set_wgrad_overlap': (ci, [ci]),
+    'sard_get_wgrad_overlap': (ci, []),
     'sard_prof_enable': (ci, [C.c_uint, ci]),
     'sard_prof_collect': (ci, [P(cd), ci]),
     'sard_build_csr': (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
@@ -184,6 +186,8 @@ def check_struct_sizes():
 check_struct_sizes()
 if os.environ.get('SARD_PDL') is not None:               # 1 = programmatic dependent launch (default), 0 = off
     lib.sard_set_pdl(int(os.environ['SARD_PDL']))
+if os.environ.get('SARD_WGRAD_OVERLAP') is not None:     # 1 = weight gradients on a side stream (default), 0 = off
+    lib.sard_set_wgrad_overlap(int(os.environ['SARD_WGRAD_OVERLAP']))
 if os.environ.get('SARD_GEMM_ENGINE') is not None:       # 0 = fp32 FFMA, 1 = tcgen05 3xTF32
     lib.sard_set_gemm_engine(int(os.environ['SARD_GEMM_ENGINE']))
 

@@ -9,6 +9,12 @@
 #include "common.cuh"
 #include "encoder.cuh"
 #include <string.h>
+#include <mutex>
+#include <unordered_map>
+
+int g_sard_wgrad_overlap = 1;
+extern "C" int sard_set_wgrad_overlap(int enabled) { g_sard_wgrad_overlap = enabled ? 1 : 0; return 0; }
+extern "C" int sard_get_wgrad_overlap(void) { return g_sard_wgrad_overlap; }
 
 thread_local char g_sard_err[1024] = "";
 int sard_set_error(const char* fmt, ...) {
@@ -36,6 +42,53 @@ namespace {
 enum { K_INFC = 0, K_GCONV = 1, K_IL = 2, K_ENC = 3, K_MLP = 4, K_HEAD = 5, K_AGG = 6 };
 inline void site(int kind, int pass) { g_sard_site = 3 * kind + pass; }
 
+// Weight gradients leave the critical path: in every backward pass the chain dz_l -> bwd_data -> dz_{l-1}
+// is what the next layer waits for, while dW_l (partials + ordered reduce) is only needed by the optimiser
+// step.  Each launching stream owns a low-priority side stream; a weight gradient is forked onto it with an
+// event recorded right after dz_l was produced, and the run joins it before returning.  The side
+// stream serialises the weight gradients among themselves, so they can share one partials scratch;
+// dz buffers are per layer (no ping-pong) so the main stream never overwrites one that is still read.
+struct SideCtx {
+  cudaStream_t main, side;
+  cudaEvent_t ev[8];
+  int k;
+  bool forked;
+};
+std::mutex g_side_mu;
+std::unordered_map<cudaStream_t, SideCtx*> g_side;
+
+SideCtx* side_for(cudaStream_t main) {
+  if (!g_sard_wgrad_overlap) return nullptr;
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  auto it = g_side.find(main);
+  if (it != g_side.end()) { it->second->forked = false; return it->second; }
+  SideCtx* c = new SideCtx();
+  c->main = main; c->k = 0; c->forked = false;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
+  for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+  g_side[main] = c;
+  return c;
+}
+// stream for a weight gradient whose inputs were just produced on `st`
+sard_stream_t wg_stream(SideCtx* c, sard_stream_t st) {
+  if (!c) return st;
+  cudaEvent_t e = c->ev[c->k++ & 7];
+  cudaEventRecord(e, c->main);
+  cudaStreamWaitEvent(c->side, e, 0);
+  c->forked = true;
+  return reinterpret_cast<sard_stream_t>(c->side);
+}
+int side_join(SideCtx* c) {
+  if (!c || !c->forked) return 0;
+  cudaEvent_t e = c->ev[c->k++ & 7];
+  SARD_CUDA(cudaEventRecord(e, c->side));
+  SARD_CUDA(cudaStreamWaitEvent(c->main, e, 0));
+  c->forked = false;
+  return 0;
+}
+
 struct Bump {
   float* base; long long off;
   float* f(long long n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~3LL; return p; }
@@ -57,7 +110,7 @@ struct TowerBufs {
   float* partials;
   float* xa[SARD_MAX_LAYERS];
   float* hout;
-  float *dz[2], *dxa;
+  float *dz[SARD_MAX_LAYERS + 1], *dxa;      // dz[l]: gradient w.r.t. the pre-activation of layer l (0 = in_fc)
   int maxh;
 };
 
@@ -71,11 +124,11 @@ void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBu
   for (int l = 0; l < tw.L; ++l) t.xa[l] = b.f((long long)n * 2 * tw.h[l]);
   t.hout = b.f((long long)n * tw.h[tw.L]);
   if (train) {
-    t.dz[0] = b.f((long long)n * t.maxh);
-    t.dz[1] = b.f((long long)n * t.maxh);
+    for (int l = 0; l <= tw.L; ++l) t.dz[l] = b.f((long long)n * tw.h[l]);
     t.dxa = b.f((long long)n * 2 * t.maxh);
   } else {
-    t.dz[0] = t.dz[1] = t.dxa = nullptr;
+    for (int l = 0; l <= tw.L; ++l) t.dz[l] = nullptr;
+    t.dxa = nullptr;
   }
 }
 
@@ -130,21 +183,20 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
   return 0;
 }
 
-// dz_top: [n, h[L]] gradient w.r.t. the pre-activation of the last layer (act' already applied), in t.dz[0]
+// dz_top: [n, h[L]] gradient w.r.t. the pre-activation of the last layer (act' already applied), in t.dz[L]
 int tower_backward(const SardTower& tw, const float* P, float* G, const SardArena* arena, const SardSel* sel,
-                   TowerBufs& t, float* wg_scratch, sard_stream_t st) {
+                   TowerBufs& t, float* wg_scratch, SideCtx* side, sard_stream_t st) {
   const int n = sel->n;
-  int cur = 0;
   for (int l = tw.L; l >= 1; --l) {
     const int hi = tw.h[l - 1], ho = tw.h[l];
-    float* dz = t.dz[cur];
+    float* dz = t.dz[l];
     float* xin = t.xa[l - 1];
     SardWGrad w = wgrad0();
     w.P = dz; w.ldp = ho; w.Q = xin; w.ldq = 2 * hi; w.M = n; w.N1 = ho; w.N2 = 2 * hi;
     w.dW0 = G + tw.wl[l - 1]; w.ldw0 = hi; w.dW1 = G + tw.wr[l - 1]; w.ldw1 = hi; w.w_split = hi;
     w.db = tw.has_bias ? G + tw.bl[l - 1] : nullptr; w.partials = wg_scratch;
     site(K_GCONV, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
     g.M = n; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
@@ -153,15 +205,15 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
     // dz_{l-1} = (dxa[:, hi:2hi] + A^T dxa[:, 0:hi]) * act'(y_{l-1});  layer 0 (in_fc) has no activation
     const float* yprev = (l - 1 >= 1) ? xin + hi : nullptr;
     site(K_AGG, 1);
-    SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[cur ^ 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
+    SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[l - 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
                                 t.nd_graph, t.nd_arena, sel->cum, sel->node_base, arena->out_ptr, arena->out_nbr, st));
-    cur ^= 1;
   }
   SardWGrad w = wgrad0();
-  w.P = t.dz[cur]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;
+  w.P = t.dz[0]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;
   w.dW0 = G + tw.in_w; w.ldw0 = tw.D; w.w_split = tw.D; w.db = G + tw.in_b; w.partials = wg_scratch;
   site(K_INFC, 2);
-  return sard_linear_bwd_weight(&w, st);
+  SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+  return side_join(side);
 }
 
 // ext[B, 3*64] written at `ext` with leading dimension ld_ext; e1[k]: [B,64] hidden activations
@@ -251,7 +303,7 @@ struct ValueBufs {
   TowerBufs t;
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
-  float* dcat; float* dm[2]; float* de1; float* wg;
+  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg;
 };
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
@@ -269,7 +321,7 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
   vb.v = b.f(B); vb.dv = b.f(B); vb.sq = b.f(B);
   if (train) {
     vb.dcat = b.f((long long)B * vb.ldcat);
-    vb.dm[0] = b.f((long long)B * (maxm > 0 ? maxm : 4)); vb.dm[1] = b.f((long long)B * (maxm > 0 ? maxm : 4));
+    for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
     vb.de1 = b.f((long long)B * SARD_EXT_DIM);
     long long need = tower_wg_need(net.tower, n);
     long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
@@ -277,7 +329,8 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
     v = wg_partials(B, 1, vb.ldcat, WG_CHUNK); need = v > need ? v : need;
     vb.wg = b.f(need);
   } else {
-    vb.dcat = vb.dm[0] = vb.dm[1] = vb.de1 = vb.wg = nullptr;
+    vb.dcat = vb.de1 = vb.wg = nullptr;
+    for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = nullptr;
   }
 }
 
@@ -343,6 +396,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   if (!bwd) return sard_value_loss(vb.v, sel->ids, B, nullptr, 0.f, nullptr, nullptr, arena->values, st);
+  SideCtx* side = side_for(as_stream(st));
 
   SARD_TRY(sard_value_loss(vb.v, sel->ids, B, arena->returns, inv_B_global, vb.dv, vb.sq, nullptr, st));
   if (sq_err_sum) SARD_TRY(sard_loss_reduce(vb.sq, B, 1, sq_err_sum, nullptr, 0, nullptr, st));
@@ -352,7 +406,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     w.P = vb.dv; w.ldp = 1; w.Q = vb.cat; w.ldq = vb.ldcat; w.M = B; w.N1 = 1; w.N2 = vb.ldcat;
     w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg;
     site(K_HEAD, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
     SardGemm g = gemm0();
     g.A = vb.dv; g.lda = 1; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat;
     g.M = B; g.N = vb.ldcat; g.R = 1; g.Y = vb.dcat; g.ldy = vb.ldcat;
@@ -361,34 +415,35 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     site(K_HEAD, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
   }
+  // the encoders' backward ends in weight gradients only: all of it runs beside the MLP / tower backward
   SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
-                             vb.de1, vb.wg, st));
+                             vb.de1, vb.wg, wg_stream(side, st)));
   // MLP backward (dz of layer j lives in dzj with leading dimension ldz)
-  const float* dzj = vb.dcat; int ldz = vb.ldcat; int cur = 0;
-  SARD_CUDA(cudaMemsetAsync(vb.t.dz[0], 0, sizeof(float) * (size_t)n * hL, as_stream(st)));
+  const float* dzj = vb.dcat; int ldz = vb.ldcat;
+  SARD_CUDA(cudaMemsetAsync(vb.t.dz[tw.L], 0, sizeof(float) * (size_t)n * hL, as_stream(st)));
   for (int j = net->n_mlp - 1; j >= 0; --j) {
     SardWGrad w = wgrad0();
     w.P = dzj; w.ldp = ldz; w.M = B; w.N1 = net->mlp[j].out; w.N2 = net->mlp[j].in;
     if (j == 0) { w.Q = vb.t.hout; w.ldq = hL; w.q_rows = vb.t.root_row; } else { w.Q = vb.m[j - 1]; w.ldq = net->mlp[j - 1].out; }
     w.dW0 = G + net->mlp[j].w; w.ldw0 = net->mlp[j].in; w.w_split = net->mlp[j].in; w.db = G + net->mlp[j].b; w.partials = vb.wg;
     site(K_MLP, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
     SardGemm g = gemm0();
     g.A = dzj; g.lda = ldz; g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in;
     g.M = B; g.N = net->mlp[j].in; g.R = net->mlp[j].out; g.dsplit = g.N;
     if (j == 0) {
       // scatter into the root rows of the tower gradient; other rows stay zero
-      g.Y = vb.t.dz[0]; g.ldy = hL; g.y_rows = vb.t.root_row;
+      g.Y = vb.t.dz[tw.L]; g.ldy = hL; g.y_rows = vb.t.root_row;
       g.Dact = vb.t.hout; g.ldd = hL; g.dact0 = tw.L > 0 ? tw.act : SARD_ACT_NONE; g.dact1 = g.dact0;
     } else {
-      g.Y = vb.dm[cur]; g.ldy = net->mlp[j - 1].out;
+      g.Y = vb.dm[j]; g.ldy = net->mlp[j - 1].out;
       g.Dact = vb.m[j - 1]; g.ldd = net->mlp[j - 1].out; g.dact0 = net->mlp[j - 1].act; g.dact1 = g.dact0;
     }
     site(K_MLP, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
-    if (j > 0) { dzj = vb.dm[cur]; ldz = net->mlp[j - 1].out; cur ^= 1; }
+    if (j > 0) { dzj = vb.dm[j]; ldz = net->mlp[j - 1].out; }
   }
-  return tower_backward(tw, P, G, arena, sel, vb.t, vb.wg, st);
+  return tower_backward(tw, P, G, arena, sel, vb.t, vb.wg, side, st);
 }
 
 // ------------------------------------------------------------------------------------------ policy stage
@@ -399,7 +454,7 @@ struct StageBufs {
   float* e1[3]; float* ext;
   int *srow, *spos, *grp_ptr, *tiles, *chunks, *grp_chunk_ptr, *counts, *sort_scratch;
   float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
-  float* dout; float* gstat; float* dH[2]; float* dxs; float* dext; float* de1; float* wg;
+  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg;
   int max_tiles, max_chunks;
 };
 
@@ -427,7 +482,7 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
   if (train) {
     sb.dout = b.f((long long)n * sb.ldo);
     sb.gstat = b.f((long long)B * (4 + s.out_dim));
-    sb.dH[0] = b.f((long long)n * maxo); sb.dH[1] = b.f((long long)n * maxo);
+    for (int j = 0; j < s.n_il; ++j) sb.dH[j] = j > 0 ? b.f((long long)n * s.il[j - 1].out) : nullptr;
     sb.dxs = b.f((long long)n * sb.ldxs);
     sb.dext = b.f((long long)B * 3 * SARD_EXT_DIM);
     sb.de1 = b.f((long long)B * SARD_EXT_DIM);
@@ -436,7 +491,8 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
     for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * (s.il[j].in + 1); need = v > need ? v : need; }
     sb.wg = b.f(need);
   } else {
-    sb.dout = sb.gstat = sb.dH[0] = sb.dH[1] = sb.dxs = sb.dext = sb.de1 = sb.wg = nullptr;
+    sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = nullptr;
+    for (int j = 0; j < s.n_il; ++j) sb.dH[j] = nullptr;
   }
 }
 }  // namespace
@@ -527,11 +583,12 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   if (outputs) SARD_REQUIRE(sb.ldo == s.out_dim || true, "outputs use the padded leading dimension");
   SARD_TRY(stage == SARD_STAGE_SKEL ? sard_cat_loss(&L, st) : sard_gauss_loss(&L, st));
   if (!bwd) return 0;
+  SideCtx* side = side_for(as_stream(st));
   SARD_TRY(sard_loss_reduce(sb.gstat, B, 4 + s.out_dim, stats, s.log_std >= 0 ? G + s.log_std : nullptr, s.out_dim,
                             s.log_std >= 0 ? P + s.log_std : nullptr, st));
 
   // ---- backward through the JSMLP (sorted row space) ----
-  const float* dz = sb.dout; int ldz = sb.ldo; const int* dz_rows = sb.srow; int cur = 0;
+  const float* dz = sb.dout; int ldz = sb.ldo; const int* dz_rows = sb.srow;
   for (int j = s.n_il - 1; j >= 0; --j) {
     const float* Aj = j == 0 ? sb.xs : sb.H[j - 1];
     const int lda = j == 0 ? sb.ldxs : s.il[j - 1].out;
@@ -542,21 +599,21 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     w.dW0 = s.GT + s.il[j].gW; w.ldw0 = s.il[j].in; w.w_split = s.il[j].in; w.w_slot_stride = (long long)s.il[j].out * s.il[j].in;
     w.db = s.GT + s.il[j].gb; w.b_slot_stride = s.il[j].out; w.partials = sb.wg;
     site(K_IL, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, st));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ldz; g.a_rows = dz_rows;
     g.B0 = s.il[j].W; g.ldb0 = s.il[j].in; g.b_split = s.il[j].in; g.b_group_stride = (long long)s.il[j].out * s.il[j].in;
     g.M = n; g.N = s.il[j].in; g.R = s.il[j].out; g.dsplit = g.N;
     g.tiles = sb.tiles; g.num_tiles = sb.counts; g.max_tiles = sb.max_tiles;
     if (j == 0) { g.Y = sb.dxs; g.ldy = sb.ldxs; }
-    else { g.Y = sb.dH[cur]; g.ldy = s.il[j - 1].out; g.Dact = sb.H[j - 1]; g.ldd = s.il[j - 1].out; g.dact0 = s.il_act; g.dact1 = s.il_act; }
+    else { g.Y = sb.dH[j]; g.ldy = s.il[j - 1].out; g.Dact = sb.H[j - 1]; g.ldd = s.il[j - 1].out; g.dact0 = s.il_act; g.dact1 = s.il_act; }
     site(K_IL, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
-    if (j > 0) { dz = sb.dH[cur]; ldz = s.il[j - 1].out; dz_rows = nullptr; cur ^= 1; }
+    if (j > 0) { dz = sb.dH[j]; ldz = s.il[j - 1].out; dz_rows = nullptr; }
   }
   SARD_TRY(sard_unsort_grad(sb.dxs, sb.ldxs, sb.spos, sel->cum, sel->node_base, B, sb.t.hout, hL, hL,
-                            tw.L > 0 ? tw.act : SARD_ACT_NONE, sb.t.dz[0], hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM,
+                            tw.L > 0 ? tw.act : SARD_ACT_NONE, sb.t.dz[tw.L], hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM,
                             sb.dext, 3 * SARD_EXT_DIM, st));
-  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg, st));
-  return tower_backward(tw, P, G, arena, sel, sb.t, sb.wg, st);
+  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg, wg_stream(side, st)));
+  return tower_backward(tw, P, G, arena, sel, sb.t, sb.wg, side, st);
 }

@@ -243,6 +243,7 @@ class Transform2ActAgent:
         comm = self.comm
         world = comm.world if comm is not None else 1
         peng, veng = self.policy_net.engine, self.value_net.engine
+        t_host0 = time.perf_counter()
         for m in self.update_modules:
             m.train(False)
         self._eval_log_probs(arena)
@@ -321,10 +322,11 @@ class Transform2ActAgent:
                 # the next epoch's plan replaces the ordering tensors the in-flight kernels read
                 plans_alive.append(plan)
         main.wait_stream(sv); main.wait_stream(sp)
+        host_enqueue_s = time.perf_counter() - t_host0        # host time to issue the whole update (no sync inside)
         logs = plog[:step].cpu().numpy()
         vlogs = vlog[:step].cpu().numpy()
         self.last_update_stats = {'h2d_bytes': arena.h2d_bytes + h2d, 'd2h_bytes': int(logs.nbytes + vlogs.nbytes),
-                                  'steps': step, 'valid_steps': int(logs[:, 3].sum()) if step else 0,
+                                  'host_enqueue_s': host_enqueue_s, 'steps': step, 'valid_steps': int(logs[:, 3].sum()) if step else 0,
                                   'value_loss': vlogs[:, 5].copy(), 'policy_log': logs}
         return self._summarise(arena, logs, cur_perm)
 
