@@ -372,8 +372,11 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   } else {
     SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
   }
+  // the ObsEncoders only need the arena: they run beside the tower and are joined before the value head
+  SideCtx* side = side_for(as_stream(st));
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
+                            wg_stream(side, st)));
   SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
-  SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat, st));
   // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
   const int hL = tw.h[tw.L];
   for (int j = 0; j < net->n_mlp; ++j) {
@@ -387,6 +390,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   SARD_REQUIRE(net->n_mlp > 0, "critic without mlp is not supported");
+  SARD_TRY(side_join(side));
   {
     SardGemm g = gemm0();
     g.A = vb.cat; g.lda = vb.ldcat; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat; g.bias = P + net->head.b;
@@ -396,7 +400,6 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     SARD_TRY(sard_linear_fwd(&g, st));
   }
   if (!bwd) return sard_value_loss(vb.v, sel->ids, B, nullptr, 0.f, nullptr, nullptr, arena->values, st);
-  SideCtx* side = side_for(as_stream(st));
 
   SARD_TRY(sard_value_loss(vb.v, sel->ids, B, arena->returns, inv_B_global, vb.dv, vb.sq, nullptr, st));
   if (sq_err_sum) SARD_TRY(sard_loss_reduce(vb.sq, B, 1, sq_err_sum, nullptr, 0, nullptr, st));
@@ -536,10 +539,16 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   } else {
     SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
   }
+  // the ObsEncoders and the body-index sort only need the gathered run: they run beside the tower
+  SideCtx* side = side_for(as_stream(st));
+  {
+    sard_stream_t s2 = wg_stream(side, st);
+    SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, s2));
+    SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
+                                sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
+  }
   SARD_TRY(tower_forward(tw, P, arena, sel, sb.t, st));
-  SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, st));
-  SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
-                              sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, st));
+  SARD_TRY(side_join(side));
   const int hL = tw.h[tw.L];
   SARD_TRY(sard_concat_sorted(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph, n,
                               sb.xs, sb.ldxs, st));
@@ -583,7 +592,6 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   if (outputs) SARD_REQUIRE(sb.ldo == s.out_dim || true, "outputs use the padded leading dimension");
   SARD_TRY(stage == SARD_STAGE_SKEL ? sard_cat_loss(&L, st) : sard_gauss_loss(&L, st));
   if (!bwd) return 0;
-  SideCtx* side = side_for(as_stream(st));
   SARD_TRY(sard_loss_reduce(sb.gstat, B, 4 + s.out_dim, stats, s.log_std >= 0 ? G + s.log_std : nullptr, s.out_dim,
                             s.log_std >= 0 ? P + s.log_std : nullptr, st));
 
