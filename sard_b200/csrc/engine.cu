@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "encoder.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -101,7 +102,7 @@ inline long long wg_partials(int M, int N1, int N2, int /*unused*/) {
   return (long long)ceil_div(M, sard_wgrad_chunk_rows(M, N1, N2)) * N1 * (N2 + 1);
 }
 
-constexpr int WG_CHUNK = 128;     // rows per grouped weight-gradient chunk
+const int WG_CHUNK = getenv("SARD_WG_CHUNK") ? atoi(getenv("SARD_WG_CHUNK")) : 256;     // rows per grouped weight-gradient chunk
 constexpr int IL_TILE = 128;      // rows per grouped-GEMM tile (= BM of gemm_kernel)
 
 struct TowerBufs {

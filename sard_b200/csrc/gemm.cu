@@ -168,6 +168,8 @@ int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st);   // umma.cu; -
 int sard_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st);      // gemm_fast.cu; -1 = not covered
 int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st);
+int sard_gemm_skinny_fwd(const SardGemm* g, cudaStream_t st);        // gemm_skinny.cu; -1 = not covered
+int sard_gemm_skinny_bwd(const SardGemm* g, cudaStream_t st);
 int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
 extern "C" int sard_set_gemm_engine(int engine) { g_sard_gemm_engine = engine; return 0; }
 extern "C" int sard_get_gemm_engine(void) { return g_sard_gemm_engine; }
@@ -183,6 +185,10 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
   if (g_sard_gemm_engine >= 1) {
     const int r = sard_umma_gemm(g, NT, st);
+    if (r >= 0) return r;
+  }
+  if (NT ? g->N <= 8 : g->R <= 8) {                   // value head, last JSMLP layer: streaming kernels
+    const int r = NT ? sard_gemm_skinny_fwd(g, st) : sard_gemm_skinny_bwd(g, st);
     if (r >= 0) return r;
   }
   {

@@ -283,50 +283,10 @@ __global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) 
   if (do_bias) part[(size_t)(c10 + tid) * ldpart + w.N2] = bsum;
 }
 
-// Skinny weight gradient (N1 <= 8: value head, last JSMLP layer): one thread per input column n2 streams the
-// chunk's rows once (coalesced), keeping the N1 partial sums in registers -- no tile padding to 64 outputs.
-__global__ void __launch_bounds__(128) wgrad_skinny_kernel(const SardWGrad w) {
-  pdl_sync();
-  int rs, re;
-  if (w.chunks) {
-    if ((int)blockIdx.x >= *w.num_chunks) return;
-    const int4 t = reinterpret_cast<const int4*>(w.chunks)[blockIdx.x];
-    rs = t.x; re = t.y;
-  } else {
-    rs = blockIdx.x * w.chunk_rows;
-    re = min(w.M, rs + w.chunk_rows);
-    if (rs >= w.M) return;
-  }
-  const int n2 = blockIdx.y * 128 + threadIdx.x;
-  const bool col_ok = n2 < w.N2;
-  const bool do_bias = blockIdx.y == 0 && threadIdx.x < w.N1;
-  float acc[8], bsum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int row = rs; row < re; ++row) {
-    const float* pz = w.P + (size_t)(w.p_rows ? w.p_rows[row] : row) * w.ldp;
-    const float x = col_ok ? __ldg(w.Q + (size_t)(w.q_rows ? w.q_rows[row] : row) * w.ldq + n2) : 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) if (i < w.N1) acc[i] = fmaf(__ldg(pz + i), x, acc[i]);
-    if (do_bias) bsum += __ldg(pz + threadIdx.x);
-  }
-  const int ldpart = w.N2 + 1;
-  float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
-  if (col_ok) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) if (i < w.N1) part[(size_t)i * ldpart + n2] = acc[i];
-  }
-  if (do_bias) part[(size_t)threadIdx.x * ldpart + w.N2] = bsum;
-}
-
 // partial products for aligned shapes; -1 = not covered (caller uses the generic kernel)
+int sard_wgrad_skinny(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st) {
-  if (w->N1 <= 8) {
-    dim3 grid(nchunks, ceil_div(w->N2, 128));
-    sard_launch(wgrad_skinny_kernel, grid, 128, 0, st, *w);
-    SARD_LAUNCH_OK("wgrad_skinny_kernel");
-    return 0;
-  }
+  if (w->N1 <= 8) return sard_wgrad_skinny(w, nchunks, st);        // gemm_skinny.cu
   if (w->N1 % 64 || w->N2 % 128 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
   if (w->N1 % 128 == 0) {
     dim3 grid(nchunks, w->N1 / 128, w->N2 / 128);

@@ -94,15 +94,31 @@ __global__ void gather_kernel(const GatherP p) {
   const int c_tail = p.lead, c_const = p.lead + p.tail, c_hot = c_const + p.nconst;
   const int c_end = c_hot + (p.onehot ? 3 : 0);
   const int total = N * p.ldx;
-  for (int idx = lane; idx < total; idx += 32) {
-    const int i = idx / p.ldx, c = idx - i * p.ldx;
-    float v;
-    if (c < c_tail) v = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + c);
-    else if (c < c_const) v = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + (p.d_obs - p.tail) + (c - c_tail));
-    else if (c < c_hot) v = __ldg(p.consts + (c - c_const));
-    else if (c < c_end) v = (c - c_hot) == st ? 1.f : 0.f;
-    else v = 0.f;
-    p.x[(size_t)(r0 + i) * p.ldx + c] = v;
+  // 4 independent loads in flight per lane: the rows of one graph are scattered over a 100+ MB arena, so
+  // this kernel is pure DRAM latency if the loads are taken one at a time
+  for (int base = lane; base < total; base += 128) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + 32 * u;
+      const int i = idx / p.ldx, c = idx - i * p.ldx;
+      float t = 0.f;
+      if (idx < total) {
+        if (c < c_tail) t = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + c);
+        else if (c < c_const) t = __ldg(p.obs + (size_t)(a0 + i) * p.d_obs + (p.d_obs - p.tail) + (c - c_tail));
+        else if (c < c_hot) t = __ldg(p.consts + (c - c_const));
+        else if (c < c_end) t = (c - c_hot) == st ? 1.f : 0.f;
+      }
+      v[u] = t;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + 32 * u;
+      if (idx < total) {
+        const int i = idx / p.ldx, c = idx - i * p.ldx;
+        p.x[(size_t)(r0 + i) * p.ldx + c] = v[u];
+      }
+    }
   }
   for (int i = lane; i < N; i += 32) {
     p.nd_graph[r0 + i] = warp;
