@@ -42,6 +42,10 @@ def main():
         arena.advantages.copy_(a.reshape(-1)); arena.returns.copy_(r.reshape(-1))
         agent.update_policy_packed(arena)
 
+    only = os.environ.get('ONLY', '')
+    if only:                      # run one net alone: how long is each stream's own chain?
+        skip = agent.value_net.engine if only == 'policy' else agent.policy_net.engine
+        skip.train_step = lambda *a, **k: None
     for overlap in (True, False):
         agent.overlap_nets = overlap
         for _ in range(2):
