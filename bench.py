@@ -262,10 +262,16 @@ def run_native(args):
     # ---- per-call-site table (diagnostic pass, not part of any reported throughput) ----------------
     site_rows = None
     top_site = None
+    # run serialised (one stream, no side streams) so a site's time is its kernels' own time, comparable with
+    # the ncu launch list; the timed region below runs the normal overlapped schedule
+    agent.overlap_nets = False
+    lib.sard_set_wgrad_overlap(0)
     if rank == 0:
         lib.sard_prof_enable(0xFFFFFFFF, 200000)
     resident_step(arena)                   # every rank takes part (the step contains collectives)
     torch.cuda.synchronize()
+    agent.overlap_nets = True
+    lib.sard_set_wgrad_overlap(1)
     if rank == 0:
         import ctypes as C
         buf = (C.c_double * (4 * 24))()
@@ -279,6 +285,7 @@ def run_native(args):
                                   'tflops': fl / ms / 1e9 if ms > 0 else 0.0, 'gbs': by / ms / 1e6 if ms > 0 else 0.0})
         site_rows.sort(key=lambda r: -r['ms'])
         top_site = site_rows[0]['id'] if site_rows else None
+        site_total_ms = sum(r['ms'] for r in site_rows)
     if world > 1:
         t = torch.tensor([top_site if top_site is not None else -1], device=dev)
         dist.broadcast(t, 0)
@@ -321,8 +328,15 @@ def run_native(args):
                     'pipe': 'fp32 FFMA (SIMT); parity target rtol 1e-4 rules out single-pass TF32/bf16',
                     'fp32_peak_tflops': FP32_PEAK_TFLOPS, 'frac_of_fp32_peak': ach / FP32_PEAK_TFLOPS,
                     'algorithmic_gbs': by / tms / 1e6}
+        iso = next(r for r in site_rows if r['id'] == top_site)
         roof.update({'kernel': f'{kind}.{SITE_PASS[top_site % 3]}', 'launches_timed': int(n), 'avg_launch_us': tms / n * 1e3 if n else None,
-                     'share_of_step': tms / ms, 'peak_source': pk['source'] + ' (sustained figure: kernel timed inside a long step)'})
+                     'share_of_step': tms / ms, 'peak_source': pk['source'] + ' (sustained figure: kernel timed inside a long step)',
+                     'timing': 'CUDA events on the launching stream inside the timed region; four streams run concurrently there '
+                               '(critic, policy and their weight-gradient side streams), so this is the launch duration while '
+                               'sharing the SMs; the isolated_* keys are the same site timed in a serialised pass before the timed region',
+                     'isolated_avg_launch_us': iso['ms'] / iso['launches'] * 1e3,
+                     'isolated_achieved': iso['gbs'] if kind == 'csr_aggregate' else iso['tflops'],
+                     'isolated_share_of_site_time': iso['ms'] / site_total_ms})
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -29,6 +29,8 @@ typedef void* sard_stream_t;
 #define SARD_MAX_MLP 4
 #define SARD_MAX_IL 4
 #define SARD_ACTION_DIM 8          /* [control(1) | attr(6) | skel(1)], transform2act_policy.py:66 */
+/* row stride of one weight-gradient partial: N2 products + the bias column, padded to 16 bytes */
+#define SARD_WG_LDPART(N2) (((N2) + 4) & ~3)
 #define SARD_EXT_DIM 64            /* ObsEncoder out_dim, jsmlp.py:8 */
 
 enum { SARD_ACT_NONE = 0, SARD_ACT_RELU = 1, SARD_ACT_TANH = 2, SARD_ACT_SIGMOID = 3 };
@@ -230,11 +232,11 @@ typedef struct {
   float* dW0; int ldw0; float* dW1; int ldw1; int w_split;   /* dW[c1, c2] destination, split on c2 */
   long long w_slot_stride;                       /* floats between slots (grouped) */
   float* db; int b_slot_stride;                  /* optional bias grad [N1] (per slot when grouped) */
-  float* partials;                               /* scratch float[max_chunks * N1 * (N2+1)] */
+  float* partials;                               /* scratch float[max_chunks * N1 * SARD_WG_LDPART(N2)] */
 } SardWGrad;
 /* dW += dZ^T A, db += colsum(dZ): two kernels (per-chunk partial products, ordered reduction).
  * Ungrouped calls may pass chunk_rows = 0 to let the library pick sard_wgrad_chunk_rows(M,N1,N2)
- * (the partials scratch must then hold ceil(M/that) * N1 * (N2+1) floats). */
+ * (the partials scratch must then hold ceil(M/that) * N1 * SARD_WG_LDPART(N2) floats). */
 int sard_wgrad_chunk_rows(int M, int N1, int N2);
 int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream);
 

@@ -99,7 +99,7 @@ struct Bump {
 inline int r4(int v) { return (v + 3) & ~3; }
 inline long long wg_partials(int M, int N1, int N2, int /*unused*/) {
   if (M <= 0) return 0;
-  return (long long)ceil_div(M, sard_wgrad_chunk_rows(M, N1, N2)) * N1 * (N2 + 1);
+  return (long long)ceil_div(M, sard_wgrad_chunk_rows(M, N1, N2)) * N1 * SARD_WG_LDPART(N2);
 }
 
 const int WG_CHUNK = getenv("SARD_WG_CHUNK") ? atoi(getenv("SARD_WG_CHUNK")) : 256;     // rows per grouped weight-gradient chunk
@@ -492,7 +492,7 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
     sb.de1 = b.f((long long)B * SARD_EXT_DIM);
     long long need = tower_wg_need(s.tower, n);
     long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
-    for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * (s.il[j].in + 1); need = v > need ? v : need; }
+    for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * SARD_WG_LDPART(s.il[j].in); need = v > need ? v : need; }
     sb.wg = b.f(need);
   } else {
     sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = nullptr;

@@ -307,7 +307,7 @@ wgrad_kernel(const SardWGrad w) {
     __syncthreads();
     buf ^= 1;
   }
-  const int ldpart = w.N2 + 1;
+  const int ldpart = SARD_WG_LDPART(w.N2);
   float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
 #pragma unroll
   for (int i = 0; i < T1; ++i) {
@@ -329,7 +329,7 @@ wgrad_kernel(const SardWGrad w) {
 __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
   pdl_sync();
   __shared__ float part[WR_SLICES][33];
-  const int ldpart = w.N2 + 1;
+  const int ldpart = SARD_WG_LDPART(w.N2);
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int total = w.N1 * ldpart;
   int k0, k1, slot = 0;
@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
 #pragma unroll
       for (int j = 1; j < WR_SLICES; ++j) s += part[j][lane];
       const int c1 = e / ldpart, c2 = e - c1 * ldpart;
-      if (c2 == w.N2) {
-        if (w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
+      if (c2 >= w.N2) {
+        if (c2 == w.N2 && w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
       } else if (c2 < w.w_split) {
         w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c2] += s;
       } else {
@@ -433,7 +433,7 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
     sard_launch(wgrad_kernel<64, 64, 16, 4, 4>, grid, 256, 0, st, *w);
   }
   if (umma_rc != 0) SARD_LAUNCH_OK("wgrad_kernel");
-  int rblocks = ceil_div((long long)w->N1 * (w->N2 + 1), 32);
+  int rblocks = ceil_div((long long)w->N1 * SARD_WG_LDPART(w->N2), 32);
   if (w->grp_chunk_ptr && rblocks > 64) rblocks = 64;
   dim3 rgrid(rblocks, w->grp_chunk_ptr ? w->n_groups : 1);
   sard_launch(wgrad_reduce_kernel, rgrid, 32 * WR_SLICES, 0, st, *w, w->chunks ? 0 : nchunks);

@@ -272,13 +272,13 @@ __global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) 
     __syncthreads();
     buf ^= 1;
   }
-  const int ldpart = w.N2 + 1;
+  const int ldpart = SARD_WG_LDPART(w.N2);
   float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pp[j] = acc[i][j];
+    float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * 8;      // 16-byte aligned: ldpart % 4 == 0
+    *reinterpret_cast<float4*>(pp) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
   }
   if (do_bias) part[(size_t)(c10 + tid) * ldpart + w.N2] = bsum;
 }

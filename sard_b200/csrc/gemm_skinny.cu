@@ -8,6 +8,7 @@
 // -1 from the sard_*_skinny entry points means "shape not covered, use the tiled kernels".
 #include "common.cuh"
 
+#define SKINNY_ROWS 16
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ------------------------------------------------------------------------------------------ forward
@@ -23,6 +24,9 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const SardGemm g) {
     row_end = min(g.M, row_start + 128);
     if (row_start >= g.M) return;
   }
+  // blockIdx.y: 16-row slice of the 128-row tile (the head has only M/128 = 16 tiles: slices fill the SMs)
+  row_start += blockIdx.y * SKINNY_ROWS;
+  row_end = min(row_end, row_start + SKINNY_ROWS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* W = g.B0 + (size_t)group * g.b_group_stride;
   const float* bias = g.bias ? g.bias + (size_t)group * g.bias_group_stride : nullptr;
@@ -65,7 +69,7 @@ int sard_gemm_skinny_fwd(const SardGemm* g, cudaStream_t st) {
     return -1;
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
-  sard_launch(skinny_fwd_kernel, tiles, 256, 0, st, *g);
+  sard_launch(skinny_fwd_kernel, dim3(tiles, 128 / SKINNY_ROWS), 256, 0, st, *g);
   SARD_LAUNCH_OK("skinny_fwd_kernel");
   return 0;
 }
@@ -83,6 +87,9 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const SardGemm g) {
     row_end = min(g.M, row_start + 128);
     if (row_start >= g.M) return;
   }
+  row_start += blockIdx.y * SKINNY_ROWS;
+  row_end = min(row_end, row_start + SKINNY_ROWS);
+  if (row_start >= row_end) return;
   const float* W = g.B0 + (size_t)group * g.b_group_stride;
   const int N4 = g.N >> 2;
   const int total = (row_end - row_start) * N4;
@@ -117,7 +124,7 @@ int sard_gemm_skinny_bwd(const SardGemm* g, cudaStream_t st) {
   if (g->Dact && (g->ldd % 4 || !al16(g->Dact))) return -1;
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
-  sard_launch(skinny_bwd_kernel, tiles, 256, 0, st, *g);
+  sard_launch(skinny_bwd_kernel, dim3(tiles, 128 / SKINNY_ROWS), 256, 0, st, *g);
   SARD_LAUNCH_OK("skinny_bwd_kernel");
   return 0;
 }
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const SardWGrad w) {
   __shared__ float bred[8][8];
   if (do_bias) bred[ty][tx] = bsum;
   __syncthreads();
-  const int ldpart = w.N2 + 1;
+  const int ldpart = SARD_WG_LDPART(w.N2);
   float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
   for (int e = ty * 32 + tx; e < w.N1 * 128; e += 256) {
     const int i = e >> 7, cc = e & 127;

@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_wgrad_kernel(const SardW
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();
 
-  const int ldpart = w.N2 + 1;
+  const int ldpart = SARD_WG_LDPART(w.N2);
   float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
   constexpr int NCHUNK = NB / 32;
   for (int cc = half; cc < NCHUNK; cc += 2) {

@@ -323,7 +323,7 @@ def test_index_linear_grouped_forward_backward_vs_oracle(L):
     slots = np.full(mi, -1, dtype=np.int32); slots[live] = np.arange(len(live))
     slot_d = dev(slots)
     gW = torch.zeros(len(live), N, K, device='cuda'); gb = torch.zeros(len(live), N, device='cuda')
-    part = torch.zeros(t['max_chunks'] * N * (K + 1), device='cuda')
+    part = torch.zeros(t['max_chunks'] * N * (K + 4), device='cuda')
     w = L.SardWGrad()
     w.P, w.ldp, w.p_rows, w.Q, w.ldq, w.M, w.N1, w.N2 = L.ptr(dZ), N, L.ptr(t['srow']), L.ptr(xs), K, n, N, K
     w.chunks, w.num_chunks, w.max_chunks, w.chunk_rows = L.ptr(t['chunks']), t['counts'].data_ptr() + 4, t['max_chunks'], 256
@@ -343,7 +343,7 @@ def test_weight_gradient_dense_split(L, M, N1, N2):
     dZd, Ad = dZ.cuda(), A.cuda()
     split = N2 // 2
     dW0 = torch.ones(N1, split, device='cuda'); dW1 = torch.ones(N1, N2 - split, device='cuda'); db = torch.ones(N1, device='cuda')
-    part = torch.zeros(((M + 255) // 256) * N1 * (N2 + 1), device='cuda')
+    part = torch.zeros(((M + 255) // 256) * N1 * (N2 + 4), device='cuda')
     w = L.SardWGrad()
     w.P, w.ldp, w.Q, w.ldq, w.M, w.N1, w.N2, w.chunk_rows = L.ptr(dZd), N1, L.ptr(Ad), N2, M, N1, N2, 256
     w.dW0, w.ldw0, w.dW1, w.ldw1, w.w_split, w.db, w.partials = L.ptr(dW0), split, L.ptr(dW1), N2 - split, split, L.ptr(db), L.ptr(part)
