@@ -68,6 +68,9 @@ int sard_get_wgrad_overlap(void);
 #define SARD_PROF_SITES 24
 int sard_prof_enable(unsigned mask, int capacity);
 int sard_prof_collect(double* rows, int n_sites);
+/* Raw timeline of the recorded launches: rows[i*4..] = {site, stream ordinal, start ms, end ms} relative to the
+ * first record; returns the number of rows written (<= capacity).  Call before sard_prof_collect. */
+int sard_prof_timeline(double* rows, int capacity);
 
 /* =====================================================================================
  * Packing: graph indexing layouts (bit-exact integer work)

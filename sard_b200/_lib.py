@@ -111,6 +111,7 @@ _PROTOS = {
     'sard_get_wgrad_overlap': (ci, []),
     'sard_prof_enable': (ci, [C.c_uint, ci]),
     'sard_prof_collect': (ci, [P(cd), ci]),
+    'sard_prof_timeline': (ci, [P(cd), ci]),
     'sard_build_csr': (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     'sard_orbit_rep': (ci, [vp, vp, ci, vp, ci, vp, vp, vp]),
     'sard_gather_nodes': (ci, [P(SardArena), P(SardSel), P(SardGatherOut), vp]),

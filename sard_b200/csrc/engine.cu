@@ -45,15 +45,17 @@ inline void site(int kind, int pass) { g_sard_site = 3 * kind + pass; }
 
 // Weight gradients leave the critical path: in every backward pass the chain dz_l -> bwd_data -> dz_{l-1}
 // is what the next layer waits for, while dW_l (partials + ordered reduce) is only needed by the optimiser
-// step.  Each launching stream owns a low-priority side stream; a weight gradient is forked onto it with an
-// event recorded right after dz_l was produced, and the run joins it before returning.  The side
-// stream serialises the weight gradients among themselves, so they can share one partials scratch;
-// dz buffers are per layer (no ping-pong) so the main stream never overwrites one that is still read.
+// step.  Each launching stream owns two low-priority side streams (one for the tower's weight gradients,
+// one for the head / MLP / JSMLP / encoder ones: a single side stream lagged 100-150 us behind the main
+// chain at the end of every minibatch); a weight gradient is forked onto its side stream with an event
+// recorded right after dz_l was produced, and the run joins both before returning.  A side stream
+// serialises its weight gradients, so each has ONE partials scratch; dz buffers are per layer (no
+// ping-pong) so the main stream never overwrites one that is still read.
 struct SideCtx {
-  cudaStream_t main, side;
+  cudaStream_t main, side[2];      // [0]: tower weight gradients, [1]: head / MLP / JSMLP / encoder work
   cudaEvent_t ev[8];
   int k;
-  bool forked;
+  bool forked[2];
 };
 std::mutex g_side_mu;
 std::unordered_map<cudaStream_t, SideCtx*> g_side;
@@ -62,31 +64,35 @@ SideCtx* side_for(cudaStream_t main) {
   if (!g_sard_wgrad_overlap) return nullptr;
   std::lock_guard<std::mutex> lock(g_side_mu);
   auto it = g_side.find(main);
-  if (it != g_side.end()) { it->second->forked = false; return it->second; }
+  if (it != g_side.end()) { it->second->forked[0] = it->second->forked[1] = false; return it->second; }
   SideCtx* c = new SideCtx();
-  c->main = main; c->k = 0; c->forked = false;
+  c->main = main; c->k = 0; c->forked[0] = c->forked[1] = false;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
   g_side[main] = c;
   return c;
 }
 // stream for a weight gradient whose inputs were just produced on `st`
-sard_stream_t wg_stream(SideCtx* c, sard_stream_t st) {
+sard_stream_t wg_stream(SideCtx* c, sard_stream_t st, int which) {
   if (!c) return st;
   cudaEvent_t e = c->ev[c->k++ & 7];
   cudaEventRecord(e, c->main);
-  cudaStreamWaitEvent(c->side, e, 0);
-  c->forked = true;
-  return reinterpret_cast<sard_stream_t>(c->side);
+  cudaStreamWaitEvent(c->side[which], e, 0);
+  c->forked[which] = true;
+  return reinterpret_cast<sard_stream_t>(c->side[which]);
 }
 int side_join(SideCtx* c) {
-  if (!c || !c->forked) return 0;
-  cudaEvent_t e = c->ev[c->k++ & 7];
-  SARD_CUDA(cudaEventRecord(e, c->side));
-  SARD_CUDA(cudaStreamWaitEvent(c->main, e, 0));
-  c->forked = false;
+  if (!c) return 0;
+  for (int i = 0; i < 2; ++i) {
+    if (!c->forked[i]) continue;
+    cudaEvent_t e = c->ev[c->k++ & 7];
+    SARD_CUDA(cudaEventRecord(e, c->side[i]));
+    SARD_CUDA(cudaStreamWaitEvent(c->main, e, 0));
+    c->forked[i] = false;
+  }
   return 0;
 }
 
@@ -197,7 +203,7 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
     w.dW0 = G + tw.wl[l - 1]; w.ldw0 = hi; w.dW1 = G + tw.wr[l - 1]; w.ldw1 = hi; w.w_split = hi;
     w.db = tw.has_bias ? G + tw.bl[l - 1] : nullptr; w.partials = wg_scratch;
     site(K_GCONV, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 0)));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
     g.M = n; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
@@ -213,7 +219,7 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
   w.P = t.dz[0]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;
   w.dW0 = G + tw.in_w; w.ldw0 = tw.D; w.w_split = tw.D; w.db = G + tw.in_b; w.partials = wg_scratch;
   site(K_INFC, 2);
-  SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+  SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 0)));
   return side_join(side);
 }
 
@@ -304,7 +310,7 @@ struct ValueBufs {
   TowerBufs t;
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
-  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg;
+  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2;
 };
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
@@ -324,13 +330,13 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
     vb.dcat = b.f((long long)B * vb.ldcat);
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
     vb.de1 = b.f((long long)B * SARD_EXT_DIM);
-    long long need = tower_wg_need(net.tower, n);
-    long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
+    vb.wg = b.f(tower_wg_need(net.tower, n));               // side stream 0
+    long long need = enc_wg_need(net.enc, B), v;            // side stream 1
     for (int j = 0; j < net.n_mlp; ++j) { v = wg_partials(B, net.mlp[j].out, net.mlp[j].in, WG_CHUNK); need = v > need ? v : need; }
     v = wg_partials(B, 1, vb.ldcat, WG_CHUNK); need = v > need ? v : need;
-    vb.wg = b.f(need);
+    vb.wg2 = b.f(need);
   } else {
-    vb.dcat = vb.de1 = vb.wg = nullptr;
+    vb.dcat = vb.de1 = vb.wg = vb.wg2 = nullptr;
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = nullptr;
   }
 }
@@ -376,7 +382,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   // the ObsEncoders only need the arena: they run beside the tower and are joined before the value head
   SideCtx* side = side_for(as_stream(st));
   SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
-                            wg_stream(side, st)));
+                            wg_stream(side, st, 1)));
   SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
   // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
   const int hL = tw.h[tw.L];
@@ -408,9 +414,9 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   {
     SardWGrad w = wgrad0();
     w.P = vb.dv; w.ldp = 1; w.Q = vb.cat; w.ldq = vb.ldcat; w.M = B; w.N1 = 1; w.N2 = vb.ldcat;
-    w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg;
+    w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg2;
     site(K_HEAD, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 1)));
     SardGemm g = gemm0();
     g.A = vb.dv; g.lda = 1; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat;
     g.M = B; g.N = vb.ldcat; g.R = 1; g.Y = vb.dcat; g.ldy = vb.ldcat;
@@ -421,7 +427,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   }
   // the encoders' backward ends in weight gradients only: all of it runs beside the MLP / tower backward
   SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
-                             vb.de1, vb.wg, wg_stream(side, st)));
+                             vb.de1, vb.wg2, wg_stream(side, st, 1)));
   // MLP backward (dz of layer j lives in dzj with leading dimension ldz)
   const float* dzj = vb.dcat; int ldz = vb.ldcat;
   SARD_CUDA(cudaMemsetAsync(vb.t.dz[tw.L], 0, sizeof(float) * (size_t)n * hL, as_stream(st)));
@@ -429,9 +435,9 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     SardWGrad w = wgrad0();
     w.P = dzj; w.ldp = ldz; w.M = B; w.N1 = net->mlp[j].out; w.N2 = net->mlp[j].in;
     if (j == 0) { w.Q = vb.t.hout; w.ldq = hL; w.q_rows = vb.t.root_row; } else { w.Q = vb.m[j - 1]; w.ldq = net->mlp[j - 1].out; }
-    w.dW0 = G + net->mlp[j].w; w.ldw0 = net->mlp[j].in; w.w_split = net->mlp[j].in; w.db = G + net->mlp[j].b; w.partials = vb.wg;
+    w.dW0 = G + net->mlp[j].w; w.ldw0 = net->mlp[j].in; w.w_split = net->mlp[j].in; w.db = G + net->mlp[j].b; w.partials = vb.wg2;
     site(K_MLP, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 1)));
     SardGemm g = gemm0();
     g.A = dzj; g.lda = ldz; g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in;
     g.M = B; g.N = net->mlp[j].in; g.R = net->mlp[j].out; g.dsplit = g.N;
@@ -458,7 +464,7 @@ struct StageBufs {
   float* e1[3]; float* ext;
   int *srow, *spos, *grp_ptr, *tiles, *chunks, *grp_chunk_ptr, *counts, *sort_scratch;
   float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
-  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg;
+  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2;
   int max_tiles, max_chunks;
 };
 
@@ -490,12 +496,12 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
     sb.dxs = b.f((long long)n * sb.ldxs);
     sb.dext = b.f((long long)B * 3 * SARD_EXT_DIM);
     sb.de1 = b.f((long long)B * SARD_EXT_DIM);
-    long long need = tower_wg_need(s.tower, n);
-    long long v = enc_wg_need(net.enc, B); need = v > need ? v : need;
+    sb.wg = b.f(tower_wg_need(s.tower, n));                 // side stream 0
+    long long need = enc_wg_need(net.enc, B), v;            // side stream 1
     for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * SARD_WG_LDPART(s.il[j].in); need = v > need ? v : need; }
-    sb.wg = b.f(need);
+    sb.wg2 = b.f(need);
   } else {
-    sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = nullptr;
+    sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = sb.wg2 = nullptr;
     for (int j = 0; j < s.n_il; ++j) sb.dH[j] = nullptr;
   }
 }
@@ -543,7 +549,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   // the ObsEncoders and the body-index sort only need the gathered run: they run beside the tower
   SideCtx* side = side_for(as_stream(st));
   {
-    sard_stream_t s2 = wg_stream(side, st);
+    sard_stream_t s2 = wg_stream(side, st, 1);
     SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, s2));
     SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
                                 sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
@@ -606,9 +612,9 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     w.chunks = sb.chunks; w.num_chunks = sb.counts + 1; w.max_chunks = sb.max_chunks;
     w.grp_chunk_ptr = sb.grp_chunk_ptr; w.n_groups = s.max_index; w.slot_of_group = s.slot_of_index;
     w.dW0 = s.GT + s.il[j].gW; w.ldw0 = s.il[j].in; w.w_split = s.il[j].in; w.w_slot_stride = (long long)s.il[j].out * s.il[j].in;
-    w.db = s.GT + s.il[j].gb; w.b_slot_stride = s.il[j].out; w.partials = sb.wg;
+    w.db = s.GT + s.il[j].gb; w.b_slot_stride = s.il[j].out; w.partials = sb.wg2;
     site(K_IL, 2);
-    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st)));
+    SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 1)));
     SardGemm g = gemm0();
     g.A = dz; g.lda = ldz; g.a_rows = dz_rows;
     g.B0 = s.il[j].W; g.ldb0 = s.il[j].in; g.b_split = s.il[j].in; g.b_group_stride = (long long)s.il[j].out * s.il[j].in;
@@ -623,6 +629,6 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   SARD_TRY(sard_unsort_grad(sb.dxs, sb.ldxs, sb.spos, sel->cum, sel->node_base, B, sb.t.hout, hL, hL,
                             tw.L > 0 ? tw.act : SARD_ACT_NONE, sb.t.dz[tw.L], hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM,
                             sb.dext, 3 * SARD_EXT_DIM, st));
-  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg, wg_stream(side, st)));
+  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg2, wg_stream(side, st, 1)));
   return tower_backward(tw, P, G, arena, sel, sb.t, sb.wg, side, st);
 }

@@ -168,6 +168,7 @@ int sard_umma_gemm(const SardGemm* g, bool nt, cudaStream_t st);   // umma.cu; -
 int sard_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st);      // gemm_fast.cu; -1 = not covered
 int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st);
+int sard_gemm_mma(const SardGemm* g, bool nt, cudaStream_t st);       // gemm_mma.cu; -1 = not covered
 int sard_gemm_skinny_fwd(const SardGemm* g, cudaStream_t st);        // gemm_skinny.cu; -1 = not covered
 int sard_gemm_skinny_bwd(const SardGemm* g, cudaStream_t st);
 int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
@@ -183,8 +184,12 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   const double groups = g->b_group_stride ? 13.0 : 1.0;   // weight slabs touched (live indices, nominal)
   ProfScope prof(st, 2.0 * g->M * (double)g->N * g->R,
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
-  if (g_sard_gemm_engine >= 1) {
+  if (g_sard_gemm_engine == 1 || g_sard_gemm_engine == 2) {
     const int r = sard_umma_gemm(g, NT, st);
+    if (r >= 0) return r;
+  }
+  if (g_sard_gemm_engine == 3) {
+    const int r = sard_gemm_mma(g, NT, st);
     if (r >= 0) return r;
   }
   if (NT ? g->N <= 8 : g->R <= 8) {                   // value head, last JSMLP layer: streaming kernels
@@ -415,7 +420,7 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
   ProfScope prof(st, 2.0 * w->M * (double)w->N1 * w->N2,
                  4.0 * ((double)w->M * w->N1 + (double)w->M * w->N2 + wgroups * (double)w->N1 * w->N2));
   int umma_rc = -1;
-  if (g_sard_gemm_engine >= 1) {
+  if (g_sard_gemm_engine == 1 || g_sard_gemm_engine == 2) {
     umma_rc = sard_umma_wgrad(w, nchunks, st);
     if (umma_rc > 0) return umma_rc;
   }

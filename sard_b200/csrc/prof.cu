@@ -9,7 +9,7 @@ extern "C" int sard_get_pdl(void) { return g_sard_pdl; }
 thread_local int g_sard_site = -1;
 
 namespace {
-struct Rec { int site; double flops, bytes; cudaEvent_t a, b; };
+struct Rec { int site; double flops, bytes; cudaEvent_t a, b; cudaStream_t st; };
 unsigned g_mask = 0;
 int g_capacity = 0;
 std::vector<Rec> g_recs;
@@ -21,7 +21,7 @@ ProfScope::ProfScope(cudaStream_t stream, double flops, double bytes) : slot(-1)
   if (g_mask == 0 || site < 0 || site >= SARD_PROF_SITES || !((g_mask >> site) & 1u)) return;
   if ((int)g_recs.size() >= g_capacity) return;
   Rec r;
-  r.site = site; r.flops = flops; r.bytes = bytes;
+  r.site = site; r.flops = flops; r.bytes = bytes; r.st = stream;
   for (cudaEvent_t* e : {&r.a, &r.b}) {
     if (!g_pool.empty()) { *e = g_pool.back(); g_pool.pop_back(); }
     else if (cudaEventCreate(e) != cudaSuccess) return;
@@ -42,6 +42,26 @@ extern "C" int sard_prof_enable(unsigned mask, int capacity) {
   g_capacity = capacity;
   if (capacity > 0) g_recs.reserve(capacity);
   return 0;
+}
+
+// rows[i*4 ..] = {site, stream ordinal (order of first use), start ms, end ms} relative to the first record;
+// does not clear the records (call sard_prof_collect afterwards)
+extern "C" int sard_prof_timeline(double* rows, int capacity) {
+  std::vector<cudaStream_t> streams;
+  int n = 0;
+  for (const Rec& r : g_recs) {
+    if (n >= capacity) break;
+    SARD_CUDA(cudaEventSynchronize(r.b));
+    float t0 = 0.f, t1 = 0.f;
+    SARD_CUDA(cudaEventElapsedTime(&t0, g_recs[0].a, r.a));
+    SARD_CUDA(cudaEventElapsedTime(&t1, g_recs[0].a, r.b));
+    int sid = -1;
+    for (size_t k = 0; k < streams.size(); ++k) if (streams[k] == r.st) sid = (int)k;
+    if (sid < 0) { streams.push_back(r.st); sid = (int)streams.size() - 1; }
+    rows[n * 4 + 0] = r.site; rows[n * 4 + 1] = sid; rows[n * 4 + 2] = t0; rows[n * 4 + 3] = t1;
+    ++n;
+  }
+  return n < 0 ? 0 : n;
 }
 
 extern "C" int sard_prof_collect(double* rows, int n_sites) {

@@ -45,7 +45,7 @@ for name, M, N1, N2 in [('gconv wgrad', 18432, 64, 128), ('il1 wgrad', 18432, 12
     dZ = torch.randn(M, N1, device='cuda'); X = torch.randn(M, N2, device='cuda')
     dW = torch.zeros(N1, N2, device='cuda'); db = torch.zeros(N1, device='cuda')
     rows = L.lib.sard_wgrad_chunk_rows(M, N1, N2)
-    part = torch.zeros(((M + rows - 1) // rows) * N1 * (N2 + 1), device='cuda')
+    part = torch.zeros(((M + rows - 1) // rows) * N1 * (N2 + 4), device='cuda')
     w = L.SardWGrad()
     w.P, w.ldp, w.Q, w.ldq, w.M, w.N1, w.N2, w.chunk_rows = L.ptr(dZ), N1, L.ptr(X), N2, M, N1, N2, 0
     w.dW0, w.ldw0, w.w_split, w.db, w.partials = L.ptr(dW), N2, N2, L.ptr(db), L.ptr(part)
