@@ -100,18 +100,28 @@ __global__ void __launch_bounds__(256) gemm_mma_kernel(const SardGemm g) {
           split_tf32(ap[4 * LDA_S], ah[i][2], al[i][2]);
           split_tf32(ap[4 * LDA_S + 8], ah[i][3], al[i][3]);
         }
+        // 4 column tiles at a time: 8 independent accumulators between two MMAs on the same one (HMMA latency)
 #pragma unroll
-        for (int j = 0; j < NTW; ++j) {
-          uint32_t bh[2], bl[2];
-          const float* bp = Bc + (k8 + tq) * LDB_S + wn + j * 8 + gq;
-          split_tf32(bp[0], bh[0], bl[0]);
-          split_tf32(bp[4 * LDB_S], bh[1], bl[1]);
+        for (int j0 = 0; j0 < NTW; j0 += 4) {
+          uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            mma_tf32(acc[i][j], al[i], bh);                 // small terms first
-            mma_tf32(acc[i][j], ah[i], bl);
-            mma_tf32(acc[i][j], ah[i], bh);
+          for (int jj = 0; jj < 4; ++jj) {
+            const float* bp = Bc + (k8 + tq) * LDB_S + wn + (j0 + jj) * 8 + gq;
+            split_tf32(bp[0], bh[jj][0], bl[jj][0]);
+            split_tf32(bp[4 * LDB_S], bh[jj][1], bl[jj][1]);
           }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) mma_tf32(acc[i][j0 + jj], al[i], bh[jj]);      // small terms first
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) mma_tf32(acc[i][j0 + jj], ah[i], bl[jj]);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) mma_tf32(acc[i][j0 + jj], ah[i], bh[jj]);
         }
       }
     }
