@@ -123,23 +123,20 @@ PyObject* py_scan(PyObject*, PyObject* args) {
   return Py_BuildValue("(LLLLLLL)", (long long)items.size(), n, e, d_obs, H, O, G);
 }
 
-PyObject* py_fill(PyObject*, PyObject* args) {
-  PyObject *states, *actions, *o_obs, *o_act, *o_np, *o_ep, *o_es, *o_ed, *o_st, *o_body, *o_hf, *o_ob, *o_go;
-  int nthreads = 4;
-  if (!PyArg_ParseTuple(args, "OOOOOOOOOOOOO|i", &states, &actions, &o_obs, &o_act, &o_np, &o_ep, &o_es, &o_ed, &o_st, &o_body,
-                        &o_hf, &o_ob, &o_go, &nthreads)) return nullptr;
-  std::vector<Item> items; std::vector<Py_buffer> keep;
+// shared by fill() and fill_collected(): items are the collected sources, outs the 11 destination buffers
+PyObject* fill_core(const std::vector<Item>& items, PyObject* const o[11], int nthreads) {
+  std::vector<Py_buffer> keep;
   Out obs, act, np_, ep, es, ed, stg, body, hf, ob, go;
-  if (!collect(states, actions, items, keep) || !get_out(o_obs, obs, 4, keep) || !get_out(o_act, act, 4, keep) ||
-      !get_out(o_np, np_, 4, keep) || !get_out(o_ep, ep, 4, keep) || !get_out(o_es, es, 4, keep) || !get_out(o_ed, ed, 4, keep) ||
-      !get_out(o_st, stg, 4, keep) || !get_out(o_body, body, 4, keep) || !get_out(o_hf, hf, 4, keep) || !get_out(o_ob, ob, 4, keep) ||
-      !get_out(o_go, go, 4, keep)) { release(keep); return nullptr; }
+  Out* outs[11] = {&obs, &act, &np_, &ep, &es, &ed, &stg, &body, &hf, &ob, &go};
+  for (int k = 0; k < 11; ++k)
+    if (!get_out(o[k], *outs[k], 4, keep)) { release(keep); return nullptr; }
   const size_t T = items.size();
   if (T == 0) { release(keep); Py_RETURN_NONE; }
   const Py_ssize_t D = items[0].obs.n1, H = items[0].hf.n1, O = items[0].ob.n1, G = items[0].go.n1;
   int32_t* node_ptr = (int32_t*)np_.ptr; int32_t* edge_ptr = (int32_t*)ep.ptr;
   long long n = 0, e = 0;
   const char* err = nullptr;
+  if (np_.len < (Py_ssize_t)T + 1 || ep.len < (Py_ssize_t)T + 1) { release(keep); PyErr_SetString(PyExc_ValueError, "hostpack: pointer buffers too small"); return nullptr; }
   for (size_t t = 0; t < T; ++t) {
     node_ptr[t] = (int32_t)n; edge_ptr[t] = (int32_t)e;
     const Item& it = items[t];
@@ -188,8 +185,54 @@ PyObject* py_fill(PyObject*, PyObject* args) {
   Py_RETURN_NONE;
 }
 
+PyObject* py_fill(PyObject*, PyObject* args) {
+  PyObject *states, *actions, *o[11];
+  int nthreads = 4;
+  if (!PyArg_ParseTuple(args, "OOOOOOOOOOOOO|i", &states, &actions, &o[0], &o[1], &o[2], &o[3], &o[4], &o[5], &o[6], &o[7],
+                        &o[8], &o[9], &o[10], &nthreads)) return nullptr;
+  std::vector<Item> items; std::vector<Py_buffer> keep;
+  if (!collect(states, actions, items, keep)) { release(keep); return nullptr; }
+  PyObject* r = fill_core(items, o, nthreads);
+  release(keep);
+  return r;
+}
+
+// One walk over the Python objects instead of two: collect() keeps the acquired buffers in a capsule that
+// fill_collected() consumes (the list walk is the serial, GIL-bound part of the host path).
+struct Collected { std::vector<Item> items; std::vector<Py_buffer> keep; };
+void collected_free(PyObject* cap) {
+  Collected* c = (Collected*)PyCapsule_GetPointer(cap, "sard_b200.collected");
+  if (c) { release(c->keep); delete c; }
+}
+PyObject* py_collect(PyObject*, PyObject* args) {
+  PyObject *states, *actions = Py_None;
+  if (!PyArg_ParseTuple(args, "O|O", &states, &actions)) return nullptr;
+  Collected* c = new Collected();
+  if (!collect(states, actions, c->items, c->keep)) { release(c->keep); delete c; return nullptr; }
+  long long n = 0, e = 0;
+  for (auto& it : c->items) { n += it.obs.n0; e += it.edges.n1; }
+  const bool any = !c->items.empty();
+  const long long T = (long long)c->items.size(), d_obs = any ? (long long)c->items[0].obs.n1 : 0,
+                  H = any ? (long long)c->items[0].hf.n1 : 0, O = any ? (long long)c->items[0].ob.n1 : 0,
+                  G = any ? (long long)c->items[0].go.n1 : 0;
+  PyObject* cap = PyCapsule_New(c, "sard_b200.collected", collected_free);
+  if (!cap) { release(c->keep); delete c; return nullptr; }
+  return Py_BuildValue("(NLLLLLLL)", cap, T, n, e, d_obs, H, O, G);
+}
+PyObject* py_fill_collected(PyObject*, PyObject* args) {
+  PyObject *cap, *o[11];
+  int nthreads = 4;
+  if (!PyArg_ParseTuple(args, "OOOOOOOOOOOO|i", &cap, &o[0], &o[1], &o[2], &o[3], &o[4], &o[5], &o[6], &o[7], &o[8], &o[9],
+                        &o[10], &nthreads)) return nullptr;
+  Collected* c = (Collected*)PyCapsule_GetPointer(cap, "sard_b200.collected");
+  if (!c) return nullptr;
+  return fill_core(c->items, o, nthreads);
+}
+
 PyMethodDef methods[] = {
     {"scan", py_scan, METH_VARARGS, "scan(states) -> (T, n_total, e_total, d_obs, H, O, G)"},
+    {"collect", py_collect, METH_VARARGS, "collect(states[, actions]) -> (handle, T, n_total, e_total, d_obs, H, O, G)"},
+    {"fill_collected", py_fill_collected, METH_VARARGS, "fill_collected(handle, obs, act, node_ptr, edge_ptr, esrc, edst, stage, body, hf, ob, go[, nthreads])"},
     {"fill", py_fill, METH_VARARGS, "fill(states, actions, obs, act, node_ptr, edge_ptr, esrc, edst, stage, body, hf, ob, go[, nthreads])"},
     {nullptr, nullptr, 0, nullptr}};
 PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_hostpack", "native rollout packer for sard_b200", -1, methods};

@@ -82,13 +82,13 @@ def host_tensors_from_lists(states, actions=None, rewards=None, masks=None, pin:
     """Same from the reference's list-of-states batch; uses the native packer when it is built."""
     if _hostpack is None or isinstance(states[0][0], torch.Tensor):
         return host_tensors_from_rollout(host_rollout_from_lists(states, actions, rewards, masks), pin)
-    T, n, e, d, H, O, G = _hostpack.scan(states)
+    handle, T, n, e, d, H, O, G = _hostpack.collect(states, actions)       # one walk over the Python objects
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
     out = {'obs': mk((n, d), torch.float32), 'actions': mk((n, 8), torch.float32), 'node_ptr': mk((T + 1,), torch.int32),
            'edge_ptr': mk((T + 1,), torch.int32), 'esrc': mk((e,), torch.int32), 'edst': mk((e,), torch.int32),
            'stage': mk((T,), torch.int32), 'body_ind': mk((n,), torch.int32), 'hfield': mk((T, H), torch.float32),
            'obj': mk((T, O), torch.float32), 'goal': mk((T, G), torch.float32)}
-    _hostpack.fill(states, actions, *[out[k].numpy() for k in ('obs', 'actions', 'node_ptr', 'edge_ptr', 'esrc', 'edst', 'stage',
+    _hostpack.fill_collected(handle, *[out[k].numpy() for k in ('obs', 'actions', 'node_ptr', 'edge_ptr', 'esrc', 'edst', 'stage',
                                                                 'body_ind', 'hfield', 'obj', 'goal')], nthreads)
     for k, v in (('rewards', rewards), ('masks', masks)):
         t = mk((T,), torch.float32)
