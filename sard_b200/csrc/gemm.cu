@@ -333,10 +333,10 @@ wgrad_kernel(const SardWGrad w) {
 #define WR_SLICES 8
 __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const SardWGrad w, int nchunks_plain) {
   pdl_sync();
-  __shared__ float part[WR_SLICES][33];
-  const int ldpart = SARD_WG_LDPART(w.N2);
+  __shared__ float4 part[WR_SLICES][32];
+  const int ldpart = SARD_WG_LDPART(w.N2);             // multiple of 4: a float4 never straddles two rows
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int total = w.N1 * ldpart;
+  const int total4 = w.N1 * ldpart / 4;
   int k0, k1, slot = 0;
   if (w.grp_chunk_ptr) {
     const int u = blockIdx.y;
@@ -347,34 +347,49 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
   } else {
     k0 = 0; k1 = nchunks_plain;
   }
-  // grid-stride over 32-element blocks (grouped launches keep the grid small: most groups are empty)
-  for (int eb = blockIdx.x; eb * 32 < total; eb += gridDim.x) {
-    const int e = eb * 32 + lane;
-    float s = 0.f;
-    if (e < total) {
-      const float* p = w.partials + (size_t)e;
-      const size_t stride = (size_t)w.N1 * ldpart;
+  const size_t stride4 = (size_t)w.N1 * ldpart / 4;
+  const float4* P4 = reinterpret_cast<const float4*>(w.partials);
+  // grid-stride over blocks of 32 float4 (grouped launches keep the grid small: most groups are empty)
+  for (int eb = blockIdx.x; eb * 32 < total4; eb += gridDim.x) {
+    const int e4 = eb * 32 + lane;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e4 < total4) {
+      const float4* p = P4 + e4;
       int k = k0 + slice;
       for (; k + 3 * WR_SLICES < k1; k += 4 * WR_SLICES) {
-        const float a0 = p[(size_t)k * stride], a1 = p[(size_t)(k + WR_SLICES) * stride];
-        const float a2 = p[(size_t)(k + 2 * WR_SLICES) * stride], a3 = p[(size_t)(k + 3 * WR_SLICES) * stride];
-        s += a0; s += a1; s += a2; s += a3;
+        const float4 a0 = p[(size_t)k * stride4], a1 = p[(size_t)(k + WR_SLICES) * stride4];
+        const float4 a2 = p[(size_t)(k + 2 * WR_SLICES) * stride4], a3 = p[(size_t)(k + 3 * WR_SLICES) * stride4];
+        s.x += a0.x; s.y += a0.y; s.z += a0.z; s.w += a0.w;
+        s.x += a1.x; s.y += a1.y; s.z += a1.z; s.w += a1.w;
+        s.x += a2.x; s.y += a2.y; s.z += a2.z; s.w += a2.w;
+        s.x += a3.x; s.y += a3.y; s.z += a3.z; s.w += a3.w;
       }
-      for (; k < k1; k += WR_SLICES) s += p[(size_t)k * stride];
+      for (; k < k1; k += WR_SLICES) {
+        const float4 a = p[(size_t)k * stride4];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
     }
     __syncthreads();                    // previous iteration's readers of `part` are done
     part[slice][lane] = s;
     __syncthreads();
-    if (slice == 0 && e < total) {
+    if (slice == 0 && e4 < total4) {
 #pragma unroll
-      for (int j = 1; j < WR_SLICES; ++j) s += part[j][lane];
-      const int c1 = e / ldpart, c2 = e - c1 * ldpart;
-      if (c2 >= w.N2) {
-        if (c2 == w.N2 && w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += s;
-      } else if (c2 < w.w_split) {
-        w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c2] += s;
-      } else {
-        w.dW1[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw1 + (c2 - w.w_split)] += s;
+      for (int j = 1; j < WR_SLICES; ++j) {
+        const float4 a = part[j][lane];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      const int c1 = (e4 * 4) / ldpart, c2 = e4 * 4 - c1 * ldpart;
+      const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c2 + i;
+        if (c >= w.N2) {
+          if (c == w.N2 && w.db) w.db[(size_t)slot * w.b_slot_stride + c1] += v[i];
+        } else if (c < w.w_split) {
+          w.dW0[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw0 + c] += v[i];
+        } else {
+          w.dW1[(size_t)slot * w.w_slot_stride + (size_t)c1 * w.ldw1 + (c - w.w_split)] += v[i];
+        }
       }
     }
   }
@@ -438,7 +453,7 @@ extern "C" int sard_linear_bwd_weight(const SardWGrad* w_in, sard_stream_t strea
     sard_launch(wgrad_kernel<64, 64, 16, 4, 4>, grid, 256, 0, st, *w);
   }
   if (umma_rc != 0) SARD_LAUNCH_OK("wgrad_kernel");
-  int rblocks = ceil_div((long long)w->N1 * SARD_WG_LDPART(w->N2), 32);
+  int rblocks = ceil_div((long long)w->N1 * SARD_WG_LDPART(w->N2) / 4, 32);
   if (w->grp_chunk_ptr && rblocks > 64) rblocks = 64;
   dim3 rgrid(rblocks, w->grp_chunk_ptr ? w->n_groups : 1);
   sard_launch(wgrad_reduce_kernel, rgrid, 32 * WR_SLICES, 0, st, *w, w->chunks ? 0 : nchunks);
