@@ -211,6 +211,16 @@ typedef struct {
   const int* tiles;            /* optional int4 tiles {row_start,row_end,index,0} from sard_sort_by_index */
   const int* num_tiles;        /* device count of tiles */
   int max_tiles;               /* host upper bound (grid size) */
+  /* Optional fused GraphConv neighbour sum (aggr='add', gnn.py:63).  With agg_cols > 0 the A operand is virtual:
+   *   A[m, r] = r < agg_cols ? sum_{j in nbr(m)} S[j, r] : S[m, r - agg_cols],   S = A with leading dimension lda,
+   * nbr(m) = rows gstart(m) + agg_nbr[e], e in [agg_ptr[a], agg_ptr[a+1]) (edge order), a = agg_node[m] the arena
+   * node of row m, gstart(m) = agg_cum[agg_graph[m]] - agg_node_base the first row of m's graph.  agg_out
+   * (optional) receives the sums, [M, agg_cols] with leading dimension ld_agg_out.  Forward: S = x, weights
+   * [lin_l | lin_r].  Backward-data: S = dz with the by-source lists and b_ksplit > 0, which splits the weights on
+   * the reduction index:  W[r, c] = r < b_ksplit ? B0[r*ldb0 + c] : B1[(r - b_ksplit)*ldb1 + c].
+   * Needs R, agg_cols multiples of 16, N a multiple of 64, a_rows == NULL (sard_gemm_agg_supported). */
+  int agg_cols; const int* agg_ptr; const int* agg_nbr; const int* agg_node; const int* agg_graph; const int* agg_cum;
+  int agg_node_base; float* agg_out; int ld_agg_out; int b_ksplit;
 } SardGemm;
 
 /* Engine behind sard_linear_fwd / sard_linear_bwd_data: 0 = fp32 FFMA SIMT tiles, 1 = tcgen05 tensor cores
@@ -221,6 +231,8 @@ int sard_get_gemm_engine(void);
 /* Y = post(act(A W^T + bias)).  Replaces nn.Linear / GraphConv lin_l+lin_r / IndexLinear.forward
  * (gnn.py:57,63; jsmlp.py:15-20,32-40; mlp.py:22-25; critic.py:103). */
 int sard_linear_fwd(const SardGemm* g, sard_stream_t stream);
+/* 1 when a GraphConv layer h_in -> h_out can use the fused neighbour sum (both directions). */
+int sard_gemm_agg_supported(int h_in, int h_out);
 /* dA = (dY W) * act'(Dact)   (autograd of the same call sites). */
 int sard_linear_bwd_data(const SardGemm* g, sard_stream_t stream);
 

@@ -42,7 +42,9 @@ class SardGemm(C.Structure):
                 ('b_group_stride', cll), ('bias', vp), ('bias_group_stride', ci),
                 ('Y', vp), ('ldy', ci), ('y_rows', vp), ('Ypre', vp), ('Dact', vp), ('ldd', ci),
                 ('act', ci), ('post', ci), ('dact0', ci), ('dact1', ci), ('dsplit', ci),
-                ('M', ci), ('N', ci), ('R', ci), ('tiles', vp), ('num_tiles', vp), ('max_tiles', ci)]
+                ('M', ci), ('N', ci), ('R', ci), ('tiles', vp), ('num_tiles', vp), ('max_tiles', ci),
+                ('agg_cols', ci), ('agg_ptr', vp), ('agg_nbr', vp), ('agg_node', vp), ('agg_graph', vp), ('agg_cum', vp),
+                ('agg_node_base', ci), ('agg_out', vp), ('ld_agg_out', ci), ('b_ksplit', ci)]
 
 
 class SardWGrad(C.Structure):
@@ -126,6 +128,7 @@ _PROTOS = {
     'sard_set_gemm_engine': (ci, [ci]),
     'sard_get_gemm_engine': (ci, []),
     'sard_linear_fwd': (ci, [P(SardGemm), vp]),
+    'sard_gemm_agg_supported': (ci, [ci, ci]),
     'sard_linear_bwd_data': (ci, [P(SardGemm), vp]),
     'sard_linear_bwd_weight': (ci, [P(SardWGrad), vp]),
     'sard_wgrad_chunk_rows': (ci, [ci, ci, ci]),

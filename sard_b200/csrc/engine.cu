@@ -14,6 +14,7 @@
 #include <unordered_map>
 
 int g_sard_wgrad_overlap = 1;
+static const int g_sard_fuse_agg = getenv("SARD_FUSE_AGG") ? atoi(getenv("SARD_FUSE_AGG")) : 1;   // GraphConv neighbour sum inside the GEMM loader
 extern "C" int sard_set_wgrad_overlap(int enabled) { g_sard_wgrad_overlap = enabled ? 1 : 0; return 0; }
 extern "C" int sard_get_wgrad_overlap(void) { return g_sard_wgrad_overlap; }
 
@@ -176,11 +177,19 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
   for (int l = 1; l <= tw.L; ++l) {
     const int hi = tw.h[l - 1], ho = tw.h[l];
     float* xin = t.xa[l - 1];
-    site(K_AGG, 0);
-    SARD_TRY(sard_csr_aggregate(xin + hi, 2 * hi, xin, 2 * hi, nullptr, 0, nullptr, 0, 0, n, hi, t.nd_graph, t.nd_arena,
-                                sel->cum, sel->node_base, arena->in_ptr, arena->in_nbr, st));
+    const bool fuse = g_sard_fuse_agg && sard_gemm_agg_supported(hi, ho);
     SardGemm g = gemm0();
-    g.A = xin; g.lda = 2 * hi; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
+    if (fuse) {
+      // the neighbour sum is taken in the GEMM's A-loader (and written to xin[:, 0:hi] for the weight gradient)
+      g.A = xin + hi; g.agg_cols = hi; g.agg_ptr = arena->in_ptr; g.agg_nbr = arena->in_nbr; g.agg_node = t.nd_arena;
+      g.agg_graph = t.nd_graph; g.agg_cum = sel->cum; g.agg_node_base = sel->node_base; g.agg_out = xin; g.ld_agg_out = 2 * hi;
+    } else {
+      site(K_AGG, 0);
+      SARD_TRY(sard_csr_aggregate(xin + hi, 2 * hi, xin, 2 * hi, nullptr, 0, nullptr, 0, 0, n, hi, t.nd_graph, t.nd_arena,
+                                  sel->cum, sel->node_base, arena->in_ptr, arena->in_nbr, st));
+      g.A = xin;
+    }
+    g.lda = 2 * hi; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
     g.bias = tw.has_bias ? P + tw.bl[l - 1] : nullptr;
     g.M = n; g.N = ho; g.R = 2 * hi; g.act = tw.act;
     if (l < tw.L) { g.Y = t.xa[l] + ho; g.ldy = 2 * ho; } else { g.Y = t.hout; g.ldy = ho; }
@@ -204,16 +213,27 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
     w.db = tw.has_bias ? G + tw.bl[l - 1] : nullptr; w.partials = wg_scratch;
     site(K_GCONV, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 0)));
-    SardGemm g = gemm0();
-    g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi; g.b_split = hi;
-    g.M = n; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
-    site(K_GCONV, 1);
-    SARD_TRY(sard_linear_bwd_data(&g, st));
-    // dz_{l-1} = (dxa[:, hi:2hi] + A^T dxa[:, 0:hi]) * act'(y_{l-1});  layer 0 (in_fc) has no activation
+    // dz_{l-1} = (dz_l W_r + A^T (dz_l W_l)) * act'(y_{l-1});  layer 0 (in_fc) has no activation
     const float* yprev = (l - 1 >= 1) ? xin + hi : nullptr;
-    site(K_AGG, 1);
-    SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[l - 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
-                                t.nd_graph, t.nd_arena, sel->cum, sel->node_base, arena->out_ptr, arena->out_nbr, st));
+    SardGemm g = gemm0();
+    g.A = dz; g.lda = ho; g.B0 = P + tw.wl[l - 1]; g.ldb0 = hi; g.B1 = P + tw.wr[l - 1]; g.ldb1 = hi;
+    g.M = n;
+    if (g_sard_fuse_agg && sard_gemm_agg_supported(hi, ho)) {
+      // one GEMM over the virtual operand [A^T dz_l | dz_l] (K = 2 ho) with the weights stacked [W_l ; W_r]
+      g.agg_cols = ho; g.agg_ptr = arena->out_ptr; g.agg_nbr = arena->out_nbr; g.agg_node = t.nd_arena; g.agg_graph = t.nd_graph;
+      g.agg_cum = sel->cum; g.agg_node_base = sel->node_base; g.b_ksplit = ho; g.b_split = hi;
+      g.N = hi; g.R = 2 * ho; g.Y = t.dz[l - 1]; g.ldy = hi; g.dsplit = hi;
+      if (yprev) { g.Dact = yprev; g.ldd = 2 * hi; g.dact0 = tw.act; g.dact1 = tw.act; }
+      site(K_GCONV, 1);
+      SARD_TRY(sard_linear_bwd_data(&g, st));
+    } else {
+      g.b_split = hi; g.N = 2 * hi; g.R = ho; g.Y = t.dxa; g.ldy = 2 * hi;
+      site(K_GCONV, 1);
+      SARD_TRY(sard_linear_bwd_data(&g, st));
+      site(K_AGG, 1);
+      SARD_TRY(sard_csr_aggregate(t.dxa, 2 * hi, t.dz[l - 1], hi, t.dxa + hi, 2 * hi, yprev, 2 * hi, tw.act, n, hi,
+                                  t.nd_graph, t.nd_arena, sel->cum, sel->node_base, arena->out_ptr, arena->out_nbr, st));
+    }
   }
   SardWGrad w = wgrad0();
   w.P = t.dz[0]; w.ldp = tw.h[0]; w.Q = t.x; w.ldq = t.ldx; w.M = n; w.N1 = tw.h[0]; w.N2 = tw.D;

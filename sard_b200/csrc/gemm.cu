@@ -184,6 +184,7 @@ static int launch_gemm(const SardGemm* g, sard_stream_t stream) {
   const double groups = g->b_group_stride ? 13.0 : 1.0;   // weight slabs touched (live indices, nominal)
   ProfScope prof(st, 2.0 * g->M * (double)g->N * g->R,
                  4.0 * ((double)g->M * g->R + (double)g->M * g->N + groups * (double)g->N * g->R));
+  if (g->agg_cols > 0) return sard_gemm_fast(g, NT, st);      // fused neighbour sum: one implementation
   if (g_sard_gemm_engine == 1 || g_sard_gemm_engine == 2) {
     const int r = sard_umma_gemm(g, NT, st);
     if (r >= 0) return r;

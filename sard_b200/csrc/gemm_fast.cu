@@ -5,9 +5,10 @@
 // ncu on the generic kernels showed them issue-bound with only 37-46 % of issued instructions being
 // FFMA; these variants are ~90 % FFMA in the main loop.  Anything unaligned falls back to gemm.cu.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------ forward / backward-data
-template <int BN, int TN, bool NT>
+template <int BN, int TN, bool NT, bool AGG>
 __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
   pdl_sync();
   constexpr int BM = 128, BK = 16, TM = 8;
@@ -34,11 +35,30 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
   const float* B1 = g.B1 ? g.B1 + (size_t)group * g.b_group_stride : nullptr;
 
   const float* a_ptr[A_LD];
+  // AGG: fused GraphConv neighbour sum (see SardGemm.agg_*): up to 4 neighbour rows per thread-row are kept
+  // as pointers, longer lists (rare) are walked from memory; the sum is taken in edge order like
+  // csr_aggregate_kernel, so the forward is bit-identical to the unfused path
+  const float* nb_ptr[AGG ? A_LD : 1][4];
+  int nb_e0[AGG ? A_LD : 1], nb_e1[AGG ? A_LD : 1], nb_gs[AGG ? A_LD : 1];
+  float* agg_dst[AGG ? A_LD : 1];
 #pragma unroll
   for (int i = 0; i < A_LD; ++i) {
     const int idx = tid + i * 256;
     const int grow = min(row_start + (idx >> 2), row_end - 1);         // clamp: extra rows are never stored
-    a_ptr[i] = g.A + (size_t)(g.a_rows ? g.a_rows[grow] : grow) * g.lda + (idx & 3) * 4;
+    if (AGG) {
+      a_ptr[i] = g.A + (size_t)grow * g.lda + (idx & 3) * 4;
+      const int a = __ldg(g.agg_node + grow);
+      const int e0 = __ldg(g.agg_ptr + a), e1 = __ldg(g.agg_ptr + a + 1);
+      const int gs = __ldg(g.agg_cum + __ldg(g.agg_graph + grow)) - g.agg_node_base;
+      nb_e0[i] = e0 + 4; nb_e1[i] = e1; nb_gs[i] = gs;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        nb_ptr[i][q] = e0 + q < e1 ? g.A + (size_t)(gs + __ldg(g.agg_nbr + e0 + q)) * g.lda + (idx & 3) * 4 : nullptr;
+      agg_dst[i] = (g.agg_out && blockIdx.y == 0 && row_start + (idx >> 2) < row_end)
+                       ? g.agg_out + (size_t)grow * g.ld_agg_out + (idx & 3) * 4 : nullptr;
+    } else {
+      a_ptr[i] = g.A + (size_t)(g.a_rows ? g.a_rows[grow] : grow) * g.lda + (idx & 3) * 4;
+    }
   }
   const int ty = tid >> 4, tx = tid & 15;
   float acc[TM][TN];
@@ -54,8 +74,30 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
   for (int kb = 0; kb <= nkb; ++kb) {
     if (kb < nkb) {
       const int k0 = kb * BK;
+      if (AGG && k0 < g.agg_cols) {
 #pragma unroll
-      for (int i = 0; i < A_LD; ++i) ra[i] = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + k0));
+        for (int i = 0; i < A_LD; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (nb_ptr[i][q]) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(nb_ptr[i][q] + k0));
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+          }
+          for (int e = nb_e0[i]; e < nb_e1[i]; ++e) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(
+                g.A + (size_t)(nb_gs[i] + __ldg(g.agg_nbr + e)) * g.lda + ((tid + i * 256) & 3) * 4 + k0));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          if (agg_dst[i]) *reinterpret_cast<float4*>(agg_dst[i] + k0) = v;
+          ra[i] = v;
+        }
+      } else {
+        const int ka = AGG ? k0 - g.agg_cols : k0;
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) ra[i] = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + ka));
+      }
 #pragma unroll
       for (int i = 0; i < B_LD; ++i) {
         const int idx = tid + i * 256;
@@ -65,8 +107,12 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
                                  : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(n0 + n) * g.ldb1 + (kk - g.b_split)));
         } else {             // W[k][c]: 4 consecutive output columns of reduction row k
           const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
-          rb[i] = n0 < g.b_split ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(k0 + r) * g.ldb0 + n0 + c))
-                                 : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(k0 + r) * g.ldb1 + (n0 - g.b_split) + c));
+          if (AGG && g.b_ksplit > 0)       // weights split on the reduction index: [W_l ; W_r]
+            rb[i] = k0 + r < g.b_ksplit ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(k0 + r) * g.ldb0 + n0 + c))
+                                        : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(k0 + r - g.b_ksplit) * g.ldb1 + n0 + c));
+          else
+            rb[i] = n0 < g.b_split ? __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(k0 + r) * g.ldb0 + n0 + c))
+                                   : __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(k0 + r) * g.ldb1 + (n0 - g.b_split) + c));
         }
       }
     }
@@ -139,27 +185,50 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
   }
 }
 
+// Tile-shape knobs.  Defaults are the LOW-REGISTER shapes: with six streams sharing the SMs the register file
+// decides how many CTAs are resident, and resident warps are what hides the latency these kernels are bound by
+// (measured on the bench workload: 128-wide GEMM tiles 220.7 ms, 64-wide 209.2 ms per update).
+static const int g_wide = getenv("SARD_GEMM_WIDE") ? atoi(getenv("SARD_GEMM_WIDE")) : 0;
+static const int g_wg_wide = getenv("SARD_WG_WIDE") ? atoi(getenv("SARD_WG_WIDE")) : 0;
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int TN, bool NT>
+template <int BN, int TN, bool NT, bool AGG = false>
 static int launch_fast(const SardGemm* g, cudaStream_t st) {
   constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
   constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
   static bool configured = false;
   if (!configured) {
-    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
   dim3 grid(tiles, g->N / BN);
-  sard_launch(gemm_fast_kernel<BN, TN, NT>, grid, 256, smem, st, *g);
+  sard_launch(gemm_fast_kernel<BN, TN, NT, AGG>, grid, 256, smem, st, *g);
   SARD_LAUNCH_OK(NT ? "gemm_fast_kernel<fwd>" : "gemm_fast_kernel<bwd_data>");
   return 0;
 }
 
 // -1: the shape / alignment is not covered, use the generic kernel
+extern "C" int sard_gemm_agg_supported(int h_in, int h_out) { return h_in > 0 && h_out > 0 && h_in % 64 == 0 && h_out % 64 == 0; }
+
+// fused neighbour-sum GEMM (SardGemm.agg_cols > 0): only this kernel family implements it
+static int sard_gemm_fast_agg(const SardGemm* g, bool nt, cudaStream_t st) {
+  SARD_REQUIRE(!g->a_rows && !g->tiles && g->agg_ptr && g->agg_nbr && g->agg_node && g->agg_graph && g->agg_cum, "fused aggregate: lists");
+  SARD_REQUIRE(g->R % 16 == 0 && g->agg_cols % 16 == 0 && g->agg_cols < g->R && g->N % 64 == 0, "fused aggregate: shape");
+  SARD_REQUIRE(g->lda % 4 == 0 && al16(g->A) && g->ldb0 % 4 == 0 && al16(g->B0) && g->B1 && g->ldb1 % 4 == 0 && al16(g->B1),
+               "fused aggregate: alignment");
+  SARD_REQUIRE(!g->agg_out || (g->ld_agg_out % 4 == 0 && al16(g->agg_out)), "fused aggregate: agg_out alignment");
+  if (nt) {
+    SARD_REQUIRE(g->b_split % 16 == 0, "fused aggregate: b_split");
+    return launch_fast<64, 4, true, true>(g, st);
+  }
+  SARD_REQUIRE(g->b_ksplit > 0 && g->b_ksplit % 16 == 0, "fused aggregate: b_ksplit");
+  return launch_fast<64, 4, false, true>(g, st);
+}
+
 int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
+  if (g->agg_cols > 0) return sard_gemm_fast_agg(g, nt, st);
   if (g->R < 16 || g->R % 16 || g->N % 64 || g->lda % 4 || !al16(g->A) || g->ldb0 % 4 || !al16(g->B0)) return -1;
   if (g->b_group_stride % 4) return -1;
   const bool split = g->B1 != nullptr;
@@ -167,7 +236,7 @@ int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
   if (nt) {
     if (split && g->b_split % 16) return -1;
     if (!split && g->b_split < g->R) return -1;
-    if (g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, true>(g, st);
+    if (g_wide && g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, true>(g, st);
     return launch_fast<64, 4, true>(g, st);
   }
   if (split) {
@@ -175,15 +244,15 @@ int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
     return launch_fast<64, 4, false>(g, st);               // every 64-column block lies in one weight matrix
   }
   if (g->b_split < g->N) return -1;
-  if (g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, false>(g, st);
+  if (g_wide && g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, false>(g, st);
   return launch_fast<64, 4, false>(g, st);
 }
 
 // ------------------------------------------------------------------------------------------ weight gradient
-template <int BN1>
-__global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) {
+template <int BN1, int T2>
+__global__ void __launch_bounds__(BN1 / 8 * (128 / T2)) wgrad_fast_kernel(const SardWGrad w) {
   pdl_sync();
-  constexpr int BN2 = 128, BKM = 16, NTH = BN1 * 2;         // 8x8 register tile: (BN1/8) x 16 threads
+  constexpr int BN2 = 128, BKM = 16, C2 = BN2 / T2, NTH = BN1 / 8 * C2;   // 8 x T2 register tile: (BN1/8) x (128/T2) threads
   constexpr int PS = BKM * (BN1 + 4), QS = BKM * (BN2 + 4);
   constexpr int P_LD = BKM * BN1 / 4 / NTH, Q_LD = BKM * BN2 / 4 / NTH;
   __shared__ __align__(16) float Ps[2 * PS];
@@ -200,12 +269,12 @@ __global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) 
   }
   const int c10 = blockIdx.y * BN1, c20 = blockIdx.z * BN2;
   const int tid = threadIdx.x;
-  const int t1 = tid >> 4, t2 = tid & 15;
-  float acc[8][8];
+  const int t1 = tid / C2, t2 = tid % C2;
+  float acc[8][T2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < T2; ++j) acc[i][j] = 0.f;
   float bsum = 0.f;
   const bool do_bias = blockIdx.z == 0 && tid < BN1;
 
@@ -236,21 +305,21 @@ __global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) 
       const float* Qc = Qs + (buf ^ 1) * QS;
 #pragma unroll
       for (int k = 0; k < BKM; ++k) {
-        float p[8], q[8];
+        float p[8], q[T2];
 #pragma unroll
         for (int i = 0; i < 8; i += 4) {
           const float4 v = *reinterpret_cast<const float4*>(Pc + k * (BN1 + 4) + t1 * 8 + i);
           p[i] = v.x; p[i + 1] = v.y; p[i + 2] = v.z; p[i + 3] = v.w;
         }
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(Qc + k * (BN2 + 4) + t2 * 8 + j);
+        for (int j = 0; j < T2; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Qc + k * (BN2 + 4) + t2 * T2 + j);
           q[j] = v.x; q[j + 1] = v.y; q[j + 2] = v.z; q[j + 3] = v.w;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p[i], q[j], acc[i][j]);
+          for (int j = 0; j < T2; ++j) acc[i][j] = fmaf(p[i], q[j], acc[i][j]);
       }
       if (do_bias) {
 #pragma unroll
@@ -276,9 +345,10 @@ __global__ void __launch_bounds__(BN1 * 2) wgrad_fast_kernel(const SardWGrad w) 
   float* part = w.partials + (size_t)blockIdx.x * w.N1 * ldpart;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * 8;      // 16-byte aligned: ldpart % 4 == 0
-    *reinterpret_cast<float4*>(pp) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * T2;     // 16-byte aligned: ldpart % 4 == 0
+#pragma unroll
+    for (int j = 0; j < T2; j += 4)
+      *reinterpret_cast<float4*>(pp + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
   }
   if (do_bias) part[(size_t)(c10 + tid) * ldpart + w.N2] = bsum;
 }
@@ -288,12 +358,15 @@ int sard_wgrad_skinny(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st) {
   if (w->N1 <= 8) return sard_wgrad_skinny(w, nchunks, st);        // gemm_skinny.cu
   if (w->N1 % 64 || w->N2 % 128 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
-  if (w->N1 % 128 == 0) {
+  if (g_wg_wide == 2 && w->N1 % 128 == 0) {             // 128 x 128 tile, 8 x 8 per thread, 130 registers
     dim3 grid(nchunks, w->N1 / 128, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<128>, grid, 256, 0, st, *w);
-  } else {
+    sard_launch(wgrad_fast_kernel<128, 8>, grid, 256, 0, st, *w);
+  } else if (g_wg_wide == 1) {                          // 64 x 128 tile, 8 x 8 per thread, 128 threads, 163 registers
     dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<64>, grid, 128, 0, st, *w);
+    sard_launch(wgrad_fast_kernel<64, 8>, grid, 128, 0, st, *w);
+  } else {                                              // 64 x 128 tile, 8 x 4 per thread, 256 threads (default: most warps per SM)
+    dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
+    sard_launch(wgrad_fast_kernel<64, 4>, grid, 256, 0, st, *w);
   }
   SARD_LAUNCH_OK("wgrad_fast_kernel");
   return 0;
