@@ -221,6 +221,10 @@ typedef struct {
    * Needs R, agg_cols multiples of 16, N a multiple of 64, a_rows == NULL (sard_gemm_agg_supported). */
   int agg_cols; const int* agg_ptr; const int* agg_nbr; const int* agg_node; const int* agg_graph; const int* agg_cum;
   int agg_node_base; float* agg_out; int ld_agg_out; int b_ksplit;
+  /* Optional split-K scratch (ungrouped, unfused launches with few rows and a long reduction, i.e. the critic
+   * MLP): when given, the reduction may be cut into S <= 8 slices whose raw partial tiles [S, M, N] go here and
+   * are summed in slice order by a finishing kernel that applies the epilogue.  splitk_floats = capacity. */
+  float* splitk_ws; long long splitk_floats;
 } SardGemm;
 
 /* Engine behind sard_linear_fwd / sard_linear_bwd_data: 0 = fp32 FFMA SIMT tiles, 1 = tcgen05 tensor cores

@@ -44,7 +44,8 @@ class SardGemm(C.Structure):
                 ('act', ci), ('post', ci), ('dact0', ci), ('dact1', ci), ('dsplit', ci),
                 ('M', ci), ('N', ci), ('R', ci), ('tiles', vp), ('num_tiles', vp), ('max_tiles', ci),
                 ('agg_cols', ci), ('agg_ptr', vp), ('agg_nbr', vp), ('agg_node', vp), ('agg_graph', vp), ('agg_cum', vp),
-                ('agg_node_base', ci), ('agg_out', vp), ('ld_agg_out', ci), ('b_ksplit', ci)]
+                ('agg_node_base', ci), ('agg_out', vp), ('ld_agg_out', ci), ('b_ksplit', ci),
+                ('splitk_ws', vp), ('splitk_floats', cll)]
 
 
 class SardWGrad(C.Structure):

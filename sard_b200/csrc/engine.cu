@@ -330,7 +330,7 @@ struct ValueBufs {
   TowerBufs t;
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
-  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2;
+  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* sk; long long sk_floats;
 };
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
@@ -346,6 +346,8 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
     maxm = net.mlp[j].out > maxm ? net.mlp[j].out : maxm;
   }
   vb.v = b.f(B); vb.dv = b.f(B); vb.sq = b.f(B);
+  vb.sk_floats = 1024LL * B;                                 // split-K partial tiles of the MLP GEMMs: S*N <= 1024 columns
+  vb.sk = b.f(vb.sk_floats);
   if (train) {
     vb.dcat = b.f((long long)B * vb.ldcat);
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
@@ -413,6 +415,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     g.B0 = P + net->mlp[j].w; g.ldb0 = net->mlp[j].in; g.b_split = net->mlp[j].in; g.bias = P + net->mlp[j].b;
     g.M = B; g.N = net->mlp[j].out; g.R = net->mlp[j].in; g.act = net->mlp[j].act;
     g.Y = vb.m[j]; g.ldy = (j < net->n_mlp - 1) ? net->mlp[j].out : vb.ldcat;
+    g.splitk_ws = vb.sk; g.splitk_floats = vb.sk_floats;
     site(K_MLP, 0);
     SARD_TRY(sard_linear_fwd(&g, st));
   }
@@ -469,6 +472,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
       g.Y = vb.dm[j]; g.ldy = net->mlp[j - 1].out;
       g.Dact = vb.m[j - 1]; g.ldd = net->mlp[j - 1].out; g.dact0 = net->mlp[j - 1].act; g.dact1 = g.dact0;
     }
+    g.splitk_ws = vb.sk; g.splitk_floats = vb.sk_floats;
     site(K_MLP, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
     if (j > 0) { dzj = vb.dm[j]; ldz = net->mlp[j - 1].out; }

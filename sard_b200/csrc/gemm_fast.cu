@@ -8,8 +8,8 @@
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------ forward / backward-data
-template <int BN, int TN, bool NT, bool AGG>
-__global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
+template <int BN, int TN, bool NT, bool AGG, int MINB, bool SPLITK>
+__global__ void __launch_bounds__(256, MINB) gemm_fast_kernel(const SardGemm g) {
   pdl_sync();
   constexpr int BM = 128, BK = 16, TM = 8;
   constexpr int AS = BK * (BM + 4), BS = BK * (BN + 4);
@@ -68,10 +68,15 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   float4 ra[A_LD], rb[B_LD];
-  const int nkb = g.R / BK;
+  // SPLITK: the gridDim.z CTAs of an output tile each walk a slice of the k-blocks and store raw partial tiles to
+  // g.splitk_ws; splitk_finish_kernel adds them in slice order and applies the epilogue.  For the critic MLP, whose
+  // 2048-row operands give only 16-128 CTAs with 16-32 k-blocks each (65-150 us latency chains on idle SMs).
+  const int nkb_all = g.R / BK;
+  const int kb_first = SPLITK ? nkb_all * (int)blockIdx.z / (int)gridDim.z : 0;
+  const int nkb = SPLITK ? nkb_all * ((int)blockIdx.z + 1) / (int)gridDim.z : nkb_all;
   int buf = 0;
 #pragma unroll 1
-  for (int kb = 0; kb <= nkb; ++kb) {
+  for (int kb = kb_first; kb <= nkb; ++kb) {
     if (kb < nkb) {
       const int k0 = kb * BK;
       if (AGG && k0 < g.agg_cols) {
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
         }
       }
     }
-    if (kb > 0) {
+    if (kb > kb_first) {
       const float* Ac = As + (buf ^ 1) * AS + ty * TM;
       const float* Bc = Bs + (buf ^ 1) * BS + tx * TN;
 #pragma unroll
@@ -160,6 +165,20 @@ __global__ void __launch_bounds__(256) gemm_fast_kernel(const SardGemm g) {
     buf ^= 1;
   }
 
+  if (SPLITK) {
+    float* ws = g.splitk_ws + (size_t)blockIdx.z * g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int grow = row_start + ty * TM + i;
+      if (grow < row_end) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4)
+          *reinterpret_cast<float4*>(ws + (size_t)grow * g.N + n0 + tx * TN + j) =
+              make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      }
+    }
+    return;
+  }
   float* Cs = smem;                                          // [BM][BN+1]; the operand tiles are dead
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -192,21 +211,91 @@ static const int g_wide = getenv("SARD_GEMM_WIDE") ? atoi(getenv("SARD_GEMM_WIDE
 static const int g_wg_wide = getenv("SARD_WG_WIDE") ? atoi(getenv("SARD_WG_WIDE")) : 0;
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int TN, bool NT, bool AGG = false>
-static int launch_fast(const SardGemm* g, cudaStream_t st) {
+template <int BN, int TN, bool NT, bool AGG, int MINB>
+static int launch_fast_mb(const SardGemm* g, cudaStream_t st) {
   constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
   constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
   static bool configured = false;
   if (!configured) {
-    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT, AGG, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
   dim3 grid(tiles, g->N / BN);
-  sard_launch(gemm_fast_kernel<BN, TN, NT, AGG>, grid, 256, smem, st, *g);
+  sard_launch(gemm_fast_kernel<BN, TN, NT, AGG, MINB, false>, grid, 256, smem, st, *g);
   SARD_LAUNCH_OK(NT ? "gemm_fast_kernel<fwd>" : "gemm_fast_kernel<bwd_data>");
   return 0;
+}
+
+template <bool NT>
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const SardGemm g, int S) {
+  pdl_sync();
+  const int N4 = g.N >> 2;
+  const long long total = (long long)g.M * N4;
+  const size_t slice = (size_t)g.M * g.N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N4), c = (int)(idx - (long long)m * N4) * 4;
+    const float* p = g.splitk_ws + (size_t)m * g.N + c;
+    float4 v = *reinterpret_cast<const float4*>(p);
+    for (int z = 1; z < S; ++z) {
+      const float4 t = *reinterpret_cast<const float4*>(p + z * slice);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const long long yrow = g.y_rows ? g.y_rows[m] : m;
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gc = c + i;
+      float x = o[i];
+      if (NT) {
+        if (g.bias) x += __ldg(g.bias + gc);
+        x = epi_forward(x, g.act, g.post, g.Ypre ? g.Ypre + yrow * g.ldy + gc : nullptr);
+      } else if (g.Dact) {
+        x *= act_grad_from_output(g.Dact[yrow * g.ldd + gc], gc < g.dsplit ? g.dact0 : g.dact1);
+      }
+      g.Y[yrow * g.ldy + gc] = x;
+    }
+  }
+}
+
+// split-K launch (ungrouped, no fused aggregate); S slices
+template <bool NT>
+static int launch_splitk(const SardGemm* g, int S, cudaStream_t st) {
+  constexpr int BN = 64;
+  constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
+  constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
+  static bool configured = false;
+  if (!configured) {
+    SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, 4, NT, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(g->M, 128), g->N / BN, S);
+  sard_launch(gemm_fast_kernel<BN, 4, NT, false, 3, true>, grid, 256, smem, st, *g);
+  SARD_LAUNCH_OK("gemm_fast_kernel<splitk>");
+  sard_launch(splitk_finish_kernel<NT>, grid_for((long long)g->M * (g->N / 4), 256), 256, 0, st, *g, S);
+  SARD_LAUNCH_OK("splitk_finish_kernel");
+  return 0;
+}
+static const int g_splitk = getenv("SARD_GEMM_SPLITK") ? atoi(getenv("SARD_GEMM_SPLITK")) : 1;
+// slices for a caller that provides a split-K workspace: largest power of two <= min(8, k-blocks / 4) keeping <= 296 CTAs
+static int splitk_slices(const SardGemm* g) {
+  if (!g_splitk || !g->splitk_ws || g->tiles || g->agg_cols > 0) return 1;
+  const long long ctas = (long long)ceil_div(g->M, 128) * (g->N / 64);
+  const int nkb = g->R / 16;
+  int S = 1;
+  while (S * 2 <= 8 && S * 2 <= nkb / 4 && ctas * S * 2 <= 296 && (long long)S * 2 * g->M * g->N <= g->splitk_floats) S *= 2;
+  return S;
+}
+static const int g_wg_minb = getenv("SARD_WG_MINB") ? atoi(getenv("SARD_WG_MINB")) : 2;
+static const int g_minb = getenv("SARD_GEMM_MINB") ? atoi(getenv("SARD_GEMM_MINB")) : 0;
+template <int BN, int TN, bool NT, bool AGG = false>
+static int launch_fast(const SardGemm* g, cudaStream_t st) {
+  // minimum resident CTAs per SM (caps registers): 64-wide tiles 3 (80 registers), fused-aggregate 2, 128-wide 1
+  constexpr int DEF = BN == 64 ? (AGG ? 2 : 3) : 1;
+  if (BN == 64 && g_minb == 4) return launch_fast_mb<BN, TN, NT, AGG, (BN == 64 ? 4 : 1)>(g, st);
+  if (BN == 64 && AGG && g_minb == 3) return launch_fast_mb<BN, TN, NT, AGG, (BN == 64 ? 3 : 1)>(g, st);
+  return launch_fast_mb<BN, TN, NT, AGG, DEF>(g, st);
 }
 
 // -1: the shape / alignment is not covered, use the generic kernel
@@ -236,6 +325,7 @@ int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
   if (nt) {
     if (split && g->b_split % 16) return -1;
     if (!split && g->b_split < g->R) return -1;
+    { const int S = splitk_slices(g); if (S > 1) return launch_splitk<true>(g, S, st); }
     if (g_wide && g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, true>(g, st);
     return launch_fast<64, 4, true>(g, st);
   }
@@ -244,13 +334,14 @@ int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
     return launch_fast<64, 4, false>(g, st);               // every 64-column block lies in one weight matrix
   }
   if (g->b_split < g->N) return -1;
+  { const int S = splitk_slices(g); if (S > 1) return launch_splitk<false>(g, S, st); }
   if (g_wide && g->N % 128 == 0 && (long long)ceil_div(g->M, 128) * (g->N / 128) >= 120) return launch_fast<128, 8, false>(g, st);
   return launch_fast<64, 4, false>(g, st);
 }
 
 // ------------------------------------------------------------------------------------------ weight gradient
-template <int BN1, int T2>
-__global__ void __launch_bounds__(BN1 / 8 * (128 / T2)) wgrad_fast_kernel(const SardWGrad w) {
+template <int BN1, int T2, int MINB>
+__global__ void __launch_bounds__(BN1 / 8 * (128 / T2), MINB) wgrad_fast_kernel(const SardWGrad w) {
   pdl_sync();
   constexpr int BN2 = 128, BKM = 16, C2 = BN2 / T2, NTH = BN1 / 8 * C2;   // 8 x T2 register tile: (BN1/8) x (128/T2) threads
   constexpr int PS = BKM * (BN1 + 4), QS = BKM * (BN2 + 4);
@@ -360,13 +451,14 @@ int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st) {
   if (w->N1 % 64 || w->N2 % 128 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
   if (g_wg_wide == 2 && w->N1 % 128 == 0) {             // 128 x 128 tile, 8 x 8 per thread, 130 registers
     dim3 grid(nchunks, w->N1 / 128, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<128, 8>, grid, 256, 0, st, *w);
+    sard_launch(wgrad_fast_kernel<128, 8, 1>, grid, 256, 0, st, *w);
   } else if (g_wg_wide == 1) {                          // 64 x 128 tile, 8 x 8 per thread, 128 threads, 163 registers
     dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<64, 8>, grid, 128, 0, st, *w);
+    sard_launch(wgrad_fast_kernel<64, 8, 1>, grid, 128, 0, st, *w);
   } else {                                              // 64 x 128 tile, 8 x 4 per thread, 256 threads (default: most warps per SM)
     dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<64, 4>, grid, 256, 0, st, *w);
+    if (g_wg_minb == 3) sard_launch(wgrad_fast_kernel<64, 4, 3>, grid, 256, 0, st, *w);
+    else sard_launch(wgrad_fast_kernel<64, 4, 2>, grid, 256, 0, st, *w);
   }
   SARD_LAUNCH_OK("wgrad_fast_kernel");
   return 0;
