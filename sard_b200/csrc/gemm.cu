@@ -399,13 +399,13 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
 // Rows per chunk for an ungrouped weight gradient: enough chunks to put ~2 CTAs on every SM, at least
 // 16 rows each (the partial products are reduced in chunk order afterwards).
 extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
-  const bool fast = N1 % 64 == 0 && N2 % 128 == 0;          // wgrad_fast_kernel tiles: (64|128) x 128
+  const bool fast = N1 % 64 == 0 && (N2 % 128 == 0 || (N2 >= 16 && N2 < 128));   // wgrad_fast_kernel tiles: 64 x 128 (masked below 128)
   if (N1 <= 8) {                                             // wgrad_skinny_kernel: rows are streamed once per 128 columns
     long long rows = ((long long)M * ceil_div(N2, 128) + 591) / 592;
     rows = (rows + 15) / 16 * 16;
     return (int)(rows < 32 ? 32 : (rows > 1024 ? 1024 : rows));
   }
-  const long long tiles = fast ? (long long)(N1 % 128 == 0 ? N1 / 128 : N1 / 64) * (N2 / 128)
+  const long long tiles = fast ? (long long)(N1 / 64) * ((N2 + 127) / 128)
                                : (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
   static const int waves = getenv("SARD_WG_WAVES") ? atoi(getenv("SARD_WG_WAVES")) : 2;   // tuning knob
   long long chunks = ((long long)waves * 148 + tiles - 1) / tiles;

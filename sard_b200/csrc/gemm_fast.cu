@@ -340,7 +340,9 @@ int sard_gemm_fast(const SardGemm* g, bool nt, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ weight gradient
-template <int BN1, int T2, int MINB>
+// MASK: N2 < 128 and not a multiple of 4 allowed (in_fc: N2 = obs width): loads beyond r4(N2) are skipped, columns
+// >= N2 are zeroed before they reach shared memory, and stores stop at N2 (column N2 of a partial row is the bias slot)
+template <int BN1, int T2, int MINB, bool MASK>
 __global__ void __launch_bounds__(BN1 / 8 * (128 / T2), MINB) wgrad_fast_kernel(const SardWGrad w) {
   pdl_sync();
   constexpr int BN2 = 128, BKM = 16, C2 = BN2 / T2, NTH = BN1 / 8 * C2;   // 8 x T2 register tile: (BN1/8) x (128/T2) threads
@@ -387,8 +389,13 @@ __global__ void __launch_bounds__(BN1 / 8 * (128 / T2), MINB) wgrad_fast_kernel(
       for (int i = 0; i < Q_LD; ++i) {
         const int idx = tid + i * NTH;
         const int row = m0 + idx / (BN2 / 4), c = (idx % (BN2 / 4)) * 4;
-        rq[i] = row < re ? __ldg(reinterpret_cast<const float4*>(w.Q + (size_t)(w.q_rows ? w.q_rows[row] : row) * w.ldq + c20 + c))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        rq[i] = (row < re && (!MASK || c20 + c < w.N2))
+                    ? __ldg(reinterpret_cast<const float4*>(w.Q + (size_t)(w.q_rows ? w.q_rows[row] : row) * w.ldq + c20 + c))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MASK) {
+          const int left = w.N2 - (c20 + c);               // valid components of this float4
+          if (left < 4) { if (left < 2) rq[i].y = 0.f; if (left < 3) rq[i].z = 0.f; rq[i].w = 0.f; }
+        }
       }
     }
     if (s > 0) {
@@ -438,8 +445,16 @@ __global__ void __launch_bounds__(BN1 / 8 * (128 / T2), MINB) wgrad_fast_kernel(
   for (int i = 0; i < 8; ++i) {
     float* pp = part + (size_t)(c10 + t1 * 8 + i) * ldpart + c20 + t2 * T2;     // 16-byte aligned: ldpart % 4 == 0
 #pragma unroll
-    for (int j = 0; j < T2; j += 4)
-      *reinterpret_cast<float4*>(pp + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+    for (int j = 0; j < T2; j += 4) {
+      const int left = MASK ? w.N2 - (c20 + t2 * T2 + j) : 4;
+      if (left >= 4) {
+        *reinterpret_cast<float4*>(pp + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      } else {
+        if (left > 0) pp[j] = acc[i][j];
+        if (left > 1) pp[j + 1] = acc[i][j + 1];
+        if (left > 2) pp[j + 2] = acc[i][j + 2];
+      }
+    }
   }
   if (do_bias) part[(size_t)(c10 + tid) * ldpart + w.N2] = bsum;
 }
@@ -448,17 +463,24 @@ __global__ void __launch_bounds__(BN1 / 8 * (128 / T2), MINB) wgrad_fast_kernel(
 int sard_wgrad_skinny(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st) {
   if (w->N1 <= 8) return sard_wgrad_skinny(w, nchunks, st);        // gemm_skinny.cu
-  if (w->N1 % 64 || w->N2 % 128 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
+  if (w->N1 % 64 || w->ldp % 4 || w->ldq % 4 || !al16(w->P) || !al16(w->Q)) return -1;
+  if (w->N2 < 128 && w->N2 >= 16 && w->ldq >= ((w->N2 + 3) & ~3)) {      // in_fc: one masked 128-column tile
+    dim3 grid(nchunks, w->N1 / 64, 1);
+    sard_launch(wgrad_fast_kernel<64, 4, 2, true>, grid, 256, 0, st, *w);
+    SARD_LAUNCH_OK("wgrad_fast_kernel<mask>");
+    return 0;
+  }
+  if (w->N2 % 128) return -1;
   if (g_wg_wide == 2 && w->N1 % 128 == 0) {             // 128 x 128 tile, 8 x 8 per thread, 130 registers
     dim3 grid(nchunks, w->N1 / 128, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<128, 8, 1>, grid, 256, 0, st, *w);
+    sard_launch(wgrad_fast_kernel<128, 8, 1, false>, grid, 256, 0, st, *w);
   } else if (g_wg_wide == 1) {                          // 64 x 128 tile, 8 x 8 per thread, 128 threads, 163 registers
     dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
-    sard_launch(wgrad_fast_kernel<64, 8, 1>, grid, 128, 0, st, *w);
+    sard_launch(wgrad_fast_kernel<64, 8, 1, false>, grid, 128, 0, st, *w);
   } else {                                              // 64 x 128 tile, 8 x 4 per thread, 256 threads (default: most warps per SM)
     dim3 grid(nchunks, w->N1 / 64, w->N2 / 128);
-    if (g_wg_minb == 3) sard_launch(wgrad_fast_kernel<64, 4, 3>, grid, 256, 0, st, *w);
-    else sard_launch(wgrad_fast_kernel<64, 4, 2>, grid, 256, 0, st, *w);
+    if (g_wg_minb == 3) sard_launch(wgrad_fast_kernel<64, 4, 3, false>, grid, 256, 0, st, *w);
+    else sard_launch(wgrad_fast_kernel<64, 4, 2, false>, grid, 256, 0, st, *w);
   }
   SARD_LAUNCH_OK("wgrad_fast_kernel");
   return 0;
