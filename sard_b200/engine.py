@@ -171,6 +171,23 @@ class ValueEngine(_EngineBase):
             comm.allreduce(self.GA)
         self.adam(B_global, log_row)
 
+    # -- software-pipelined single-GPU step: the gather + RunningNorm moments of minibatch k+1 (they read only the
+    #    arena) are issued on a gather stream into the other of two workspaces while minibatch k computes
+    def prefetch(self, arena: PackedRollout, run: Run, slot: int):
+        net = self.net
+        ws = self._workspace(('v', slot), lib.sard_value_workspace(C.byref(net), run.n, run.B))
+        ml, _ = self._moments(('v', slot), net.tower.D, 1)
+        check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, ptr(ml), None, 1,
+                                 self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+
+    def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int):
+        net = self.net
+        self.GA.zero_()
+        ws, ml = self.ws[('v', slot)], self.mom_local[('v', slot)]
+        check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, 1.0 / B_global, ptr(ml),
+                                 None, 1, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+        self.adam(B_global, log_row)
+
     def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None):
         opt = self.opt
         st = stream()
@@ -389,6 +406,33 @@ class PolicyEngine(_EngineBase):
             comm.allreduce(self.GA)
             world = comm.world
         self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row)
+
+    def prefetch(self, arena: PackedRollout, runs: List[Optional[Run]], slot: int):
+        net = self.net
+        for s in (2, 1, 0):
+            run = runs[s]
+            if run is None:
+                continue
+            if net.stage[s].tie_c1 > net.stage[s].tie_c0 and not arena.has_orbits:
+                raise _lib.SardError('orbit representatives missing: call PackedRollout.set_orbits first')
+            ws = self._workspace((s, slot), lib.sard_policy_workspace(C.byref(net), s, run.n, run.B))
+            ml, _ = self._moments((s, slot), net.stage[s].tower.D, 1)
+            check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, 0.0, ptr(ml),
+                                      None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), stream()))
+
+    def train_step_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
+                              active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
+                              log_row, slot: int):
+        net = self.net
+        self.GA.zero_()
+        for s in (2, 1, 0):
+            run = runs[s]
+            if run is None:
+                continue
+            ws, ml = self.ws[(s, slot)], self.mom_local[(s, slot)]
+            check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, clip_eps,
+                                      1.0 / B_global, ptr(ml), None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), stream()))
+        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row)
 
     def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None):
         opt = self.opt

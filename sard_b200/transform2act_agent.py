@@ -78,6 +78,8 @@ class Transform2ActAgent:
         self.enable_infer = cfg.enable_infer
         self.total_time_steps = 0
         self.last_update_stats = {}
+        self.prefetch_gather = os.environ.get('SARD_PREFETCH', '1') != '0'
+        self._gather_ctx = None
         self.overlap_nets = True          # critic and policy updates of a minibatch on two CUDA streams
         self._streams = None
         if checkpoint != 0:
@@ -307,6 +309,25 @@ class Transform2ActAgent:
                     with torch.cuda.stream(sp):
                         peng.dp_allreduce(comm)
                         peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step])
+                elif self.overlap_nets and self.prefetch_gather:
+                    # gather + RunningNorm moments of minibatch k+1 run on the gather streams (second workspace) while
+                    # minibatch k computes: they only read the arena, and they are 3 of the ~10 small kernels that
+                    # otherwise sit between two minibatches on each net's critical path
+                    slot = k & 1
+                    if k == 0:
+                        self._issue_prefetch(arena, plan, 0, 0, main)
+                    if k + 1 < plan.n_mb:
+                        self._issue_prefetch(arena, plan, k + 1, slot ^ 1, None)
+                    gv, gp, ready, free = self._gather_ctx
+                    with torch.cuda.stream(sv):
+                        sv.wait_event(ready[0][slot])
+                        veng.train_step_prefetched(arena, vrun, B_glob, vlog[step], slot)
+                        free[0][slot].record(sv)
+                    with torch.cuda.stream(sp):
+                        sp.wait_event(ready[1][slot])
+                        peng.train_step_prefetched(arena, pruns, B_glob, skel_nodes, active, self.clip_epsilon,
+                                                   40.0, self.clip_first_step_only, plog[step], slot)
+                        free[1][slot].record(sp)
                 elif self.overlap_nets:
                     with torch.cuda.stream(sv):
                         veng.train_step(arena, vrun, B_glob, vlog[step], comm)
@@ -329,6 +350,21 @@ class Transform2ActAgent:
                                   'host_enqueue_s': host_enqueue_s, 'steps': step, 'valid_steps': int(logs[:, 3].sum()) if step else 0,
                                   'value_loss': vlogs[:, 5].copy(), 'policy_log': logs}
         return self._summarise(arena, logs, cur_perm)
+
+    def _issue_prefetch(self, arena: PackedRollout, plan, k: int, slot: int, after):
+        """GATHER phase of minibatch k of `plan` for both nets on their gather streams, into workspace `slot`."""
+        if self._gather_ctx is None or self._gather_ctx[0].device != self.device:
+            ev = lambda: [[torch.cuda.Event() for _ in range(2)] for _ in range(2)]
+            self._gather_ctx = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), ev(), ev())
+        gv, gp, ready, free = self._gather_ctx
+        veng, peng = self.value_net.engine, self.policy_net.engine
+        for net, (g, eng, run) in enumerate(((gv, veng, plan.value_run(k)), (gp, peng, plan.policy_runs(k)))):
+            if after is not None:
+                g.wait_stream(after)                       # the epoch's ordering upload
+            g.wait_event(free[net][slot])                  # the previous user of this workspace has finished
+            with torch.cuda.stream(g):
+                eng.prefetch(arena, run, slot)
+                ready[net][slot].record(g)
 
     def _summarise(self, arena: PackedRollout, logs: np.ndarray, last_perm: np.ndarray) -> dict:
         """Epoch log with the reference's keys (agent :371-387)."""
