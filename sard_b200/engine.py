@@ -173,19 +173,26 @@ class ValueEngine(_EngineBase):
 
     # -- software-pipelined single-GPU step: the gather + RunningNorm moments of minibatch k+1 (they read only the
     #    arena) are issued on a gather stream into the other of two workspaces while minibatch k computes
-    def prefetch(self, arena: PackedRollout, run: Run, slot: int):
+    def prefetch(self, arena: PackedRollout, run: Run, slot: int, comm: Optional[Comm] = None):
+        """GATHER phase (+ the moments all-gather when data parallel) into workspace `slot`."""
         net = self.net
+        world = comm.world if comm is not None else 1
         ws = self._workspace(('v', slot), lib.sard_value_workspace(C.byref(net), run.n, run.B))
-        ml, _ = self._moments(('v', slot), net.tower.D, 1)
+        ml, ma = self._moments(('v', slot), net.tower.D, world)
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, ptr(ml), None, 1,
                                  self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+        if world > 1:
+            comm.allgather(ml, ma)
 
-    def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int):
+    def compute_prefetched(self, arena: PackedRollout, run: Run, B_global: int, slot: int, world: int = 1):
         net = self.net
         self.GA.zero_()
-        ws, ml = self.ws[('v', slot)], self.mom_local[('v', slot)]
+        ws, ml, ma = self.ws[('v', slot)], self.mom_local[('v', slot)], self.mom_all.get(('v', slot))
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, 1.0 / B_global, ptr(ml),
-                                 None, 1, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+                                 ptr(ma) if world > 1 else None, world, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+
+    def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int):
+        self.compute_prefetched(arena, run, B_global, slot)
         self.adam(B_global, log_row)
 
     def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None):
@@ -407,31 +414,47 @@ class PolicyEngine(_EngineBase):
             world = comm.world
         self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row)
 
-    def prefetch(self, arena: PackedRollout, runs: List[Optional[Run]], slot: int):
+    def prefetch(self, arena: PackedRollout, runs: List[Optional[Run]], slot: int, comm: Optional[Comm] = None,
+                 active_global: Optional[Sequence[bool]] = None):
+        """GATHER phase of every present stage (+ the moments all-gathers when data parallel) into workspace `slot`."""
         net = self.net
+        world = comm.world if comm is not None else 1
         for s in (2, 1, 0):
             run = runs[s]
             if run is None:
+                if world > 1 and active_global[s]:         # another rank has graphs of this stage: empty record
+                    ml, ma = self._moments((s, slot), net.stage[s].tower.D, world)
+                    ml.zero_()
+                    comm.allgather(ml, ma)
                 continue
             if net.stage[s].tie_c1 > net.stage[s].tie_c0 and not arena.has_orbits:
                 raise _lib.SardError('orbit representatives missing: call PackedRollout.set_orbits first')
             ws = self._workspace((s, slot), lib.sard_policy_workspace(C.byref(net), s, run.n, run.B))
-            ml, _ = self._moments((s, slot), net.stage[s].tower.D, 1)
+            ml, ma = self._moments((s, slot), net.stage[s].tower.D, world)
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, 0.0, ptr(ml),
                                       None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), stream()))
+            if world > 1:
+                comm.allgather(ml, ma)
 
-    def train_step_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
-                              active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
-                              log_row, slot: int):
+    def compute_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, clip_eps: float, slot: int,
+                           world: int = 1, active_global: Optional[Sequence[bool]] = None):
         net = self.net
         self.GA.zero_()
         for s in (2, 1, 0):
             run = runs[s]
             if run is None:
+                if world > 1 and active_global[s]:
+                    self._empty_norm_update(s, self.mom_all[(s, slot)], world)
                 continue
-            ws, ml = self.ws[(s, slot)], self.mom_local[(s, slot)]
+            ws, ml, ma = self.ws[(s, slot)], self.mom_local[(s, slot)], self.mom_all.get((s, slot))
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, clip_eps,
-                                      1.0 / B_global, ptr(ml), None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), stream()))
+                                      1.0 / B_global, ptr(ml), ptr(ma) if world > 1 else None, world, ptr(self.GA), None, None,
+                                      ptr(ws), ws.numel(), stream()))
+
+    def train_step_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
+                              active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
+                              log_row, slot: int):
+        self.compute_prefetched(arena, runs, B_global, clip_eps, slot)
         self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row)
 
     def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None):

@@ -288,7 +288,31 @@ class Transform2ActAgent:
                 active = [bool(counts[k, s] > 0) for s in range(3)]
                 vrun, pruns = plan.value_run(k), plan.policy_runs(k)
                 skel_nodes = int(counts[k, 3])
-                if world > 1 and self.overlap_nets:
+                if world > 1 and self.overlap_nets and self.prefetch_gather:
+                    # as below, and the moments all-gathers of minibatch k+1 leave the critical path with the gather;
+                    # every rank issues the same sequence of collectives (NCCL runs them in issue order)
+                    slot = k & 1
+                    act_of = lambda j: [bool(counts[j, s] > 0) for s in range(3)]
+                    if k == 0:
+                        self._issue_prefetch(arena, plan, 0, 0, main, comm, act_of(0))
+                    if k + 1 < plan.n_mb:
+                        self._issue_prefetch(arena, plan, k + 1, slot ^ 1, None, comm, act_of(k + 1))
+                    gv, gp, ready, free = self._gather_ctx
+                    with torch.cuda.stream(sv):
+                        sv.wait_event(ready[0][slot])
+                        veng.compute_prefetched(arena, vrun, B_glob, slot, world)
+                    with torch.cuda.stream(sp):
+                        sp.wait_event(ready[1][slot])
+                        peng.compute_prefetched(arena, pruns, B_glob, self.clip_epsilon, slot, world, active)
+                    with torch.cuda.stream(sv):
+                        veng.dp_allreduce(comm)
+                        veng.adam(B_glob, vlog[step])
+                        free[0][slot].record(sv)
+                    with torch.cuda.stream(sp):
+                        peng.dp_allreduce(comm)
+                        peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step])
+                        free[1][slot].record(sp)
+                elif world > 1 and self.overlap_nets:
                     # phases interleaved so both nets' collectives are issued back to back (NCCL runs them in
                     # issue order) while their compute overlaps on the two streams
                     with torch.cuda.stream(sv):
@@ -351,7 +375,7 @@ class Transform2ActAgent:
                                   'value_loss': vlogs[:, 5].copy(), 'policy_log': logs}
         return self._summarise(arena, logs, cur_perm)
 
-    def _issue_prefetch(self, arena: PackedRollout, plan, k: int, slot: int, after):
+    def _issue_prefetch(self, arena: PackedRollout, plan, k: int, slot: int, after, comm=None, active=None):
         """GATHER phase of minibatch k of `plan` for both nets on their gather streams, into workspace `slot`."""
         if self._gather_ctx is None or self._gather_ctx[0].device != self.device:
             ev = lambda: [[torch.cuda.Event() for _ in range(2)] for _ in range(2)]
@@ -363,7 +387,10 @@ class Transform2ActAgent:
                 g.wait_stream(after)                       # the epoch's ordering upload
             g.wait_event(free[net][slot])                  # the previous user of this workspace has finished
             with torch.cuda.stream(g):
-                eng.prefetch(arena, run, slot)
+                if net == 0:
+                    eng.prefetch(arena, run, slot, comm)
+                else:
+                    eng.prefetch(arena, run, slot, comm, active)
                 ready[net][slot].record(g)
 
     def _summarise(self, arena: PackedRollout, logs: np.ndarray, last_perm: np.ndarray) -> dict:
