@@ -346,6 +346,15 @@ int sard_adam_prepare(const float* stats, float inv_B, float inv_world, float in
 int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max_seg_len, float lr, float beta1, float beta2,
                     float eps, int active_mask, const float* ctl_f, const int* ctl_i, sard_stream_t stream);
 
+/* The whole optimiser tail in one call, for update loops that keep the gradient bucket resident: optional
+ * sum of squares of g_sq[n_sq] (NULL: no clipping; scratch float[1024]), sard_adam_prepare, sard_adam_apply, and
+ * the bucket is left ZEROED for the next step (stats[0..15] and every segment's gradients, also when the step
+ * is gated off), which replaces the memset before the next backward.  Same arithmetic as the three calls. */
+int sard_adam_update(float* stats, float inv_B, float inv_world, float inv_cat_nodes, const float* g_sq, long long n_sq,
+                     float* sq_scratch, float max_norm, int first_only, int use_gate, int active_mask, double beta1,
+                     double beta2, float* ctl_f, int* ctl_i, float* log_row, const SardAdamSeg* segs, int n_seg,
+                     long long max_seg_len, float lr, float eps, sard_stream_t stream);
+
 /* =====================================================================================
  * Network schedules: the whole forward/backward of one net over one run, launched from C++
  * (one host call per minibatch instead of ~100)

@@ -142,6 +142,7 @@ _PROTOS = {
     'sard_sqnorm': (ci, [vp, cll, vp, vp, vp]),
     'sard_adam_prepare': (ci, [vp, cf, cf, cf, vp, cf, ci, ci, ci, cd, cd, vp, vp, vp, vp]),
     'sard_adam_apply': (ci, [vp, ci, cll, cf, cf, cf, cf, ci, vp, vp, vp]),
+    'sard_adam_update': (ci, [vp, cf, cf, cf, vp, cll, vp, cf, ci, ci, ci, cd, cd, vp, vp, vp, vp, ci, cll, cf, cf, vp]),
     'sard_value_workspace': (cll, [P(SardValueNet), ci, ci]),
     'sard_policy_workspace': (cll, [P(SardPolicyNet), ci, ci, ci]),
     'sard_value_run': (ci, [P(SardValueNet), P(SardArena), P(SardSel), ci, ci, cf, vp, vp, ci, vp, vp, cll, vp]),

@@ -51,11 +51,30 @@ extern "C" int sard_sqnorm(const float* g, long long n, float* scratch, float* o
   return 0;
 }
 
-__global__ void adam_prepare_kernel(const float* stats, float inv_B, float inv_world, float inv_cat_nodes,
-                                    const float* sqnorm, float max_norm, int first_only, int use_gate,
+// sq_count > 1: `sqnorm` holds sq_count partial sums (sqnorm_partial_kernel), reduced here exactly like
+// sqnorm_final_kernel does (same per-thread strides and tree, fp64) -> one launch fewer on the optimiser tail.
+// zero_stats: the 16 statistics are cleared after use (with adam_apply's zero_grads this replaces the separate
+// fill of the gradient bucket before the next step).
+__global__ void adam_prepare_kernel(float* stats, float inv_B, float inv_world, float inv_cat_nodes,
+                                    const float* sqnorm, int sq_count, float max_norm, int first_only, int use_gate,
                                     int active_mask, double beta1, double beta2, float* ctl_f, int* ctl_i,
-                                    float* log_row) {
+                                    float* log_row, int zero_stats) {
   pdl_sync();
+  __shared__ double red[256];
+  float sq_total = 0.f;
+  if (sqnorm && sq_count > 1) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < sq_count; i += 256) s += (double)sqnorm[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    sq_total = (float)red[0];
+  } else if (sqnorm) {
+    sq_total = sqnorm[0];
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float surr_loss = 0.f, kl = 0.f, entropy = 0.f, extra = 0.f;
   if (stats) {
@@ -66,7 +85,7 @@ __global__ void adam_prepare_kernel(const float* stats, float inv_B, float inv_w
   }
   int valid = 1;
   if (use_gate && (kl > 0.1f || surr_loss > 10.f || !(kl == kl) || !(surr_loss == surr_loss))) valid = 0;
-  const float norm = sqnorm ? sqrtf(sqnorm[0]) : 0.f;
+  const float norm = sqnorm ? sqrtf(sq_total) : 0.f;
   float scale = 1.f;
   const int armed = ctl_i[1];
   if (max_norm > 0.f && sqnorm && armed) {
@@ -89,25 +108,31 @@ __global__ void adam_prepare_kernel(const float* stats, float inv_B, float inv_w
     log_row[0] = surr_loss; log_row[1] = entropy; log_row[2] = kl; log_row[3] = (float)valid;
     log_row[4] = norm; log_row[5] = extra;
   }
+  if (zero_stats && stats) {
+    for (int i = 0; i < 16; ++i) stats[i] = 0.f;
+  }
 }
 
 extern "C" int sard_adam_prepare(const float* stats, float inv_B, float inv_world, float inv_cat_nodes,
                                  const float* sqnorm, float max_norm, int first_only, int use_gate, int active_mask,
                                  double beta1, double beta2, float* ctl_f, int* ctl_i, float* log_row,
                                  sard_stream_t stream) {
-  sard_launch(adam_prepare_kernel, 1, 32, 0, as_stream(stream), stats, inv_B, inv_world, inv_cat_nodes, sqnorm, max_norm,
-                                                      first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i,
-                                                      log_row);
+  sard_launch(adam_prepare_kernel, 1, 256, 0, as_stream(stream), const_cast<float*>(stats), inv_B, inv_world, inv_cat_nodes, sqnorm, 1,
+              max_norm, first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i, log_row, 0);
   SARD_LAUNCH_OK("adam_prepare_kernel");
   return 0;
 }
 
 __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr, float beta1, float beta2, float eps,
-                                  int active_mask, const float* __restrict__ ctl_f, const int* __restrict__ ctl_i) {
+                                  int active_mask, const float* __restrict__ ctl_f, const int* __restrict__ ctl_i,
+                                  int zero_grads) {
   pdl_sync();
-  if (ctl_i[0] == 0) return;
   const SardAdamSeg s = segs[blockIdx.y];
-  if (!((active_mask >> s.group) & 1)) return;
+  if (ctl_i[0] == 0 || !((active_mask >> s.group) & 1)) {
+    if (zero_grads)
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) const_cast<float*>(s.g)[i] = 0.f;
+    return;
+  }
   const float scale = ctl_f[0];
   const float bc1 = ctl_f[8 + s.group], bc2s = ctl_f[16 + s.group];
   const float step_size = lr / bc1;
@@ -120,6 +145,7 @@ __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr
     s.p[i] = s.p[i] - step_size * (m / denom);
     s.m[i] = m;
     s.v[i] = v;
+    if (zero_grads) const_cast<float*>(s.g)[i] = 0.f;
   }
 }
 
@@ -130,7 +156,35 @@ extern "C" int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max
   int gx = (int)((max_seg_len + 255) / 256);
   if (gx > 256) gx = 256;
   dim3 grid(gx, n_seg);
-  sard_launch(adam_apply_kernel, grid, 256, 0, as_stream(stream), segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i);
+  sard_launch(adam_apply_kernel, grid, 256, 0, as_stream(stream), segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i, 0);
+  SARD_LAUNCH_OK("adam_apply_kernel");
+  return 0;
+}
+
+// Fused optimiser tail: [sum-of-squares partials ->] gate / clip / bias corrections -> Adam, and the gradient bucket
+// (statistics + every segment's gradients) is left zeroed for the next step.  g_sq == NULL: no clipping (critic).
+extern "C" int sard_adam_update(float* stats, float inv_B, float inv_world, float inv_cat_nodes, const float* g_sq,
+                                long long n_sq, float* sq_scratch, float max_norm, int first_only, int use_gate,
+                                int active_mask, double beta1, double beta2, float* ctl_f, int* ctl_i, float* log_row,
+                                const SardAdamSeg* segs, int n_seg, long long max_seg_len, float lr, float eps,
+                                sard_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  int nb = 0;
+  if (g_sq) {
+    nb = (int)((n_sq + 1023) / 1024);
+    if (nb > SQ_BLOCKS) nb = SQ_BLOCKS;
+    if (nb < 2) nb = 2;                              // >= 2 partials so that prepare takes the reduction branch
+    sard_launch(sqnorm_partial_kernel, nb, 256, 0, st, g_sq, n_sq, sq_scratch);
+    SARD_LAUNCH_OK("sqnorm_partial_kernel");
+  }
+  sard_launch(adam_prepare_kernel, 1, 256, 0, st, stats, inv_B, inv_world, inv_cat_nodes, g_sq ? sq_scratch : nullptr, nb,
+              max_norm, first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i, log_row, 1);
+  SARD_LAUNCH_OK("adam_prepare_kernel");
+  if (n_seg <= 0 || max_seg_len <= 0) return 0;
+  int gx = (int)((max_seg_len + 255) / 256);
+  if (gx > 256) gx = 256;
+  dim3 grid(gx, n_seg);
+  sard_launch(adam_apply_kernel, grid, 256, 0, st, segs, lr, (float)beta1, (float)beta2, eps, active_mask, ctl_f, ctl_i, 1);
   SARD_LAUNCH_OK("adam_apply_kernel");
   return 0;
 }

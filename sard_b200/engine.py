@@ -185,19 +185,25 @@ class ValueEngine(_EngineBase):
             comm.allgather(ml, ma)
 
     def compute_prefetched(self, arena: PackedRollout, run: Run, B_global: int, slot: int, world: int = 1):
+        """COMPUTE phase on a prefetched workspace.  The gradient bucket must be zero on entry: ``adam(fused=True)``
+        leaves it zeroed, the agent clears it once before the first step."""
         net = self.net
-        self.GA.zero_()
         ws, ml, ma = self.ws[('v', slot)], self.mom_local[('v', slot)], self.mom_all.get(('v', slot))
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, 1.0 / B_global, ptr(ml),
                                  ptr(ma) if world > 1 else None, world, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
 
     def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int):
         self.compute_prefetched(arena, run, B_global, slot)
-        self.adam(B_global, log_row)
+        self.adam(B_global, log_row, fused=True)
 
-    def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None):
+    def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None, fused: bool = False):
         opt = self.opt
         st = stream()
+        if fused:          # one call: gate + Adam, and the gradient bucket is left zeroed for the next step
+            check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0, 0.0, None, 0, None, -1.0, 0, 0, 1, opt.betas[0],
+                                       opt.betas[1], ptr(opt.ctl_f), ptr(opt.ctl_i), ptr(log_row), ptr(opt.segs), opt.n_seg,
+                                       opt.max_seg, opt.lr, opt.eps, st))
+            return
         check(lib.sard_adam_prepare(ptr(self.GA), 1.0 / B_global, 1.0, 0.0, None, -1.0, 0, 0, 1, opt.betas[0], opt.betas[1],
                                     ptr(opt.ctl_f), ptr(opt.ctl_i), ptr(log_row), st))
         check(lib.sard_adam_apply(ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.betas[0], opt.betas[1], opt.eps, 1,
@@ -438,8 +444,7 @@ class PolicyEngine(_EngineBase):
 
     def compute_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, clip_eps: float, slot: int,
                            world: int = 1, active_global: Optional[Sequence[bool]] = None):
-        net = self.net
-        self.GA.zero_()
+        net = self.net                  # gradient bucket zero on entry (see ValueEngine.compute_prefetched)
         for s in (2, 1, 0):
             run = runs[s]
             if run is None:
@@ -455,12 +460,20 @@ class PolicyEngine(_EngineBase):
                               active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
                               log_row, slot: int):
         self.compute_prefetched(arena, runs, B_global, clip_eps, slot)
-        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row)
+        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row, fused=True)
 
-    def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None):
+    def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None,
+             fused: bool = False):
         opt = self.opt
         mask = (1 if any(active_global) else 0) | sum((1 << (1 + s)) for s in range(3) if active_global[s])
         st = stream()
+        if fused:          # grad-norm partials + gate / clip + Adam in one call; leaves the gradient bucket zeroed
+            inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0
+            check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0 / world, inv_cat, self.GA.data_ptr() + 4 * N_STATS,
+                                       self.GA.numel() - N_STATS, ptr(self.sq_scratch), float(max_norm),
+                                       1 if clip_first_only else 0, 1, mask, opt.betas[0], opt.betas[1], ptr(opt.ctl_f),
+                                       ptr(opt.ctl_i), ptr(log_row), ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.eps, st))
+            return
         check(lib.sard_sqnorm(self.GA.data_ptr() + 4 * N_STATS, self.GA.numel() - N_STATS, ptr(self.sq_scratch),
                               ptr(self.sq_out), st))
         inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0

@@ -269,6 +269,8 @@ class Transform2ActAgent:
         if self._streams is None or self._streams[0].device != self.device:
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         sv, sp = self._streams
+        if self.overlap_nets and self.prefetch_gather:
+            veng.GA.zero_(); peng.GA.zero_()         # the fused optimiser tail keeps the buckets zeroed from here on
         sv.wait_stream(main); sp.wait_stream(main)
         for ep in range(self.opt_num_epochs):
             # like the reference, each epoch permutes the already permuted lists (agent :331-342)
@@ -306,11 +308,11 @@ class Transform2ActAgent:
                         peng.compute_prefetched(arena, pruns, B_glob, self.clip_epsilon, slot, world, active)
                     with torch.cuda.stream(sv):
                         veng.dp_allreduce(comm)
-                        veng.adam(B_glob, vlog[step])
+                        veng.adam(B_glob, vlog[step], fused=True)
                         free[0][slot].record(sv)
                     with torch.cuda.stream(sp):
                         peng.dp_allreduce(comm)
-                        peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step])
+                        peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step], fused=True)
                         free[1][slot].record(sp)
                 elif world > 1 and self.overlap_nets:
                     # phases interleaved so both nets' collectives are issued back to back (NCCL runs them in
