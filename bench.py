@@ -244,14 +244,7 @@ def run_native(args):
         # fresh synthetic rewards every step: re-using one batch would let the policy over-fit its
         # advantages and trip the KL gate (transform2act_agent.py:404-407), which real rollouts do not
         arena.rewards.normal_(0.01, 0.1, generator=gen)
-        for m in agent.update_modules:
-            m.train(False)
-        agent._eval_values(arena)
-        for m in agent.update_modules:
-            m.train(True)
-        a, r = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), agent.gamma, agent.tau)
-        arena.advantages.copy_(a.reshape(-1)); arena.returns.copy_(r.reshape(-1))
-        agent.update_policy_packed(arena)
+        agent.update_arena(arena)          # value pre-pass, GAE, fixed log-prob pre-pass, 240 minibatch updates
 
     arena = agent.pack(roll)
     agent._prepare(arena)

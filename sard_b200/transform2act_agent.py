@@ -214,18 +214,37 @@ class Transform2ActAgent:
         with torch.cuda.device(self.device):
             arena = self.pack(batch)
             self._prepare(arena)
-            for m in self.update_modules:
-                m.train(False)
-            self._eval_values(arena)
-            for m in self.update_modules:
-                m.train(True)
-            adv, ret = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), self.gamma, self.tau)
-            arena.advantages.copy_(adv.reshape(-1))
-            arena.returns.copy_(ret.reshape(-1))
-            if self.cfg.agent_specs.get('reinforce', False):
-                arena.advantages.copy_(arena.returns)
-            log = self.update_policy_packed(arena)
+            log = self.update_arena(arena)
         return time.time() - t0, log
+
+    def _net_streams(self):
+        if self._streams is None or self._streams[0].device != self.device:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._streams
+
+    def update_arena(self, arena: PackedRollout):
+        """``update_params`` after packing, on a resident arena: value pre-pass, GAE, fixed log-prob pre-pass (agent
+        :284-296, :316-327), then the minibatch loop.  The two pre-passes are independent (critic / policy, disjoint
+        outputs), so the policy's runs on the policy stream beside the critic's and the GAE."""
+        for m in self.update_modules:
+            m.train(False)
+        fixed_ready = False
+        if self.overlap_nets:
+            main = torch.cuda.current_stream(self.device)
+            sp = self._net_streams()[1]
+            sp.wait_stream(main)
+            with torch.cuda.stream(sp):
+                self._fixed_order = self._eval_log_probs(arena)      # keep the ordering tensors alive
+            fixed_ready = True
+        self._eval_values(arena)
+        for m in self.update_modules:
+            m.train(True)
+        adv, ret = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), self.gamma, self.tau)
+        arena.advantages.copy_(adv.reshape(-1))
+        arena.returns.copy_(ret.reshape(-1))
+        if self.cfg.agent_specs.get('reinforce', False):
+            arena.advantages.copy_(arena.returns)
+        return self.update_policy_packed(arena, fixed_ready=fixed_ready)
 
     def update_policy(self, states, actions, returns, advantages, exps):
         """Reference signature (agent :313): lists of states/actions plus ``[T,1]`` tensors."""
@@ -241,16 +260,17 @@ class Transform2ActAgent:
         np.random.shuffle(perm)          # same RNG call as the reference (agent :333)
         return perm
 
-    def update_policy_packed(self, arena: PackedRollout, perms: Optional[List[np.ndarray]] = None):
+    def update_policy_packed(self, arena: PackedRollout, perms: Optional[List[np.ndarray]] = None, fixed_ready: bool = False):
         comm = self.comm
         world = comm.world if comm is not None else 1
         peng, veng = self.policy_net.engine, self.value_net.engine
         t_host0 = time.perf_counter()
-        for m in self.update_modules:
-            m.train(False)
-        self._eval_log_probs(arena)
-        for m in self.update_modules:
-            m.train(True)
+        if not fixed_ready:                  # fixed_ready: update_arena already queued the pre-pass on the policy stream
+            for m in self.update_modules:
+                m.train(False)
+            self._eval_log_probs(arena)
+            for m in self.update_modules:
+                m.train(True)
         T = arena.T
         M = self.mini_batch_size if self.use_mini_batch else T
         batch_design = bool(self.cfg.agent_specs.get('batch_design', False))
@@ -266,9 +286,7 @@ class Transform2ActAgent:
         # workspaces and gradient buckets; the arena is read-only), and each one alone launches grids of
         # only ~150-300 CTAs on 148 SMs: run them on two streams so their kernels share the machine.
         main = torch.cuda.current_stream(self.device)
-        if self._streams is None or self._streams[0].device != self.device:
-            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-        sv, sp = self._streams
+        sv, sp = self._net_streams()
         if self.overlap_nets and self.prefetch_gather:
             veng.GA.zero_(); peng.GA.zero_()         # the fused optimiser tail keeps the buckets zeroed from here on
         sv.wait_stream(main); sp.wait_stream(main)

@@ -33,14 +33,7 @@ def main():
 
     def step():
         arena.rewards.normal_(0.01, 0.1, generator=gen)
-        for m in agent.update_modules:
-            m.train(False)
-        agent._eval_values(arena)
-        for m in agent.update_modules:
-            m.train(True)
-        a, r = estimate_advantages(arena.rewards, arena.masks, arena.values.unsqueeze(1), agent.gamma, agent.tau)
-        arena.advantages.copy_(a.reshape(-1)); arena.returns.copy_(r.reshape(-1))
-        agent.update_policy_packed(arena)
+        agent.update_arena(arena)
 
     only = os.environ.get('ONLY', '')
     if only:                      # run one net alone: how long is each stream's own chain?
