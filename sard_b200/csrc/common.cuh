@@ -39,7 +39,8 @@ struct ProfScope {
 // k+1 is processed while kernel k drains and its CTAs start the moment k's last CTA exits (the implicit
 // trigger).  Measured on the 50 k-transition update (two streams): 319 -> 296 ms.  An EARLY trigger
 // (griddepcontrol.launch_dependents at kernel entry) was measured too and is worse (376 ms): the parked
-// CTAs of k+1 hold shared memory and registers that the other stream's kernels need.
+// CTAs of k+1 hold shared memory and registers that the other stream's kernels need.  A LATE trigger (after the
+// GEMM kernels' main loop) was neutral to slightly worse (195.9 -> 197.3 ms).
 // Launched without the attribute (sard_set_pdl(0)) the wait is a no-op.
 extern int g_sard_pdl;
 __device__ __forceinline__ void pdl_sync() {
