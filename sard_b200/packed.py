@@ -180,10 +180,11 @@ class PackedRollout:
 
 class Run:
     """A contiguous range of an ordering: graphs ``[lo, hi)`` of ``ids`` with node prefix ``cum``."""
-    __slots__ = ('sel', 'B', 'n', 'lo', 'hi')
+    __slots__ = ('sel', 'B', 'n', 'lo', 'hi', '_keep')
 
     def __init__(self, ids_t: torch.Tensor, cum_t: torch.Tensor, cum_np: np.ndarray, lo: int, hi: int):
         self.lo, self.hi = lo, hi
+        self._keep = (ids_t, cum_t)          # the selection holds raw pointers into these tensors
         self.B = hi - lo
         self.n = int(cum_np[hi] - cum_np[lo])
         s = SardSel()

@@ -246,3 +246,93 @@ def test_update_is_deterministic(cuda_device):
         outs.append({k: v.detach().cpu().clone() for k, v in list(ag.policy_net.state_dict().items()) + list(ag.value_net.state_dict().items())})
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_full_width_nets_loss_and_gradients_match_oracle_autograd(cuda_device):
+    """derl.yml network sizes (GNN 64x3, JSMLP 128x2 over 256 body indices, critic MLP 512/256): this is the
+    configuration the aligned fast paths serve (fused neighbour-sum GEMMs, 64x128 weight-gradient tiles, masked in_fc
+    tile, skinny layers, fused encoders), which the 16-wide golden nets never reach.  Gradients of one stage-partitioned
+    minibatch against fp64 autograd of the oracle, policy (all three stages) and critic."""
+    from oracle import sard_oracle as O
+    from sard_b200 import synthetic
+    from sard_b200.config import derl_config
+    from sard_b200.packed import Ordering, PackedRollout, stage_partition
+    from sard_b200.transform2act_agent import Transform2ActAgent
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['manipulation_box']
+    T = 300
+    roll = synthetic.generate_rollout(shape, T, seed=31, min_exec=6, max_exec=20, dtype=np.float32)
+    for f in ('obs', 'hfield', 'obj', 'goal', 'actions', 'rewards', 'masks'):
+        setattr(roll, f, getattr(roll, f).astype(np.float64))
+    torch.manual_seed(3)
+    ag = Transform2ActAgent(derl_config(), torch.float32, 'cuda', 0, 1, env=synthetic.SyntheticEnv(shape))
+    with torch.no_grad():
+        for nm in ('skel', 'attr', 'control'):
+            lin = getattr(ag.policy_net, f'{nm}_ind_mlp').linear
+            lin.b.add_(0.05 * torch.randn_like(lin.b))
+    psd = {k: v.detach().cpu().double().clone() for k, v in ag.policy_net.state_dict().items()}
+    vsd = {k: v.detach().cpu().double().clone() for k, v in ag.value_net.state_dict().items()}
+    for sd in (psd, vsd):
+        for k, v in sd.items():
+            if v.is_floating_point() and not any(k.endswith(s) for s in ('.mean', '.var', '.std')):
+                v.requires_grad_(True)
+    spec = O.Spec(attr_fixed_dim=shape.attr_fixed_dim, index_base=shape.index_base,
+                  embeds=ag.policy_net.group.get_cur_subgroup_embeds().double(),
+                  orbits={int(k): [int(x) for x in v] for k, v in ag.policy_net.group.get_cur_orbits().items()})
+    batch = roll.to_traj_batch()
+    states = [[torch.tensor(x) if i in (0, 1, 5, 6, 7) else x for i, x in enumerate(s)] for s in batch.states]
+    actions = [torch.tensor(a) for a in batch.actions]
+    g = torch.Generator().manual_seed(1)
+    adv = torch.randn(T, 1, dtype=torch.float64, generator=g)
+    ret = torch.randn(T, 1, dtype=torch.float64, generator=g)
+    perm = O.stage_partition(states)
+    st_p = [states[i] for i in perm]; ac_p = [actions[i] for i in perm]
+    with torch.no_grad():
+        fixed = O.policy_log_prob(psd, spec, st_p, ac_p, training=False) + 0.05 * torch.randn(T, 1, dtype=torch.float64, generator=g)
+    lp = O.policy_log_prob(psd, spec, st_p, ac_p, training=True)
+    loss, kl, _ = O.ppo_loss(lp, fixed, adv[perm], 0.2)
+    loss.backward()
+    vloss = (O.value_forward(vsd, spec, states, training=True) - ret).pow(2).mean()
+    vloss.backward()
+
+    arena = PackedRollout(roll, 'cuda')
+    ag._prepare(arena)
+    arena.advantages.copy_(adv.reshape(-1).float()); arena.returns.copy_(ret.reshape(-1).float())
+    fl = torch.empty(T, dtype=torch.float64); fl[torch.from_numpy(perm)] = fixed.reshape(-1)
+    arena.fixed_log_probs.copy_(fl.float())
+    ag.policy_net.train(); ag.value_net.train()
+    peng, veng = ag.policy_net.engine, ag.value_net.engine
+    order = Ordering(arena, stage_partition(arena.stage_np))
+    runs = order.stage_runs(0, T)
+    assert all(r is not None for r in runs), 'the rollout must contain all three stages'
+    peng.GA.zero_()
+    for s in (2, 1, 0):
+        peng.run_stage(s, arena, runs[s], 1, 0.2, 1.0 / T)
+    GA = peng.GA.cpu().numpy().astype(np.float64)
+    assert_close(-GA[0] / T, float(loss), rtol=1e-4, atol=1e-6, what='surr loss')
+    assert_close(GA[1] / T, kl, rtol=1e-4, atol=1e-6, what='approx kl')
+    for name, p, off, grp in peng.store.entries:
+        want = psd[name].grad.numpy()
+        got = GA[16 + off:16 + off + p.numel()].reshape(want.shape)
+        assert_close(got, want, atol=1e-6 + 2e-5 * float(np.abs(want).max()), what='policy ' + name, **GRAD)
+    for s, nm in enumerate(('skel', 'attr', 'control')):
+        live = np.flatnonzero(peng.ever_live[s])
+        st = peng.net.stage[s]
+        tabs = ag.policy_net.__getattr__(f'{nm}_ind_mlp').layers()
+        base = peng.gt_off[s]
+        for j, t in enumerate(tabs):
+            pre = f'{nm}_ind_mlp.' + (f'affine_layers.{j}.' if j < len(tabs) - 1 else 'linear.')
+            wW, wb = psd[pre + 'W'].grad.numpy(), psd[pre + 'b'].grad.numpy()
+            rw = t.out_dim * t.input_dim
+            gW = GA[base + st.il[j].gW: base + st.il[j].gW + len(live) * rw].reshape(len(live), t.out_dim, t.input_dim)
+            gb = GA[base + st.il[j].gb: base + st.il[j].gb + len(live) * t.out_dim].reshape(len(live), t.out_dim)
+            assert_close(gW, wW[live], atol=1e-6 + 2e-5 * float(np.abs(wW).max()), what=pre + 'W', **GRAD)
+            assert_close(gb, wb[live], atol=1e-6 + 2e-5 * float(np.abs(wb).max()), what=pre + 'b', **GRAD)
+    veng.GA.zero_()
+    veng.run(arena, Ordering(arena, np.arange(T)).run(0, T), 1, 1.0 / T)
+    GV = veng.GA.cpu().numpy().astype(np.float64)
+    assert_close(GV[5] / T, float(vloss), rtol=1e-4, atol=1e-6, what='value loss')
+    for name, p, off, grp in veng.store.entries:
+        want = vsd[name].grad.numpy()
+        got = GV[16 + off:16 + off + p.numel()].reshape(want.shape)
+        assert_close(got, want, atol=1e-6 + 2e-5 * float(np.abs(want).max()), what='value ' + name, **GRAD)

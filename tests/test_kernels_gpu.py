@@ -227,6 +227,103 @@ def test_csr_aggregate_forward_and_adjoint(L):
     assert_close(out.cpu(), want.cpu(), rtol=1e-5, atol=1e-5, what='aggregate adjoint')
 
 
+@pytest.mark.parametrize('n_legs', [4, 7])
+def test_fused_graphconv_gemm_matches_aggregate_then_linear(L, n_legs):
+    """SardGemm.agg_*: forward Y = relu([sum_nbr x | x] [Wl|Wr]^T + b) and the adjoint [A^T dz | dz] [Wl; Wr] * act',
+    against fp64 torch built from the edge list.  7 legs give the root 7 neighbours: the loader keeps 4 neighbour
+    rows in registers and walks longer lists from memory."""
+    from sard_b200 import synthetic
+    from sard_b200.packed import Ordering, PackedRollout
+    shape = synthetic.EnvShape('wide', n_legs=n_legs, max_body_depth=5)
+    roll = synthetic.generate_rollout(shape, 180, seed=11, min_exec=5, max_exec=30)
+    ar = PackedRollout(roll, 'cuda')
+    order = Ordering(ar, np.random.default_rng(4).permutation(180))
+    run = order.run(7, 171)
+    sel = order.ids_np[7:171]
+    H = 64
+    n = run.n
+    assert L.lib.sard_gemm_agg_supported(H, H) == 1
+    ndg = dev(np.repeat(np.arange(len(sel)), roll.num_nodes[sel]), torch.int32)
+    nda = dev(np.concatenate([np.arange(roll.node_ptr[t], roll.node_ptr[t + 1]) for t in sel]), torch.int32)
+    start = np.concatenate([[0], np.cumsum(roll.num_nodes[sel])[:-1]])
+    src = np.concatenate([roll.edges[0, roll.edge_ptr[t]:roll.edge_ptr[t + 1]] + s for t, s in zip(sel, start)])
+    dst = np.concatenate([roll.edges[1, roll.edge_ptr[t]:roll.edge_ptr[t + 1]] + s for t, s in zip(sel, start)])
+    src_t, dst_t = torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda()
+    assert np.bincount(dst).max() >= min(n_legs, 5)
+    g = torch.Generator().manual_seed(n_legs)
+    xa = torch.zeros(n, 2 * H, device='cuda')
+    xa[:, H:] = torch.randn(n, H, generator=g).cuda()
+    Wl, Wr, b = (torch.randn(H, H, generator=g) / 8).cuda(), (torch.randn(H, H, generator=g) / 8).cuda(), torch.randn(H, generator=g).cuda()
+    Y = torch.zeros(n, H, device='cuda')
+    gm = L.SardGemm()
+    gm.A, gm.lda = xa.data_ptr() + 4 * H, 2 * H
+    gm.B0, gm.ldb0, gm.B1, gm.ldb1, gm.b_split, gm.bias = L.ptr(Wl), H, L.ptr(Wr), H, H, L.ptr(b)
+    gm.Y, gm.ldy, gm.M, gm.N, gm.R, gm.act = L.ptr(Y), H, n, H, 2 * H, L.ACT['relu']
+    gm.agg_cols, gm.agg_ptr, gm.agg_nbr, gm.agg_node, gm.agg_graph = H, L.ptr(ar.in_ptr), L.ptr(ar.in_nbr), L.ptr(nda), L.ptr(ndg)
+    gm.agg_cum, gm.agg_node_base, gm.agg_out, gm.ld_agg_out = run.sel.cum, run.sel.node_base, L.ptr(xa), 2 * H
+    L.check(L.lib.sard_linear_fwd(C.byref(gm), L.stream()))
+    x64 = xa[:, H:].double()
+    agg = torch.zeros(n, H, dtype=torch.float64, device='cuda').index_add_(0, dst_t, x64[src_t])
+    want = torch.relu(agg @ Wl.double().t() + x64 @ Wr.double().t() + b.double())
+    assert_close(xa[:, :H].cpu(), agg.cpu(), rtol=1e-6, atol=1e-6, what='fused aggregate side product')
+    assert_close(Y.cpu(), want.cpu(), rtol=1e-4, atol=2e-5, what='fused graphconv forward')
+    # adjoint: dx = (A^T dz Wl + dz Wr) * relu'(yprev)
+    dz = torch.randn(n, H, generator=g).cuda()
+    yprev = torch.randn(n, H, generator=g).cuda()
+    dx = torch.zeros(n, H, device='cuda')
+    gb = L.SardGemm()
+    gb.A, gb.lda, gb.B0, gb.ldb0, gb.B1, gb.ldb1, gb.b_split, gb.b_ksplit = L.ptr(dz), H, L.ptr(Wl), H, L.ptr(Wr), H, H, H
+    gb.Y, gb.ldy, gb.M, gb.N, gb.R, gb.dsplit = L.ptr(dx), H, n, H, 2 * H, H
+    gb.Dact, gb.ldd, gb.dact0, gb.dact1 = L.ptr(yprev), H, L.ACT['relu'], L.ACT['relu']
+    gb.agg_cols, gb.agg_ptr, gb.agg_nbr, gb.agg_node, gb.agg_graph = H, L.ptr(ar.out_ptr), L.ptr(ar.out_nbr), L.ptr(nda), L.ptr(ndg)
+    gb.agg_cum, gb.agg_node_base = run.sel.cum, run.sel.node_base
+    L.check(L.lib.sard_linear_bwd_data(C.byref(gb), L.stream()))
+    dz64 = dz.double()
+    aggT = torch.zeros(n, H, dtype=torch.float64, device='cuda').index_add_(0, src_t, dz64[dst_t])
+    want = (aggT @ Wl.double() + dz64 @ Wr.double()) * (yprev > 0)
+    assert_close(dx.cpu(), want.cpu(), rtol=1e-4, atol=2e-5, what='fused graphconv adjoint')
+
+
+@pytest.mark.parametrize('M,N,R', [(2048, 256, 512), (2048, 64, 512), (1000, 512, 256)])
+def test_linear_split_k_matches_dense(L, M, N, R):
+    """SardGemm.splitk_ws: few rows, long reduction (critic MLP): forward with tanh and backward-data with act' and
+    scattered rows must match fp64, and must be bit-identical from run to run (slice-ordered sum)."""
+    g = torch.Generator().manual_seed(M + N + R)
+    A = torch.randn(M, R, generator=g).cuda(); W = (torch.randn(N, R, generator=g) / np.sqrt(R)).cuda(); b = torch.randn(N, generator=g).cuda()
+    ws = torch.zeros(1024 * M, device='cuda')
+    Y = torch.zeros(M, N, device='cuda')
+    gm = L.SardGemm()
+    gm.A, gm.lda, gm.B0, gm.ldb0, gm.b_split, gm.bias = L.ptr(A), R, L.ptr(W), R, R, L.ptr(b)
+    gm.Y, gm.ldy, gm.M, gm.N, gm.R, gm.act = L.ptr(Y), N, M, N, R, L.ACT['tanh']
+    gm.splitk_ws, gm.splitk_floats = L.ptr(ws), ws.numel()
+    n0 = L.lib.sard_launch_count()
+    L.check(L.lib.sard_linear_fwd(C.byref(gm), L.stream()))
+    launched = L.lib.sard_launch_count() - n0
+    want = torch.tanh(A.double() @ W.double().t() + b.double())
+    assert_close(Y.cpu(), want.cpu(), rtol=1e-4, atol=2e-5, what='split-K forward')
+    if (M, N, R) != (1000, 512, 256):
+        assert launched == 2, 'expected the split-K pair (partial tiles + finish)'
+    Y1 = Y.clone(); Y.zero_()
+    L.check(L.lib.sard_linear_fwd(C.byref(gm), L.stream()))
+    assert torch.equal(Y, Y1)
+    # backward-data: dA[yrows] = (dY W) * tanh'(saved)
+    Nb, Rb = R, N                                   # dY [M, N] times W [N, R] -> [M, R]
+    dY = torch.randn(M, Rb, generator=g).cuda()
+    saved = torch.tanh(torch.randn(M, Nb, generator=g)).cuda()
+    yrows = torch.randperm(M, generator=g).int().cuda()
+    dA = torch.zeros(M, Nb, device='cuda')
+    gb = L.SardGemm()
+    gb.A, gb.lda, gb.B0, gb.ldb0, gb.b_split = L.ptr(dY), Rb, L.ptr(W), R, Nb
+    gb.Y, gb.ldy, gb.y_rows, gb.M, gb.N, gb.R, gb.dsplit = L.ptr(dA), Nb, L.ptr(yrows), M, Nb, Rb, Nb
+    gb.Dact, gb.ldd, gb.dact0, gb.dact1 = L.ptr(saved), Nb, L.ACT['tanh'], L.ACT['tanh']
+    gb.splitk_ws, gb.splitk_floats = L.ptr(ws), ws.numel()
+    L.check(L.lib.sard_linear_bwd_data(C.byref(gb), L.stream()))
+    want = torch.zeros(M, Nb, dtype=torch.float64, device='cuda')
+    want[yrows.long()] = (dY.double() @ W.double())
+    want = want * (1 - saved.double() ** 2)
+    assert_close(dA.cpu(), want.cpu(), rtol=1e-4, atol=2e-5, what='split-K backward-data')
+
+
 # ------------------------------------------------------------------------------------------ linear layers
 @pytest.mark.parametrize('M,N,R,act', [(1000, 64, 71, 'none'), (517, 64, 128, 'relu'), (300, 128, 256, 'tanh'),
                                        (77, 1, 448, 'none'), (2048, 64, 1410, 'relu'), (130, 6, 128, 'none'),
