@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(32 * WR_SLICES) wgrad_reduce_kernel(const Sard
   }
 }
 
-// Rows per chunk for an ungrouped weight gradient: enough chunks to put ~2 CTAs on every SM, at least
+// Rows per chunk for an ungrouped weight gradient: enough chunks to put ~1 CTA on every SM, at least
 // 16 rows each (the partial products are reduced in chunk order afterwards).
 extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
   const bool fast = N1 % 64 == 0 && (N2 % 128 == 0 || (N2 >= 16 && N2 < 128));   // wgrad_fast_kernel tiles: 64 x 128 (masked below 128)
@@ -407,7 +407,7 @@ extern "C" int sard_wgrad_chunk_rows(int M, int N1, int N2) {
   }
   const long long tiles = fast ? (long long)(N1 / 64) * ((N2 + 127) / 128)
                                : (long long)ceil_div(N1, N1 <= 16 ? 16 : 64) * ceil_div(N2, 64);
-  static const int waves = getenv("SARD_WG_WAVES") ? atoi(getenv("SARD_WG_WAVES")) : 2;   // tuning knob
+  static const int waves = getenv("SARD_WG_WAVES") ? atoi(getenv("SARD_WG_WAVES")) : 1;   // tuning knob: 1 wave (195.5 -> 193.2 ms, fewer partials)
   long long chunks = ((long long)waves * 148 + tiles - 1) / tiles;
   if (chunks < 1) chunks = 1;
   long long rows = (M + chunks - 1) / chunks;

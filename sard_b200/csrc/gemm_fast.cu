@@ -287,7 +287,7 @@ static int splitk_slices(const SardGemm* g) {
   while (S * 2 <= 8 && S * 2 <= nkb / 4 && ctas * S * 2 <= 296 && (long long)S * 2 * g->M * g->N <= g->splitk_floats) S *= 2;
   return S;
 }
-static const int g_wg_minb = getenv("SARD_WG_MINB") ? atoi(getenv("SARD_WG_MINB")) : 2;
+static const int g_wg_minb = getenv("SARD_WG_MINB") ? atoi(getenv("SARD_WG_MINB")) : 3;     // 3 CTAs/SM (80 registers, 32 B of spill): 195.5 -> 191.2 ms
 static const int g_minb = getenv("SARD_GEMM_MINB") ? atoi(getenv("SARD_GEMM_MINB")) : 0;
 template <int BN, int TN, bool NT, bool AGG = false>
 static int launch_fast(const SardGemm* g, cudaStream_t st) {
