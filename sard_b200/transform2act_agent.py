@@ -448,7 +448,9 @@ class Transform2ActAgent:
 
     def ppo_loss(self, states, actions, advantages, fixed_log_probs):
         """agent :390-409.  Forward + loss (+ backward into the engine's gradient bucket); returns
-        ``(surr_loss tensor, log dict, valid_loss)``.  ``policy_step_from_loss()`` applies clip + Adam."""
+        ``(surr_loss tensor, log dict, valid_loss)``.  The returned tensor carries no autograd graph: where the
+        reference calls ``surr_loss.backward(); clip_policy_grad(); optimizer_policy.step()`` (agent :354-357),
+        call ``policy_step_from_loss()``."""
         with torch.cuda.device(self.device):
             arena = PackedRollout.from_lists(states, actions, device=self.device)
             self._prepare(arena)
@@ -470,6 +472,17 @@ class Transform2ActAgent:
             valid = not (kl > 0.1 or surr > 10)
             self._pending = (arena, runs)
             return torch.tensor(surr, device=self.device), log, valid
+
+    def policy_step_from_loss(self):
+        """Gradient clip + Adam (gated on device like agent :404-407) on the gradients the last ``ppo_loss()`` left in
+        the policy engine's bucket: the ``backward / clip_policy_grad / optimizer_policy.step`` of agent :354-357."""
+        if getattr(self, '_pending', None) is None:
+            raise RuntimeError('policy_step_from_loss() needs a preceding ppo_loss()')
+        arena, runs = self._pending
+        self._pending = None
+        with torch.cuda.device(self.device):
+            n_skel = int(arena.num_nodes_np[arena.stage_np == 0].sum())
+            self.policy_net.engine.adam(arena.T, n_skel, [r is not None for r in runs], 40.0, self.clip_first_step_only, 1)
 
     def clip_policy_grad(self):
         """Clipping is fused into the optimiser step (``sard_adam_prepare``); kept for API compatibility."""

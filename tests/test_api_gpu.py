@@ -139,3 +139,38 @@ def test_checkpoint_interchange(tmp_path, cuda_device):
         a.policy_net.eval(); a.value_net.eval()
     assert torch.equal(ag.policy_net.get_log_prob(b.states, b.actions), ag2.policy_net.get_log_prob(b.states, b.actions))
     assert torch.equal(ag.value_net(b.states), ag2.value_net(b.states))
+
+
+def test_ppo_loss_then_policy_step_equals_train_step(cuda_device):
+    """The reference's single-step API: ppo_loss() + policy_step_from_loss() must leave the same weights as one
+    engine train_step on the same (stage-partitioned) batch."""
+    from sard_b200 import synthetic
+    from sard_b200.packed import Ordering, PackedRollout, stage_partition
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['patrol']
+    roll = synthetic.generate_rollout(shape, 80, seed=13, min_exec=5, max_exec=15)
+    b = roll.to_traj_batch()
+    g = torch.Generator().manual_seed(2)
+    adv = torch.randn(80, 1, generator=g)
+    a1, a2 = make_agent(shape, seed=4), make_agent(shape, seed=4)
+    for ag in (a1, a2):
+        ag.policy_net.train()
+    fixed = a1.policy_net.get_log_prob(b.states, b.actions).detach().clone()
+    for ag in (a1, a2):        # get_log_prob in train mode updated a1's RunningNorm: bring both to the same state
+        ag.policy_net.load_state_dict(a1.policy_net.state_dict())
+    before = {k: v.detach().clone() for k, v in a1.policy_net.state_dict().items()}
+    loss, log, valid = a1.ppo_loss(b.states, b.actions, adv, fixed)
+    assert valid and np.isfinite(float(loss))
+    a1.policy_step_from_loss()
+    arena = PackedRollout.from_lists(b.states, b.actions, device='cuda')
+    a2._prepare(arena)
+    arena.advantages.copy_(adv.reshape(-1).cuda()); arena.fixed_log_probs.copy_(fixed.reshape(-1).cuda())
+    order = Ordering(arena, stage_partition(arena.stage_np))
+    runs = order.stage_runs(0, arena.T)
+    n_skel = int(arena.num_nodes_np[arena.stage_np == 0].sum())
+    a2.policy_net.engine.train_step(arena, runs, arena.T, n_skel, [r is not None for r in runs], a2.clip_epsilon, 40.0,
+                                    a2.clip_first_step_only)
+    s1, s2 = a1.policy_net.state_dict(), a2.policy_net.state_dict()
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k
+    assert any(not torch.equal(s1[k], before[k]) for k in s1 if k.endswith('in_fc.weight')), 'the step must move the weights'
