@@ -252,6 +252,46 @@ class AdamState:
     def zero_grad(self, set_to_none=True):   # API compatibility; gradients live in the engine's bucket
         pass
 
+    # -- checkpointing (the reference omits optimiser state, transform2act_agent.py:192-199) -----------
+    def state_dict(self, module: nn.Module, store: 'FlatStore') -> dict:
+        """Adam moments by parameter name.  IndexLinear tables are stored sparsely: only rows that ever received a
+        gradient have non-zero moments (38 M table entries, 13 live body indices in a 4-leg run)."""
+        out = {'dense': {}, 'tables': {}, 'ctl_i': None if self.ctl_i is None else self.ctl_i.cpu().clone()}
+        if self.m is not None and store is not None and store.flat is not None and self.m.shape == store.flat.shape:
+            for name, p, off, _ in store.entries:
+                out['dense'][name] = (self.m[off:off + p.numel()].cpu().clone().view(p.shape),
+                                      self.v[off:off + p.numel()].cpu().clone().view(p.shape))
+        for name, p in module.named_parameters():
+            k = id(p)
+            if k in self.table_m:
+                m, v = self.table_m[k], self.table_v[k]
+                rows = torch.nonzero((m.reshape(m.shape[0], -1) != 0).any(1) | (v.reshape(v.shape[0], -1) != 0).any(1)).reshape(-1)
+                out['tables'][name] = (rows.cpu(), m[rows].cpu().clone(), v[rows].cpu().clone(), tuple(m.shape))
+        return out
+
+    def load_state_dict(self, state: dict, module: nn.Module, store: 'FlatStore'):
+        """Inverse of :meth:`state_dict`; call after the engine has built its flat store (``prepare``)."""
+        if store is None or store.flat is None:
+            raise RuntimeError('load_state_dict: the parameter store is not built yet (run prepare / one update first)')
+        self.ensure(store.flat)
+        for name, p, off, _ in store.entries:
+            if name in state['dense']:
+                m, v = state['dense'][name]
+                self.m[off:off + p.numel()].copy_(m.reshape(-1).to(self.m.device))
+                self.v[off:off + p.numel()].copy_(v.reshape(-1).to(self.v.device))
+        params = dict(module.named_parameters())
+        for name, (rows, m_rows, v_rows, shape) in state['tables'].items():
+            p = params[name]
+            if tuple(p.shape) != tuple(shape):
+                raise ValueError(f'optimizer state of {name}: table shape {tuple(shape)} != {tuple(p.shape)}')
+            m, v = self.table_state(p)
+            m.zero_(); v.zero_()
+            if len(rows):
+                m[rows.to(m.device)] = m_rows.to(m.device)
+                v[rows.to(v.device)] = v_rows.to(v.device)
+        if state.get('ctl_i') is not None:
+            self.ctl_i.copy_(state['ctl_i'].to(self.ctl_i.device))
+
 
 def dense_segments(flat, m, v, grad_base_ptr: int, ranges: Sequence[Tuple[int, int]]) -> list:
     """Split each group's [start,end) of the flat buffer into <= SEG_MAX-element Adam segments."""

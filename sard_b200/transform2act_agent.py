@@ -139,6 +139,11 @@ class Transform2ActAgent:
               'value_dict': {k: v.detach().cpu() for k, v in self.value_net.state_dict().items()},
               'running_state': self.running_state, 'loss_iter': self.loss_iter, 'best_rewards': self.best_rewards,
               'epoch': epoch, 'symmetry': self.policy_net.group.cur_subgroup_name if self.enable_infer else None}
+        # beyond the reference's keys (agent :192-199 drops the optimiser): Adam moments and step counters, the
+        # IndexLinear tables' moments stored sparsely (live rows only); ignored by the reference's load_checkpoint
+        cp['optimizer_state'] = {
+            'policy': self.optimizer_policy.state_dict(self.policy_net, self.policy_net.engine.store),
+            'value': self.optimizer_value.state_dict(self.value_net, self.value_net.engine.store)}
         with open(cp_path, 'wb') as f:
             pickle.dump(cp, f)
 
@@ -166,6 +171,13 @@ class Transform2ActAgent:
         self.running_state = cp['running_state']
         self.loss_iter = cp['loss_iter']
         self.best_rewards = cp.get('best_rewards', self.best_rewards)
+        ost = cp.get('optimizer_state')
+        if ost is not None and self.policy_net.control_action_log_std.device.type == 'cuda':
+            with torch.cuda.device(self.device):
+                self.policy_net.prepare(None, self.optimizer_policy)         # build the flat stores the moments map onto
+                self.value_net.prepare(self.optimizer_value)
+                self.optimizer_policy.load_state_dict(ost['policy'], self.policy_net, self.policy_net.engine.store)
+                self.optimizer_value.load_state_dict(ost['value'], self.value_net, self.value_net.engine.store)
         if self.enable_infer and cp.get('symmetry') is not None:
             self.policy_net.group.cur_subgroup_name = cp['symmetry']
 

@@ -124,7 +124,8 @@ def test_checkpoint_interchange(tmp_path, cuda_device):
     path = os.path.join(tmp_path, 'cp.p')
     ag.save_checkpoint_to(path, epoch=3)
     cp = pickle.load(open(path, 'rb'))
-    assert set(cp) == {'policy_dict', 'value_dict', 'running_state', 'loss_iter', 'best_rewards', 'epoch', 'symmetry'}
+    assert set(cp) == {'policy_dict', 'value_dict', 'running_state', 'loss_iter', 'best_rewards', 'epoch', 'symmetry',
+                       'optimizer_state'}                      # the reference's keys + the optimiser
     keys = set(cp['policy_dict'])
     for k in ('control_action_log_std', 'attr_action_log_std', 'hfield_enc.enc.0.weight', 'goal_enc.enc.2.bias', 'skel_norm.n',
               'control_gnn.in_fc.weight', 'attr_gnn.gconv_layers.2.lin_l.bias', 'attr_gnn.gconv_layers.0.lin_r.weight',
@@ -139,6 +140,19 @@ def test_checkpoint_interchange(tmp_path, cuda_device):
         a.policy_net.eval(); a.value_net.eval()
     assert torch.equal(ag.policy_net.get_log_prob(b.states, b.actions), ag2.policy_net.get_log_prob(b.states, b.actions))
     assert torch.equal(ag.value_net(b.states), ag2.value_net(b.states))
+    # optimiser state: sparse table moments, and a resumed run continues bit-identically
+    tabs = cp['optimizer_state']['policy']['tables']
+    rows, m_rows, _, tshape = tabs['control_ind_mlp.affine_layers.0.W']
+    assert 0 < len(rows) <= 13 and m_rows.shape[0] == len(rows) and tshape[0] == 40
+    roll2 = synthetic.generate_rollout(shape, 96, seed=6, min_exec=6, max_exec=20)
+    for a in (ag, ag2):
+        a.policy_net.train(); a.value_net.train()
+        np.random.seed(123)
+        a.update_params(roll2)
+    for k, v in ag.policy_net.state_dict().items():
+        assert torch.equal(v, ag2.policy_net.state_dict()[k]), k
+    for k, v in ag.value_net.state_dict().items():
+        assert torch.equal(v, ag2.value_net.state_dict()[k]), k
 
 
 def test_ppo_loss_then_policy_step_equals_train_step(cuda_device):
