@@ -64,6 +64,17 @@ static inline void sard_launch(void (*kernel)(P...), dim3 grid, dim3 block, size
   cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);   // errors surface through SARD_LAUNCH_OK
 }
 
+// cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) whether it was applied
+#define SARD_MAX_DEVICES 32
+static inline bool sard_first_use_on_device(bool (&done)[SARD_MAX_DEVICES]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= SARD_MAX_DEVICES) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 #define SARD_REQUIRE(cond, msg)                                                              \
   do {                                                                                       \
     if (!(cond)) return sard_set_error("%s:%d requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \

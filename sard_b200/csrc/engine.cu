@@ -59,12 +59,15 @@ struct SideCtx {
   bool forked[2];
 };
 std::mutex g_side_mu;
-std::unordered_map<cudaStream_t, SideCtx*> g_side;
+std::unordered_map<unsigned long long, SideCtx*> g_side;    // key: launching stream handle ^ device (the default stream's handle is 0 on every device)
 
 SideCtx* side_for(cudaStream_t main) {
   if (!g_sard_wgrad_overlap) return nullptr;
   std::lock_guard<std::mutex> lock(g_side_mu);
-  auto it = g_side.find(main);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(main) ^ ((unsigned long long)(dev + 1) << 56);
+  auto it = g_side.find(key);
   if (it != g_side.end()) { it->second->forked[0] = it->second->forked[1] = false; return it->second; }
   SideCtx* c = new SideCtx();
   c->main = main; c->k = 0; c->forked[0] = c->forked[1] = false;
@@ -73,7 +76,7 @@ SideCtx* side_for(cudaStream_t main) {
   for (int i = 0; i < 2; ++i)
     if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
-  g_side[main] = c;
+  g_side[key] = c;
   return c;
 }
 // stream for a weight gradient whose inputs were just produced on `st`

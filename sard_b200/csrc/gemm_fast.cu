@@ -215,10 +215,9 @@ template <int BN, int TN, bool NT, bool AGG, int MINB>
 static int launch_fast_mb(const SardGemm* g, cudaStream_t st) {
   constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
   constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, TN, NT, AGG, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
@@ -265,10 +264,9 @@ static int launch_splitk(const SardGemm* g, int S, cudaStream_t st) {
   constexpr int BN = 64;
   constexpr int tile_f = 2 * 16 * (128 + 4) + 2 * 16 * (BN + 4), c_f = 128 * (BN + 1);
   constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, 4, NT, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid(ceil_div(g->M, 128), g->N / BN, S);
   sard_launch(gemm_fast_kernel<BN, 4, NT, false, 3, true>, grid, 256, smem, st, *g);

@@ -182,10 +182,9 @@ template <int BN, bool NT>
 static int launch_mma(const SardGemm* g, cudaStream_t st) {
   constexpr int tile_f = 2 * 16 * (128 + 8) + 2 * 16 * (BN + 8), c_f = 128 * (BN + 1);
   constexpr size_t smem = sizeof(float) * (tile_f > c_f ? tile_f : c_f);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(gemm_mma_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;

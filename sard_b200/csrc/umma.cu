@@ -268,10 +268,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_gemm_kernel(const SardGe
 template <int NT_TILE, bool NT>
 static int launch_umma_t(const SardGemm* g, cudaStream_t st) {
   constexpr size_t smem = 2 * (2 * UMMA_BM * UMMA_KC + 2 * NT_TILE * UMMA_KC) * sizeof(float) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<NT_TILE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, UMMA_BM);
   if (tiles <= 0) return 0;
@@ -515,10 +514,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_gemm_ts_kernel(const Sar
 template <int NT_TILE, bool NT>
 static int launch_umma_ts(const SardGemm* g, cudaStream_t st) {
   constexpr size_t smem = 2 * (2 * 2 * NT_TILE * UMMA_KC) * sizeof(float) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(umma_gemm_ts_kernel<NT_TILE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, UMMA_BM);
   if (tiles <= 0) return 0;
@@ -694,10 +692,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) umma_wgrad_kernel(const SardW
 template <int NB>
 static int launch_umma_wgrad(const SardWGrad* w, int nchunks, cudaStream_t st) {
   constexpr size_t smem = 2 * (2 * NB * UMMA_KC) * sizeof(float) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[SARD_MAX_DEVICES] = {};
+  if (sard_first_use_on_device(configured)) {
     SARD_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid(nchunks, ceil_div(w->N1, UMMA_BM), ceil_div(w->N2, NB));
   sard_launch(umma_wgrad_kernel<NB>, grid, UMMA_THREADS, smem, st, *w);
