@@ -188,3 +188,37 @@ def test_ppo_loss_then_policy_step_equals_train_step(cuda_device):
     for k in s1:
         assert torch.equal(s1[k], s2[k]), k
     assert any(not torch.equal(s1[k], before[k]) for k in s1 if k.endswith('in_fc.weight')), 'the step must move the weights'
+
+
+def test_action_server_serves_the_batched_policy(cuda_device):
+    """Rollout workers (threads here) get, through the action server, exactly the rows a direct per-state
+    select_action(mean_action=True) gives -- from batched forwards."""
+    import threading
+    from sard_b200 import synthetic
+    from sard_b200.action_server import ActionServer
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['point_nav']
+    ag = make_agent(shape, 'K_1>0>K_1>4')
+    roll = synthetic.generate_rollout(shape, 48, seed=9, orbits=synthetic.SYMMETRIC_ORBITS['K_1'], min_exec=4, max_exec=10)
+    b = roll.to_traj_batch()
+    ag.policy_net.eval()
+    want = [ag.policy_net.select_action([s], True) for s in b.states]
+    srv = ActionServer(ag.policy_net, max_batch=16, max_wait_ms=20.0)
+    clients = [srv.client() for _ in range(4)]
+    got = [None] * len(b.states)
+
+    def work(w):
+        for i in range(w, len(b.states), 4):
+            got[i] = clients[w].select_action([b.states[i]], True)
+
+    srv.start()
+    th = [threading.Thread(target=work, args=(w,)) for w in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    srv.stop()
+    assert srv.served == len(b.states) and srv.batches < len(b.states), 'requests must have been batched'
+    for i, ((a, ae), (wa, wae)) in enumerate(zip(got, want)):
+        assert_close(a, wa, rtol=1e-5, atol=1e-6, what=f'action {i}')
+        assert_close(ae, wae, rtol=1e-5, atol=1e-6, what=f'action_env {i}')
