@@ -25,8 +25,9 @@ HOSTPACK = os.path.join(HERE, '_hostpack.so')
 def build_hostpack() -> str:
     """Native host packer (CPython extension, no CUDA): g++ only."""
     import sysconfig
+    import numpy
     inc = sysconfig.get_paths()['include']
-    subprocess.check_call(['g++', '-O3', '-std=c++17', '-shared', '-fPIC', '-pthread', f'-I{inc}',
+    subprocess.check_call(['g++', '-O3', '-std=c++17', '-shared', '-fPIC', '-pthread', f'-I{inc}', f'-I{numpy.get_include()}',
                            os.path.join(CSRC, 'hostpack.cpp'), '-o', HOSTPACK])
     return HOSTPACK
 
