@@ -34,6 +34,18 @@ UNIT = 'transition-updates/s'
 SITE_KINDS = ('in_fc', 'graphconv', 'index_linear', 'obs_encoder', 'critic_mlp', 'value_head', 'csr_aggregate')
 SITE_PASS = ('fwd', 'bwd_data', 'bwd_weight')
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FFMA lanes x 2 flop x boost clock
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of a site's kernels, from the committed `ncu --set full`
+# captures profiles/r01_ncu_full_wgrad_all_layers.csv and r01_ncu_full_final_gemm_wgrad_reduce.csv (cold caches: ncu
+# flushes between kernels; in the real run a minibatch's working set is L2-resident).  A site launch is one
+# sard_linear_* call, i.e. partial-product kernel + ordered reduction for the weight gradients.  Sites without an
+# unambiguous capture report null.
+NCU_TRAFFIC_BYTES = {
+    'graphconv.bwd_weight': 14.62e6 + 4.54e6,    # wgrad_fast_kernel<64,4,3,0> (133 chunks) + wgrad_reduce_kernel (66 CTAs)
+    # mean over the three JSMLP layers of a stage: (29.23 + 12.11) MB for 256->128, (19.49 + 6.15) MB for 128->128,
+    # ~9.6 MB for the skinny last layer (one pass over its 128-wide input; not in the capture)
+    'index_linear.bwd_weight': (29.23e6 + 12.11e6 + 19.49e6 + 6.15e6 + 9.6e6) / 3,
+    'graphconv.fwd': 6.21e6,                     # gemm_fast_kernel<64,4,1,1,2,0> (fused neighbour sum), 149 tiles
+}
 
 
 def parse():
@@ -322,10 +334,11 @@ def run_native(args):
                     'fp32_peak_tflops': FP32_PEAK_TFLOPS, 'frac_of_fp32_peak': ach / FP32_PEAK_TFLOPS,
                     'algorithmic_gbs': by / tms / 1e6}
         iso = next(r for r in site_rows if r['id'] == top_site)
+        roof['traffic'] = NCU_TRAFFIC_BYTES.get(f'{kind}.{SITE_PASS[top_site % 3]}')
         roof.update({'kernel': f'{kind}.{SITE_PASS[top_site % 3]}', 'launches_timed': int(n), 'avg_launch_us': tms / n * 1e3 if n else None,
                      'share_of_step': tms / ms, 'peak_source': pk['source'] + ' (sustained figure: kernel timed inside a long step)',
-                     'timing': 'CUDA events on the launching stream inside the timed region; four streams run concurrently there '
-                               '(critic, policy and their weight-gradient side streams), so this is the launch duration while '
+                     'timing': 'CUDA events on the launching stream inside the timed region; up to eight streams run concurrently there '
+                               '(critic, policy, their side and gather streams), so this is the launch duration while '
                                'sharing the SMs; the isolated_* keys are the same site timed in a serialised pass before the timed region',
                      'isolated_avg_launch_us': iso['ms'] / iso['launches'] * 1e3,
                      'isolated_achieved': iso['gbs'] if kind == 'csr_aggregate' else iso['tflops'],
