@@ -39,7 +39,7 @@ enum { SARD_STAGE_SKEL = 0, SARD_STAGE_ATTR = 1, SARD_STAGE_CONTROL = 2 };
 
 int sard_abi_version(void);
 const char* sard_last_error_string(void);
-/* sizeof() of the 13 ABI structs in declaration order, for binding self-checks (host memory, no GPU). */
+/* sizeof() of the ABI structs (SardJsmlpTc last, the others in declaration order), for binding self-checks (host memory, no GPU). */
 int sard_struct_sizes(int* out, int capacity);
 
 /* Kernels launched by the library since load (monotonic; host counter). */
@@ -258,6 +258,34 @@ typedef struct {
  * (the partials scratch must then hold ceil(M/that) * N1 * SARD_WG_LDPART(N2) floats). */
 int sard_wgrad_chunk_rows(int M, int N1, int N2);
 int sard_linear_bwd_weight(const SardWGrad* w, sard_stream_t stream);
+
+/* =====================================================================================
+ * Fused JSMLP on the tcgen05 tensor cores (sm_100a): the three IndexLinear layers of JSMLP.forward
+ * (design_opt/models/jsmlp.py:32-40, 74-79) in one launch per direction, 3xTF32 error-compensated,
+ * TMA-fed, hidden activations handed from layer to layer through tensor memory.
+ * Rows are in body-index-sorted order (sard_sort_by_index with tile_rows = 128).
+ * ===================================================================================== */
+typedef struct {
+  int n, in_dim, hid, out_dim, act, post, max_index, n_slots;
+  const float* xs; int ld_xs;            /* [n, in_dim] sorted input rows (sard_jsmlp_tc_split_input reads it) */
+  const float* W[3]; const float* b[3];  /* IndexLinear tables W[max_index, out, in], b[max_index, out] */
+  const int* slot_of_index;              /* [max_index] compact slot of each live body index, -1 otherwise */
+  const int* tiles; const int* num_tiles; int max_tiles;    /* sard_sort_by_index */
+  const int* srow;                       /* [n] destination row of sorted position p for `out` / `pre` (NULL: p) */
+  float* H[2]; int ldh;                  /* hidden activations tanh(IL1), tanh(IL2), raw fp32 [n, hid], sorted rows (may be NULL) */
+  float* Hhl[2];                         /* optional [n, 2*hid] pair copies (hi | lo) for the tensor-core weight gradients */
+  float* out; float* pre; int ldo;       /* IL3 output after `post`, optional value before it */
+  float* ws; long long ws_floats;        /* scratch: pair copies of the live weight slabs and of xs (256-byte aligned) */
+} SardJsmlpTc;
+/* 1 when the fused kernels cover JSMLP(in_dim -> h1 -> h2 -> out_dim) with n_il layers. */
+int sard_jsmlp_tc_supported(int in_dim, int h1, int h2, int out_dim, int n_il);
+long long sard_jsmlp_tc_workspace(int n, int in_dim, int out_dim, int n_slots);
+/* hi/lo pair copies of the live weight slabs (call after every optimiser step, before forward / backward). */
+int sard_jsmlp_tc_presplit(const SardJsmlpTc* a, sard_stream_t stream);
+/* hi/lo pair copy of xs into the scratch; sard_jsmlp_tc_xs_hl returns where it lives ([n, 2*in_dim]). */
+int sard_jsmlp_tc_split_input(const SardJsmlpTc* a, sard_stream_t stream);
+float* sard_jsmlp_tc_xs_hl(const SardJsmlpTc* a);
+int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream);
 
 /* =====================================================================================
  * Losses (fused forward + backward)

@@ -102,6 +102,13 @@ class SardPolicyNet(C.Structure):
                 ('P', vp), ('G', vp)]
 
 
+class SardJsmlpTc(C.Structure):
+    _fields_ = [('n', ci), ('in_dim', ci), ('hid', ci), ('out_dim', ci), ('act', ci), ('post', ci), ('max_index', ci),
+                ('n_slots', ci), ('xs', vp), ('ld_xs', ci), ('W', vp * 3), ('b', vp * 3), ('slot_of_index', vp),
+                ('tiles', vp), ('num_tiles', vp), ('max_tiles', ci), ('srow', vp), ('H', vp * 2), ('ldh', ci),
+                ('Hhl', vp * 2), ('out', vp), ('pre', vp), ('ldo', ci), ('ws', vp), ('ws_floats', cll)]
+
+
 P = C.POINTER
 _PROTOS = {
     'sard_abi_version': (ci, []),
@@ -143,6 +150,12 @@ _PROTOS = {
     'sard_adam_prepare': (ci, [vp, cf, cf, cf, vp, cf, ci, ci, ci, cd, cd, vp, vp, vp, vp]),
     'sard_adam_apply': (ci, [vp, ci, cll, cf, cf, cf, cf, ci, vp, vp, vp]),
     'sard_adam_update': (ci, [vp, cf, cf, cf, vp, cll, vp, cf, ci, ci, ci, cd, cd, vp, vp, vp, vp, ci, cll, cf, cf, vp]),
+    'sard_jsmlp_tc_supported': (ci, [ci, ci, ci, ci, ci]),
+    'sard_jsmlp_tc_workspace': (cll, [ci, ci, ci, ci]),
+    'sard_jsmlp_tc_presplit': (ci, [P(SardJsmlpTc), vp]),
+    'sard_jsmlp_tc_split_input': (ci, [P(SardJsmlpTc), vp]),
+    'sard_jsmlp_tc_xs_hl': (vp, [P(SardJsmlpTc)]),
+    'sard_jsmlp_tc_forward': (ci, [P(SardJsmlpTc), vp]),
     'sard_value_workspace': (cll, [P(SardValueNet), ci, ci]),
     'sard_policy_workspace': (cll, [P(SardPolicyNet), ci, ci, ci]),
     'sard_value_run': (ci, [P(SardValueNet), P(SardArena), P(SardSel), ci, ci, cf, vp, vp, ci, vp, vp, cll, vp]),
@@ -175,7 +188,7 @@ def _load():
 
 
 ABI_STRUCTS = (SardArena, SardSel, SardGatherOut, SardGemm, SardWGrad, SardPolicyLoss, SardAdamSeg, SardDense,
-               SardTower, SardValueNet, SardIndexLinear, SardPolicyStage, SardPolicyNet)
+               SardTower, SardValueNet, SardIndexLinear, SardPolicyStage, SardPolicyNet, SardJsmlpTc)
 
 lib = _load()
 

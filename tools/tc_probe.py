@@ -1,0 +1,168 @@
+"""GPU probe of the fused tcgen05 JSMLP kernels against fp64 torch (and timing against the SIMT path).
+
+    python tools/tc_probe.py [fwd] [bwd] [wgrad]      (default: everything that is built)
+"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from sard_b200 import _lib as L
+
+torch.cuda.set_device(0)
+dev = 'cuda'
+LIVE = [0, 1, 2, 3, 4, 6, 7, 8, 9, 31, 32, 33, 34]
+MAXI = 256
+
+
+def make_case(n, in_dim, out_dim, seed=0, post=0):
+    g = torch.Generator().manual_seed(seed)
+    body = torch.tensor(LIVE)[torch.randint(0, len(LIVE), (n,), generator=g)].int()
+    # skew like real rollouts: many roots / legs, few deep nodes
+    body[: n // 3] = torch.tensor(LIVE[:5])[torch.randint(0, 5, (n // 3,), generator=g)].int()
+    W = [torch.zeros(MAXI, 128, in_dim), torch.zeros(MAXI, 128, 128), torch.zeros(MAXI, out_dim, 128)]
+    b = [torch.zeros(MAXI, 128), torch.zeros(MAXI, 128), torch.zeros(MAXI, out_dim)]
+    for u in LIVE:
+        W[0][u] = torch.randn(128, in_dim, generator=g) / in_dim ** 0.5
+        W[1][u] = torch.randn(128, 128, generator=g) / 128 ** 0.5
+        W[2][u] = torch.randn(out_dim, 128, generator=g) / 128 ** 0.5
+        for j in range(3):
+            b[j][u] = torch.randn(b[j].shape[1], generator=g) * 0.1
+    x = torch.randn(n, in_dim, generator=g)
+    slot = torch.full((MAXI,), -1, dtype=torch.int32)
+    slot[LIVE] = torch.arange(len(LIVE), dtype=torch.int32)
+    return dict(n=n, in_dim=in_dim, out_dim=out_dim, post=post, body=body.to(dev), W=[w.to(dev) for w in W],
+                b=[v.to(dev) for v in b], x=x.to(dev), slot=slot.to(dev))
+
+
+def sort_rows(c, tile_rows=128, chunk_rows=256):
+    n = c['n']
+    i32 = lambda k: torch.zeros(k, dtype=torch.int32, device=dev)
+    max_tiles = n // tile_rows + len(LIVE)
+    max_chunks = n // chunk_rows + len(LIVE)
+    c.update(srow=i32(n), spos=i32(n), grp_ptr=i32(MAXI + 1), tiles=i32(4 * max_tiles), chunks=i32(4 * max_chunks),
+             grp_chunk_ptr=i32(MAXI + 1), counts=i32(4), max_tiles=max_tiles, max_chunks=max_chunks)
+    scratch = i32(((n + 255) // 256 + 2) * MAXI)
+    L.check(L.lib.sard_sort_by_index(L.ptr(c['body']), n, MAXI, tile_rows, chunk_rows, L.ptr(c['srow']), L.ptr(c['spos']),
+                                     L.ptr(c['grp_ptr']), L.ptr(c['tiles']), L.ptr(c['chunks']), L.ptr(c['grp_chunk_ptr']),
+                                     L.ptr(c['counts']), L.ptr(scratch), L.stream()))
+    torch.cuda.synchronize()
+    c['xs'] = c['x'][c['srow'].long()].contiguous()           # sorted rows
+    c['body_s'] = c['body'][c['srow'].long()].long()
+
+
+def reference(c):
+    xs, ind = c['xs'].double(), c['body_s']
+    W, b = [w.double() for w in c['W']], [v.double() for v in c['b']]
+    h1 = torch.tanh(torch.einsum('nk,nok->no', xs, W[0][ind]) + b[0][ind])
+    h2 = torch.tanh(torch.einsum('nk,nok->no', h1, W[1][ind]) + b[1][ind])
+    pre = torch.einsum('nk,nok->no', h2, W[2][ind]) + b[2][ind]
+    out = torch.sin(pre * np.pi / 2) if c['post'] else pre
+    return h1, h2, pre, out
+
+
+def tc_args(c):
+    n, in_dim, out_dim = c['n'], c['in_dim'], c['out_dim']
+    a = L.SardJsmlpTc()
+    a.n, a.in_dim, a.hid, a.out_dim, a.act, a.post, a.max_index, a.n_slots = n, in_dim, 128, out_dim, 2, c['post'], MAXI, len(LIVE)
+    a.xs, a.ld_xs = L.ptr(c['xs']), in_dim
+    for j in range(3):
+        a.W[j] = L.ptr(c['W'][j]); a.b[j] = L.ptr(c['b'][j])
+    a.slot_of_index = L.ptr(c['slot'])
+    a.tiles, a.num_tiles, a.max_tiles = L.ptr(c['tiles']), L.ptr(c['counts']), c['max_tiles']
+    a.srow = L.ptr(c['srow'])
+    c['H'] = [torch.zeros(n, 128, device=dev) for _ in range(2)]
+    c['Hhl'] = [torch.zeros(n, 256, device=dev) for _ in range(2)]
+    ldo = (out_dim + 3) // 4 * 4
+    c['out'] = torch.zeros(n, ldo, device=dev); c['pre'] = torch.zeros(n, ldo, device=dev)
+    for j in range(2):
+        a.H[j] = L.ptr(c['H'][j]); a.Hhl[j] = L.ptr(c['Hhl'][j])
+    a.ldh, a.out, a.pre, a.ldo = 128, L.ptr(c['out']), L.ptr(c['pre']), ldo
+    need = L.lib.sard_jsmlp_tc_workspace(n, in_dim, out_dim, len(LIVE))
+    c['ws'] = torch.zeros(need + 64, device=dev)
+    off = (-c['ws'].data_ptr() // 4) % 64
+    a.ws, a.ws_floats = c['ws'].data_ptr() + 4 * off, need
+    return a
+
+
+def timeit(fn, iters=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def probe_fwd(n, in_dim, out_dim, post):
+    c = make_case(n, in_dim, out_dim, seed=n % 97, post=post)
+    sort_rows(c)
+    a = tc_args(c)
+    st = L.stream()
+    L.check(L.lib.sard_jsmlp_tc_presplit(C.byref(a), st))
+    L.check(L.lib.sard_jsmlp_tc_split_input(C.byref(a), st))
+    L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st))
+    torch.cuda.synchronize()
+    h1, h2, pre, out = reference(c)
+    inv = c['spos'].long()                      # out rows are scattered to original order
+    d = out_dim
+    e = dict(h1=rel(c['H'][0], h1), h2=rel(c['H'][1], h2), pre=rel(c['pre'][inv][:, :d], pre), out=rel(c['out'][inv][:, :d], out),
+             h1hl=rel(c['Hhl'][0][:, :128].double() + c['Hhl'][0][:, 128:].double(), h1))
+    us = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st)))
+    us_pre = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_presplit(C.byref(a), st)))
+    us_split = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_split_input(C.byref(a), st)))
+    flops = 2.0 * n * (in_dim * 128 + 128 * 128 + 128 * out_dim)
+    ok = all(v < 2e-5 for v in e.values())
+    print(f'fwd n={n} in={in_dim} out={out_dim} post={post}: {"OK " if ok else "BAD"} rel err {e}  '
+          f'{us:.1f} us ({flops / us / 1e6:.1f} TFLOP/s), presplit {us_pre:.1f} us, split_input {us_split:.1f} us, '
+          f'tiles={int(c["counts"][0])}', flush=True)
+    return ok
+
+
+def probe_simt_fwd(n, in_dim, out_dim):
+    """the three grouped sard_linear_fwd launches of the SIMT path on the same case, for the timing comparison"""
+    c = make_case(n, in_dim, out_dim, seed=n % 97)
+    sort_rows(c)
+    H = [torch.zeros(n, 128, device=dev), torch.zeros(n, 128, device=dev), torch.zeros(n, 4 * ((out_dim + 3) // 4), device=dev)]
+    gs = []
+    dims = [(in_dim, 128), (128, 128), (128, out_dim)]
+    for j, (i, o) in enumerate(dims):
+        g = L.SardGemm()
+        A = c['xs'] if j == 0 else H[j - 1]
+        g.A, g.lda = L.ptr(A), i
+        g.B0, g.ldb0, g.b_split, g.b_group_stride = L.ptr(c['W'][j]), i, i, o * i
+        g.bias, g.bias_group_stride = L.ptr(c['b'][j]), o
+        g.M, g.N, g.R = n, o, i
+        g.tiles, g.num_tiles, g.max_tiles = L.ptr(c['tiles']), L.ptr(c['counts']), c['max_tiles']
+        g.act = 2 if j < 2 else 0
+        g.Y, g.ldy = L.ptr(H[j]), H[j].shape[1]
+        gs.append(g)
+    c['keep'] = H
+    st = L.stream()
+
+    def run():
+        for g in gs:
+            L.check(L.lib.sard_linear_fwd(C.byref(g), st))
+    us = timeit(run)
+    print(f'simt fwd n={n}: {us:.1f} us (3 launches)', flush=True)
+
+
+if __name__ == '__main__':
+    what = set(sys.argv[1:]) or {'fwd'}
+    ok = True
+    if 'fwd' in what:
+        for n, i, o, post in [(300, 256, 1, 0), (5000, 256, 6, 1), (18432, 256, 1, 0), (18432, 256, 3, 0), (26000, 256, 6, 1)]:
+            ok &= probe_fwd(n, i, o, post)
+        probe_simt_fwd(18432, 256, 1)
+    print('PROBE', 'PASS' if ok else 'FAIL')
+    sys.exit(0 if ok else 1)
