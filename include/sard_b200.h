@@ -286,6 +286,8 @@ int sard_jsmlp_tc_presplit(const SardJsmlpTc* a, sard_stream_t stream);
 int sard_jsmlp_tc_split_input(const SardJsmlpTc* a, sard_stream_t stream);
 float* sard_jsmlp_tc_xs_hl(const SardJsmlpTc* a);
 int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream);
+/* Tuning aid: clock64() stamps written by block 0 of the last fused launch (host array of n <= 32 values). */
+int sard_tc_debug_read(long long* out, int n);
 
 /* =====================================================================================
  * Losses (fused forward + backward)

@@ -156,6 +156,7 @@ _PROTOS = {
     'sard_jsmlp_tc_split_input': (ci, [P(SardJsmlpTc), vp]),
     'sard_jsmlp_tc_xs_hl': (vp, [P(SardJsmlpTc)]),
     'sard_jsmlp_tc_forward': (ci, [P(SardJsmlpTc), vp]),
+    'sard_tc_debug_read': (ci, [P(cll), ci]),
     'sard_value_workspace': (cll, [P(SardValueNet), ci, ci]),
     'sard_policy_workspace': (cll, [P(SardPolicyNet), ci, ci, ci]),
     'sard_value_run': (ci, [P(SardValueNet), P(SardArena), P(SardSel), ci, ci, cf, vp, vp, ci, vp, vp, cll, vp]),

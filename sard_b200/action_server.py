@@ -11,6 +11,11 @@ graph.  The call a worker makes keeps the reference's shape::
 
 Works with threads and with forked / spawned processes (``multiprocessing`` queues; states and actions are numpy).
 Requests with different ``mean_action`` are never mixed in one batch.
+
+A client may carry a ``key`` = the name of a design subgroup (``LearnedGroup.set_cur_subgroup_name``): its requests are
+served with the policy's group switched to that subgroup (embedding, orbit tie and symmetrizer all follow it), so the
+neighbour subgroups that ``optimize_policy`` evaluates (reference ``transform2act_agent.py:244-256``) can be sampled
+concurrently through one server instead of one after the other.  Requests with different keys are never mixed.
 """
 from __future__ import annotations
 
@@ -38,13 +43,13 @@ def _to_numpy_state(state: Sequence) -> list:
 class ActionClient:
     """Worker-side handle.  One per worker; create it with :meth:`ActionServer.client` BEFORE forking."""
 
-    def __init__(self, cid: int, request_q, response_q):
-        self.cid, self._req, self._resp = cid, request_q, response_q
+    def __init__(self, cid: int, request_q, response_q, key=None):
+        self.cid, self._req, self._resp, self.key = cid, request_q, response_q, key
 
     def select_action(self, x: Sequence[Sequence], mean_action: bool = False) -> Tuple[np.ndarray, np.ndarray]:
         """``x``: list of states (the reference passes one) -> ``(action, action_env)`` float64 ``[sum N, 8]``."""
         states = [_to_numpy_state(s) for s in x]
-        self._req.put((self.cid, bool(mean_action), states))
+        self._req.put((self.cid, (bool(mean_action), self.key), states))
         res = self._resp.get()
         if isinstance(res, BaseException):
             raise res
@@ -65,10 +70,10 @@ class ActionServer:
         self.batches = 0            # statistics: batched forwards run / states served
         self.served = 0
 
-    def client(self) -> ActionClient:
+    def client(self, key=None) -> ActionClient:
         q = self._ctx.Queue()
         self._resp.append(q)
-        return ActionClient(len(self._resp) - 1, self._req, q)
+        return ActionClient(len(self._resp) - 1, self._req, q, key)
 
     # -- serving ---------------------------------------------------------------------------------------------
     def start(self):
@@ -99,7 +104,7 @@ class ActionServer:
             except queue.Empty:
                 break
             if r == _STOP or r[1] != first[1]:
-                carry = r                       # a stop, or a request of the other sampling mode: next round
+                carry = r                       # a stop, or a request of another sampling mode / subgroup: next round
                 break
             batch.append(r)
             n_states += len(r[2])
@@ -126,7 +131,16 @@ class ActionServer:
             spans.append((cid, n, n + rows))
             n += rows
         try:
-            action, action_env = self.policy.select_action(states, batch[0][1])
+            mean_action, key = batch[0][1]
+            group = getattr(self.policy, 'group', None) if key is not None else None
+            prev = group.cur_subgroup_name if group is not None else None      # (not store/restore: that single
+            if group is not None:                                               #  backup slot belongs to optimize_policy)
+                group.set_cur_subgroup_name(key)
+            try:
+                action, action_env = self.policy.select_action(states, mean_action)
+            finally:
+                if group is not None:
+                    group.set_cur_subgroup_name(prev)
             for cid, a, b in spans:
                 self._resp[cid].put((np.array(action[a:b]), np.array(action_env[a:b])))
         except BaseException as e:               # noqa: BLE001  -- the worker re-raises it

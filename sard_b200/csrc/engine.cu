@@ -14,6 +14,7 @@
 #include <unordered_map>
 
 int g_sard_wgrad_overlap = 1;
+extern int g_sard_gemm_engine;
 static const int g_sard_fuse_agg = getenv("SARD_FUSE_AGG") ? atoi(getenv("SARD_FUSE_AGG")) : 1;   // GraphConv neighbour sum inside the GEMM loader
 extern "C" int sard_set_wgrad_overlap(int enabled) { g_sard_wgrad_overlap = enabled ? 1 : 0; return 0; }
 extern "C" int sard_get_wgrad_overlap(void) { return g_sard_wgrad_overlap; }
@@ -103,6 +104,16 @@ int side_join(SideCtx* c) {
 struct Bump {
   float* base; long long off;
   float* f(long long n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~3LL; return p; }
+  // 256-byte aligned block (TMA sources / destinations); alignment is relative to the ADDRESS, so the sizing pass
+  // (base == nullptr) reserves the worst case
+  float* a256(long long n) {
+    if (!base) { off += 64 + ((n + 63) & ~63LL); return nullptr; }
+    const uintptr_t cur = reinterpret_cast<uintptr_t>(base + off);
+    const long long pad = (long long)(((cur + 255) & ~uintptr_t(255)) - cur) / 4;
+    float* p = base + off + pad;
+    off += 64 + ((n + 63) & ~63LL);
+    return p;
+  }
   int* i(long long n) { return reinterpret_cast<int*>(f(n)); }
 };
 
@@ -493,7 +504,33 @@ struct StageBufs {
   float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
   float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2;
   int max_tiles, max_chunks;
+  bool tc;                       // fused tcgen05 JSMLP (jsmlp_tc.cu)
+  float* tcws; long long tcws_floats; float* Hhl[2];
 };
+
+// the fused tensor-core JSMLP serves engine 4 (the default) when the stage's shapes are covered
+bool stage_uses_tc(const SardPolicyStage& s) {
+  return g_sard_gemm_engine == 4 && s.n_il == 3 &&
+         sard_jsmlp_tc_supported(s.il[0].in, s.il[0].out, s.il[1].out, s.out_dim, s.n_il) && s.il[1].in == s.il[0].out &&
+         s.il[2].in == s.il[1].out;
+}
+SardJsmlpTc jsmlp_tc_args(const SardPolicyStage& s, const StageBufs& sb, int n, bool bwd) {
+  SardJsmlpTc a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.in_dim = s.il[0].in; a.hid = s.il[0].out; a.out_dim = s.out_dim; a.act = s.il_act; a.post = s.post;
+  a.max_index = s.max_index; a.n_slots = s.n_live;
+  a.xs = sb.xs; a.ld_xs = sb.ldxs;
+  for (int j = 0; j < 3; ++j) { a.W[j] = s.il[j].W; a.b[j] = s.il[j].b; }
+  a.slot_of_index = s.slot_of_index;
+  a.tiles = sb.tiles; a.num_tiles = sb.counts; a.max_tiles = sb.max_tiles;
+  a.srow = sb.srow;
+  // the hidden activations only leave the SM when a backward pass follows
+  a.H[0] = bwd ? sb.H[0] : nullptr; a.H[1] = bwd ? sb.H[1] : nullptr; a.ldh = s.il[0].out;
+  a.Hhl[0] = nullptr; a.Hhl[1] = nullptr;
+  a.out = sb.out; a.pre = s.post != SARD_POST_NONE ? sb.pre : nullptr; a.ldo = sb.ldo;
+  a.ws = sb.tcws; a.ws_floats = sb.tcws_floats;
+  return a;
+}
 
 void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, int n, int B, bool train, StageBufs& sb) {
   carve_tower(b, s.tower, n, B, train, sb.t);
@@ -516,6 +553,13 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
   sb.ldo = r4(s.out_dim);
   sb.out = b.f((long long)n * sb.ldo);
   sb.pre = b.f((long long)n * sb.ldo);
+  sb.tc = stage_uses_tc(s);
+  sb.tcws = nullptr; sb.tcws_floats = 0; sb.Hhl[0] = sb.Hhl[1] = nullptr;
+  if (sb.tc) {
+    sb.tcws_floats = sard_jsmlp_tc_workspace(n, s.il[0].in, s.out_dim, s.n_live);
+    sb.tcws = b.a256(sb.tcws_floats);
+    if (train) for (int j = 0; j < 2; ++j) sb.Hhl[j] = b.a256((long long)n * 2 * s.il[j].out);
+  }
   if (train) {
     sb.dout = b.f((long long)n * sb.ldo);
     sb.gstat = b.f((long long)B * (4 + s.out_dim));
@@ -580,6 +624,10 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, s2));
     SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
                                 sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
+    if (sb.tc) {                   // hi/lo pair copies of the live weight slabs (they change with every optimiser step)
+      const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
+      SARD_TRY(sard_jsmlp_tc_presplit(&a, s2));
+    }
   }
   SARD_TRY(tower_forward(tw, P, arena, sel, sb.t, st));
   SARD_TRY(side_join(side));
@@ -587,6 +635,13 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   SARD_TRY(sard_concat_sorted(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph, n,
                               sb.xs, sb.ldxs, st));
   SARD_REQUIRE(s.il[0].in == sb.ldxs, "first index-linear input width");
+  if (sb.tc) {
+    // the three IndexLinear layers in one tcgen05 launch (jsmlp_tc.cu)
+    const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
+    SARD_TRY(sard_jsmlp_tc_split_input(&a, st));
+    site(K_IL, 0);
+    SARD_TRY(sard_jsmlp_tc_forward(&a, st));
+  } else
   for (int j = 0; j < s.n_il; ++j) {
     const bool last = j == s.n_il - 1;
     SardGemm g = gemm0();

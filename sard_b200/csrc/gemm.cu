@@ -171,7 +171,7 @@ int sard_wgrad_fast(const SardWGrad* w, int nchunks, cudaStream_t st);
 int sard_gemm_mma(const SardGemm* g, bool nt, cudaStream_t st);       // gemm_mma.cu; -1 = not covered
 int sard_gemm_skinny_fwd(const SardGemm* g, cudaStream_t st);        // gemm_skinny.cu; -1 = not covered
 int sard_gemm_skinny_bwd(const SardGemm* g, cudaStream_t st);
-int g_sard_gemm_engine = 0;                                        // 0 = fp32 FFMA (SIMT), 1 = tcgen05 3xTF32
+int g_sard_gemm_engine = 4;   // 0 fp32 FFMA (SIMT) | 1,2 per-layer tcgen05 | 3 mma.sync | 4 (default) fused tcgen05 JSMLP + SIMT elsewhere
 extern "C" int sard_set_gemm_engine(int engine) { g_sard_gemm_engine = engine; return 0; }
 extern "C" int sard_get_gemm_engine(void) { return g_sard_gemm_engine; }
 

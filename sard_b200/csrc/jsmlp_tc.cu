@@ -119,14 +119,18 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ forward
-#define JS_THREADS 192
+#define JS_EPI_WARPS 16              // epilogue warps: 4 per TMEM lane quarter, one 32-column chunk each
+#define JS_THREADS (64 + 32 * JS_EPI_WARPS)
 #define JS_STAGES 3
 #define JS_STAGE_BYTES 65536        // A_hi | A_lo | W_hi | W_lo, 16 KB each (128 rows x 32 fp32, SWIZZLE_128B)
 #define JS_SUB 16384
 #define JS_HID 128
+#define JS_STAGING3 (JS_STAGES * JS_STAGE_BYTES)    // 32 KB store staging of column chunk 3 (chunks 0-2 reuse the ring's A regions)
+#define JS_SMEM (JS_STAGES * JS_STAGE_BYTES + 32768 + 1024)
 
 struct JsFwdParams {
   CUtensorMap tm_x, tm_w1, tm_w2, tm_w3;
+  CUtensorMap tm_h1, tm_h2;                               // H1hl / H2hl [n, 256], 32 x 32 store boxes
   const int4* tiles; const int* num_tiles; const int* slot_of_index;
   const float* b1; const float* b2; const float* b3;     // bias tables [max_index, out]
   float* H1; float* H2; int ldh;                          // hidden activations, raw fp32 [n, 128] (sorted rows)
@@ -135,9 +139,30 @@ struct JsFwdParams {
   int in_dim, out_dim, act, post;
 };
 
-__device__ __forceinline__ float js_act(float v, int act) {
-  return act == SARD_ACT_TANH ? tanhf(v) : act_apply(v, act);
+// 8 activations; the branch on the activation kind is taken once per call, not once per element
+__device__ __forceinline__ void js_act8(float* v, const float* b, int act) {
+  if (act == SARD_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tc::tanh_fast(v[j] + b[j]);
+  } else if (act == SARD_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + b[j], 0.f);
+  } else if (act == SARD_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 1.f / (1.f + __expf(-(v[j] + b[j])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += b[j];
+  }
 }
+
+// cycle stamps of block 0 (debug / tuning): sard_tc_debug_read copies them out
+__device__ long long g_js_dbg[32];
+extern "C" int sard_tc_debug_read(long long* out, int n) {
+  SARD_CUDA(cudaMemcpyFromSymbol(out, g_js_dbg, sizeof(long long) * (n < 32 ? n : 32)));
+  return 0;
+}
+#define JS_STAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_js_dbg[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __grid_constant__ JsFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -151,7 +176,7 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
     for (int s = 0; s < JS_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
     for (int l = 0; l < 3; ++l) tc::mbar_init(&bar_d[l], 1);
     for (int l = 0; l < 2; ++l)
-      for (int c = 0; c < 4; ++c) tc::mbar_init(&bar_a[l][c], 128);
+      for (int c = 0; c < 4; ++c) tc::mbar_init(&bar_a[l][c], 32 * JS_EPI_WARPS);
     tc::mbar_fence_init();
     tc::tma_prefetch_desc(&p.tm_x); tc::tma_prefetch_desc(&p.tm_w1); tc::tma_prefetch_desc(&p.tm_w2); tc::tma_prefetch_desc(&p.tm_w3);
   }
@@ -159,7 +184,9 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) JS_STAMP(0);
   pdl_sync();                                  // everything above overlaps the predecessor's tail
+  if (tid == 0) JS_STAMP(1);
 
   const bool active = (int)blockIdx.x < *p.num_tiles;
   if (active) {
@@ -222,6 +249,7 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
           tc::mma_commit(&bar_empty[s]);
         }
         tc::mma_commit(&bar_d[0]);
+        JS_STAMP(8);
         // ---- layer 2: A = tanh(layer 1) from tensor memory, chunk by chunk as the epilogue produces it
         for (int kc = 0; kc < 4; ++kc, ++it) {
           const int s = it % JS_STAGES;
@@ -240,6 +268,7 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
           tc::mma_commit(&bar_empty[s]);
         }
         tc::mma_commit(&bar_d[1]);
+        JS_STAMP(9);
         // ---- layer 3 (N = 16): accumulator reuses D1's columns
         {
           const int s = it % JS_STAGES;
@@ -262,57 +291,89 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
         }
       }
     } else {
-      // ---- epilogue: thread <-> tile row <-> TMEM lane (a warp may only touch lanes 32*(warp%4) ..)
+      // ---- epilogue: thread <-> tile row <-> TMEM lane (a warp may only touch lanes 32*(warp%4) ..).  The four warps
+      //      of a lane quarter work on the SAME 32-column chunk, 8 columns each, so the chunks of a layer complete one
+      //      after the other and the next layer's MMAs (which wait per chunk) trail the epilogue instead of following it
       const int q = warp & 3;
+      const int sub = (warp - 2) >> 2;                   // 0..3: which 8 columns of every chunk
       const int trow = q * 32 + lane;
       const int r = row_start + trow;
       const bool valid = r < row_end;
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      const bool slab_full = row_start + q * 32 + 32 <= row_end;       // this warp's 32 rows all belong to the tile
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const float* bias = (l == 0 ? p.b1 : p.b2) + (size_t)u * JS_HID;
         float* H = l == 0 ? p.H1 : p.H2;
         float* Hhl = l == 0 ? p.H1hl : p.H2hl;
         const uint32_t D = l == 0 ? D1 : D2;
+        float bv[4][8];                                  // this thread's 32 bias values (8 per chunk), loaded under the MMAs
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + sub * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + sub * 8 + 4));
+          bv[c][0] = b0.x; bv[c][1] = b0.y; bv[c][2] = b0.z; bv[c][3] = b0.w;
+          bv[c][4] = b1.x; bv[c][5] = b1.y; bv[c][6] = b1.z; bv[c][7] = b1.w;
+        }
+        if (l == 1 && Hhl) {                             // layer 1's stores have read the staging slabs
+          if (lane == 0) tc::tma_store_wait_read();
+          tc::named_sync(1 + q, 128);
+        }
         tc::mbar_wait(&bar_d[l], 0);
         tc::tc_fence_after();
-#pragma unroll 1
+        if (warp == 2) JS_STAMP(2 + 2 * l);
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tc::tmem_ld32(D + lane_off + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
-            v[j] = js_act(v[j] + b.x, p.act); v[j + 1] = js_act(v[j + 1] + b.y, p.act);
-            v[j + 2] = js_act(v[j + 2] + b.z, p.act); v[j + 3] = js_act(v[j + 3] + b.w, p.act);
-          }
-          if (valid) {
-            if (H) {
-              float* hp = H + (size_t)r * p.ldh + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (Hhl) {
-              float* hp = Hhl + (size_t)r * 2 * JS_HID + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 h, lo;
-                tc::split4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), h, lo);
-                *reinterpret_cast<float4*>(hp + j) = h;
-                *reinterpret_cast<float4*>(hp + JS_HID + j) = lo;
-              }
-            }
-          }
-          tc::tmem_st16_split(AH + lane_off + c * 32, AL + lane_off + c * 32, v);
-          tc::tmem_st16_split(AH + lane_off + c * 32 + 16, AL + lane_off + c * 32 + 16, v + 16);
+          const int c0 = c * 32 + sub * 8;
+          float v[8];
+          tc::tmem_ld8(D + lane_off + c0, v);
+          js_act8(v, bv[c], p.act);
+          // hand the activation to the next layer first (its MMAs wait on this), then write it out for the backward
+          tc::tmem_st8_split(AH + lane_off + c0, AL + lane_off + c0, v);
           tc::tmem_st_wait();
           tc::tc_fence_before();
           tc::mbar_arrive(&bar_a[l][c]);
+          if (H && valid) {                               // raw copy: bring-up / SIMT consumers only (scattered stores, slow)
+            float* hp = H + (size_t)r * p.ldh + c0;
+            *reinterpret_cast<float4*>(hp) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(hp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (Hhl) {
+            float4 h0, l0, h1, l1;
+            tc::split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+            tc::split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+            // pair copy for the backward / weight gradient: staged in shared memory in the swizzled box layout
+            // (conflict-free: 8 lanes cover all 32 banks) and written out by TMA, one 32 x 32 box per quarter and chunk
+            uint8_t* stg = base + (c < 3 ? c * JS_STAGE_BYTES : JS_STAGING3) + q * 4096;     // [hi 16 KB | lo 16 KB]
+            if (slab_full) {
+              const uint32_t o0 = tc::sw128_off(lane, sub * 2), o1 = tc::sw128_off(lane, sub * 2 + 1);
+              *reinterpret_cast<float4*>(stg + o0) = h0;
+              *reinterpret_cast<float4*>(stg + o1) = h1;
+              *reinterpret_cast<float4*>(stg + JS_SUB + o0) = l0;
+              *reinterpret_cast<float4*>(stg + JS_SUB + o1) = l1;
+              tc::fence_async_smem();
+              tc::named_sync(1 + q, 128);
+              if (sub == c && lane == 0) {
+                const CUtensorMap* tm = l == 0 ? &p.tm_h1 : &p.tm_h2;
+                tc::tma_store_2d(tm, c * 32, row_start + q * 32, stg);
+                tc::tma_store_2d(tm, JS_HID + c * 32, row_start + q * 32, stg + JS_SUB);
+                tc::tma_store_commit();
+              }
+            } else if (valid) {                           // ragged last tile of a body index: predicated row stores
+              float* hp = Hhl + (size_t)r * 2 * JS_HID + c0;
+              *reinterpret_cast<float4*>(hp) = h0;
+              *reinterpret_cast<float4*>(hp + 4) = h1;
+              *reinterpret_cast<float4*>(hp + JS_HID) = l0;
+              *reinterpret_cast<float4*>(hp + JS_HID + 4) = l1;
+            }
+          }
         }
+        if (warp == 2) JS_STAMP(3 + 2 * l);
       }
-      tc::mbar_wait(&bar_d[2], 0);
-      tc::tc_fence_after();
-      {
+      if (sub == 0) {
+        tc::mbar_wait(&bar_d[2], 0);
+        tc::tc_fence_after();
+        if (warp == 2) JS_STAMP(6);
         float v[16];
         tc::tmem_ld16(D1 + lane_off, v);
         if (valid) {
@@ -327,7 +388,9 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
             }
           }
         }
+        if (warp == 2) JS_STAMP(7);
       }
+      if (lane == 0) tc::tma_store_wait_all();
     }
   }
   tc::tc_fence_before();
@@ -410,7 +473,9 @@ extern "C" int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream)
   p.H1 = a->H[0]; p.H2 = a->H[1]; p.ldh = a->ldh; p.H1hl = a->Hhl[0]; p.H2hl = a->Hhl[1];
   p.out = a->out; p.pre = a->pre; p.ldo = a->ldo; p.srow = a->srow;
   p.in_dim = a->in_dim; p.out_dim = a->out_dim; p.act = a->act; p.post = a->post;
-  constexpr size_t smem = JS_STAGES * JS_STAGE_BYTES + 1024;
+  if (a->Hhl[0]) SARD_TRY(sard_tmap_2d(&p.tm_h1, a->Hhl[0], a->n, 2 * JS_HID, 2 * JS_HID, 32, 32));
+  if (a->Hhl[1]) SARD_TRY(sard_tmap_2d(&p.tm_h2, a->Hhl[1], a->n, 2 * JS_HID, 2 * JS_HID, 32, 32));
+  constexpr size_t smem = JS_SMEM;
   static bool configured[SARD_MAX_DEVICES] = {};
   if (sard_first_use_on_device(configured))
     SARD_CUDA(cudaFuncSetAttribute(jsmlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,6 +26,17 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   h.w = tf32_hi(v.w); l.w = v.w - h.w;
 }
 
+// tanh(x) = 1 - 2 / (1 + 2^(x * 2/ln 2)) on the special-function unit (ex2.approx, rcp.approx): absolute error
+// < 5e-7 over the whole range (saturates correctly at +-1), 5 instructions instead of tanhf's ~40.  The fused
+// epilogues are bound by this math (one thread per tile row), and the activations feed 3xTF32 products whose own
+// error is of the same order.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
 // ---------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -84,6 +95,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// shared -> global tile store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes complete
+// byte offset of 16-byte piece j (0..7) of row r inside a SWIZZLE_128B slab of 128-byte rows (slab base 1024-aligned)
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
 // ---------------------------------------------------------------------------------------- tensor memory
 // whole warp; `cols` a power of two in [32, 512]; the base address lands in *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -125,6 +147,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// named barrier among `threads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -141,13 +175,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
         "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
       : "memory");
 }
-// split 16 values and store hi / lo into two tensor-memory column ranges of this thread's lane
-__device__ __forceinline__ void tmem_st16_split(uint32_t t_hi, uint32_t t_lo, const float* v) {
-  float h[16], l[16];
+// split 8 values and store hi / lo into two tensor-memory column ranges of this thread's lane
+__device__ __forceinline__ void tmem_st8_split(uint32_t t_hi, uint32_t t_lo, const float* v) {
+  float h[8], l[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { h[j] = tf32_hi(v[j]); l[j] = v[j] - h[j]; }
-  tmem_st16(t_hi, h);
-  tmem_st16(t_lo, l);
+  for (int j = 0; j < 8; ++j) { h[j] = tf32_hi(v[j]); l[j] = v[j] - h[j]; }
+  tmem_st8(t_hi, h);
+  tmem_st8(t_lo, l);
 }
 
 // ---------------------------------------------------------------------------------------- UMMA

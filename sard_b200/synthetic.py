@@ -300,3 +300,69 @@ class SyntheticEnv:
 
     def seed(self, seed):
         pass
+
+
+class SyntheticRolloutEnv(SyntheticEnv):
+    """A stand-in simulator with the DERL env's step protocol (``derl_env.py:213-264``): 5 skeleton-transform steps,
+    1 attribute-transform step, then ``exec_steps`` execution steps of a fixed symmetric ant tree.  It exists so that
+    ``agent.sample()`` / ``agent.optimize()`` -- the host glue around the CUDA path -- can run where MuJoCo cannot;
+    rewards are a smooth function of the actions, nothing is simulated."""
+
+    def __init__(self, shape: EnvShape, exec_steps: int = 20, depth: int = 2, seed: int = 0):
+        super().__init__(shape)
+        self.exec_steps, self.depth = exec_steps, depth
+        self.rng = np.random.default_rng(seed)
+        self.num = None
+        self.t = 0
+
+    def _graph(self):
+        legs = self.shape.n_legs
+        parents, body, depth_of = [-1], [0], [0]
+        prev = {}
+        for d in range(1, self.depth + 1):
+            for leg in range(1, legs + 1):
+                parents.append(0 if d == 1 else prev[leg])
+                body.append(int('1' * (d - 1) + str(leg), self.index_base))
+                depth_of.append(d)
+                prev[leg] = len(parents) - 1
+        n = len(parents)
+        e = []
+        for i in range(1, n):
+            e += [[i, parents[i]], [parents[i], i]]
+        return n, np.array(e, dtype=np.int64).T.reshape(2, -1), np.array(body, dtype=np.int64), depth_of
+
+    def _state(self, stage: int):
+        n, edges, body, depth_of = self._graph()
+        sh = self.shape
+        obs = np.zeros((n, sh.state_dim))
+        for i in range(n):
+            obs[i, min(depth_of[i], sh.max_body_depth - 1)] = 1.0
+        if stage == 2:
+            obs[:, sh.attr_fixed_dim:sh.attr_fixed_dim + sh.sim_obs_dim] = self.rng.standard_normal((n, sh.sim_obs_dim))
+        obs[:, -ATTR_DESIGN_DIM:] = self.attr
+        return [obs, edges, np.array([stage]), np.array([n]), body, self.rng.standard_normal(sh.hfield_dim),
+                self.rng.standard_normal(sh.obj_dim), self.rng.standard_normal(sh.goal_dim)]
+
+    def reset(self, extra_args=None):
+        self.num = (extra_args or {}).get('num')
+        self.t = 0
+        n = self._graph()[0]
+        self.attr = np.zeros((n, ATTR_DESIGN_DIM))
+        return self._state(0)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64)
+        self.t += 1
+        if self.t <= 5:
+            stage, name, reward = (0 if self.t < 5 else 1), 'skeleton_transform', 0.0
+        elif self.t == 6:
+            self.attr = np.clip(a[:, 1:1 + ATTR_DESIGN_DIM], -1, 1)
+            stage, name, reward = 2, 'attribute_transform', 0.0
+        else:
+            stage, name = 2, 'execution'
+            reward = float(1.0 - np.mean(a[:, 0] ** 2))
+        done = self.t >= 6 + self.exec_steps
+        info = {'stage': name, 'done': done}
+        if done:
+            info['done_max_nsteps'] = 1.0
+        return self._state(stage), reward, done, info

@@ -78,6 +78,8 @@ class Transform2ActAgent:
         self.enable_infer = cfg.enable_infer
         self.total_time_steps = 0
         self.last_update_stats = {}
+        self.sampler = None                 # rollout source: RolloutSampler-like object with sample() / sample_many()
+        self.subgroup_eval_batch_size = 1000        # agent :252
         self.prefetch_gather = os.environ.get('SARD_PREFETCH', '1') != '0'
         self._gather_ctx = None
         self.overlap_nets = True          # critic and policy updates of a minibatch on two CUDA streams
@@ -185,10 +187,111 @@ class Transform2ActAgent:
         for p in self.scheduled_params.values():
             p.set_epoch(epoch)
 
-    # ---- rollouts: host side, outside the scope of the CUDA path ---------------------------------
+    # ---- epoch driver (agent :216-272, :411-455) --------------------------------------------------------------
+    def optimize(self, epoch):
+        """agent :216-219."""
+        self.pre_epoch_update(epoch)
+        info = self.optimize_policy(epoch)
+        self.log_optimize_policy(epoch, info)
+
+    def optimize_policy(self, epoch):
+        """agent :221-272: sample -> update_params -> evaluation rollouts -> subgroup-neighbour evaluation ->
+        symmetry update.  The neighbour subgroups are sampled concurrently through one action server
+        (``sample_subgroups``) instead of one after the other (agent :250-253)."""
+        cfg = self.cfg
+        t0 = time.time()
+        batch, log = self.sample(cfg.min_batch_size)
+        self.total_time_steps += log.num_steps
+        t1 = time.time()
+        _, log_train = self.update_params(batch)
+        t2 = time.time()
+        _, log_eval = self.sample(cfg.eval_batch_size, mean_action=True)
+        t3 = time.time()
+        if self.enable_infer:
+            group = self.policy_net.group
+            group.store_cur_subgroup_name()
+            if getattr(cfg, 'enable_design', True) and cfg.updating_subgroup:
+                if cfg.struct_subgroup:
+                    evaluate_names = list(group.get_neibor_subgroup_name())
+                else:
+                    evaluate_names = list(np.random.choice(group.get_neibor_subgroup_name(), size=2, replace=False))
+            else:
+                evaluate_names = []
+            value_dict = {name: lg.avg_episode_reward
+                          for name, lg in self.sample_subgroups(evaluate_names, self.subgroup_eval_batch_size).items()}
+            group.update_all_values(value_dict)
+            group.restore_cur_subgroup_name()
+            self.policy_net.update_symmetry(log.avg_episode_reward)
+            for k, v in self.policy_net.get_info().items():
+                if isinstance(v, dict):
+                    for k1, v1 in v.items():
+                        log_train[f'{k}_{k1}'] = v1
+                else:
+                    log_train[f'{k}'] = v
+        return {'log': log, 'log_eval': log_eval, 'T_sample': t1 - t0, 'T_update': t2 - t1, 'T_eval': t3 - t2,
+                'T_total': t3 - t0, 'log_train': log_train}
+
+    def log_optimize_policy(self, epoch, info):
+        """agent :411-455: console line, best-reward flag, TensorBoard / wandb scalars when a writer is attached."""
+        cfg = self.cfg
+        log, log_eval, log_train = info['log'], info['log_eval'], info['log_train']
+        if self.logger is not None:
+            self.logger.info(f'{epoch}\tT_sample {info["T_sample"]:.2f}\tT_update {info["T_update"]:.2f}\tT_eval {info["T_eval"]:.2f}\t'
+                             f'train_R {log.avg_reward:.2f}\ttrain_R_eps {log.avg_episode_reward:.2f}\t'
+                             f'exec_R {log_eval.avg_exec_reward:.2f}\texec_R_eps {log_eval.avg_exec_episode_reward:.2f}\t'
+                             f'{getattr(cfg, "id", "")}')
+        if log_eval.avg_exec_episode_reward > self.best_rewards:
+            self.best_rewards = log_eval.avg_exec_episode_reward
+            self.save_best_flag = True
+        else:
+            self.save_best_flag = False
+        tb = self.tb_logger
+        if tb is None:
+            return
+        tb_x = self.total_time_steps
+        for name, v in (('train_R_avg', log.avg_reward), ('train_R_eps_avg', log.avg_episode_reward),
+                        ('eval_R_eps_avg', log_eval.avg_episode_reward), ('exec_R_avg', log_eval.avg_exec_reward),
+                        ('exec_R_eps_avg', log_eval.avg_exec_episode_reward)):
+            tb.add_scalar(name + '_t', v, tb_x)
+            tb.add_scalar(name, v, epoch)
+        for k, v in log.stats_loggers.items():
+            if 'done_' in k:
+                tb.add_scalar(f'train_{k}', v.avg(), epoch)
+        for k, v in log_train.items():
+            tb.add_scalar(f'train_{k}', v, epoch)
+
+    # ---- rollouts: the simulator is external host code; the policy stays on the GPU behind the action server ----
+    def _sampler(self):
+        if self.sampler is None:
+            env = self.env
+            if not (hasattr(env, 'reset') and hasattr(env, 'step')):
+                raise NotImplementedError('this env has no reset()/step(): attach a rollout source with agent.sampler = '
+                                          'RolloutSampler(...) or feed update_params() a TrajBatchDisc-like batch '
+                                          '(see INTEGRATION.md)')
+            from .sampling import RolloutSampler
+            factory = getattr(self, 'env_factory', None)
+            if factory is None:
+                if self.num_threads > 1:
+                    raise NotImplementedError('num_threads > 1 needs agent.env_factory(pid) -> env (one simulator per worker)')
+                factory = lambda pid: env
+            self.sampler = RolloutSampler(self.policy_net, factory, self.num_threads, noise_rate=self.noise_rate)
+        return self.sampler
+
     def sample(self, min_batch_size, mean_action=False, render=False, nthreads=None):
-        raise NotImplementedError('MuJoCo rollouts stay on the reference host stack; feed update_params() a '
-                                  'TrajBatchDisc-like batch (see INTEGRATION.md)')
+        """agent.py:109-135: ``(TrajBatchDisc, LoggerRLV1)``.  Workers call ``select_action`` through the batching
+        server (one batched GPU forward per window) instead of moving the nets to the CPU (agent.py:114-115)."""
+        for m in self.sample_modules:
+            m.train(False)
+        return self._sampler().sample(min_batch_size, mean_action, nthreads)
+
+    def sample_subgroups(self, names, min_batch_size, mean_action=False):
+        """Rollouts under each of the subgroups ``names`` (agent :250-253), all at once: name -> LoggerRLV1."""
+        if not names:
+            return {}
+        for m in self.sample_modules:
+            m.train(False)
+        out = self._sampler().sample_many({n: min_batch_size for n in names}, mean_action)
+        return {n: lg for n, (_, lg) in out.items()}
 
     # ---- the hot path ------------------------------------------------------------------------------
     def pack(self, batch) -> PackedRollout:

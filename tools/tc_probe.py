@@ -64,7 +64,7 @@ def reference(c):
     return h1, h2, pre, out
 
 
-def tc_args(c):
+def tc_args(c, raw=True):
     n, in_dim, out_dim = c['n'], c['in_dim'], c['out_dim']
     a = L.SardJsmlpTc()
     a.n, a.in_dim, a.hid, a.out_dim, a.act, a.post, a.max_index, a.n_slots = n, in_dim, 128, out_dim, 2, c['post'], MAXI, len(LIVE)
@@ -79,7 +79,8 @@ def tc_args(c):
     ldo = (out_dim + 3) // 4 * 4
     c['out'] = torch.zeros(n, ldo, device=dev); c['pre'] = torch.zeros(n, ldo, device=dev)
     for j in range(2):
-        a.H[j] = L.ptr(c['H'][j]); a.Hhl[j] = L.ptr(c['Hhl'][j])
+        a.H[j] = L.ptr(c['H'][j]) if raw else None
+        a.Hhl[j] = L.ptr(c['Hhl'][j])
     a.ldh, a.out, a.pre, a.ldo = 128, L.ptr(c['out']), L.ptr(c['pre']), ldo
     need = L.lib.sard_jsmlp_tc_workspace(n, in_dim, out_dim, len(LIVE))
     c['ws'] = torch.zeros(need + 64, device=dev)
@@ -114,18 +115,32 @@ def probe_fwd(n, in_dim, out_dim, post):
     L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st))
     torch.cuda.synchronize()
     h1, h2, pre, out = reference(c)
-    inv = c['spos'].long()                      # out rows are scattered to original order
+    inv = c['srow'].long()                      # out rows are scattered to their original row srow[p]
     d = out_dim
     e = dict(h1=rel(c['H'][0], h1), h2=rel(c['H'][1], h2), pre=rel(c['pre'][inv][:, :d], pre), out=rel(c['out'][inv][:, :d], out),
-             h1hl=rel(c['Hhl'][0][:, :128].double() + c['Hhl'][0][:, 128:].double(), h1))
+             h1hl=rel(c['Hhl'][0][:, :128].double() + c['Hhl'][0][:, 128:].double(), h1),
+             h2hl=rel(c['Hhl'][1][:, :128].double() + c['Hhl'][1][:, 128:].double(), h2))
+    us_raw = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st)))
+    a = tc_args(c, raw=False)                   # the production configuration: pair copies only (TMA stores)
+    L.check(L.lib.sard_jsmlp_tc_presplit(C.byref(a), st))
+    L.check(L.lib.sard_jsmlp_tc_split_input(C.byref(a), st))
+    L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st))
+    torch.cuda.synchronize()
+    e['h2hl_noraw'] = rel(c['Hhl'][1][:, :128].double() + c['Hhl'][1][:, 128:].double(), h2)
+    e['out_noraw'] = rel(c['out'][inv][:, :d], out)
     us = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_forward(C.byref(a), st)))
     us_pre = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_presplit(C.byref(a), st)))
     us_split = timeit(lambda: L.check(L.lib.sard_jsmlp_tc_split_input(C.byref(a), st)))
     flops = 2.0 * n * (in_dim * 128 + 128 * 128 + 128 * out_dim)
     ok = all(v < 2e-5 for v in e.values())
     print(f'fwd n={n} in={in_dim} out={out_dim} post={post}: {"OK " if ok else "BAD"} rel err {e}  '
-          f'{us:.1f} us ({flops / us / 1e6:.1f} TFLOP/s), presplit {us_pre:.1f} us, split_input {us_split:.1f} us, '
+          f'{us:.1f} us ({flops / us / 1e6:.1f} TFLOP/s; with raw H copies {us_raw:.1f} us), presplit {us_pre:.1f} us, split_input {us_split:.1f} us, '
           f'tiles={int(c["counts"][0])}', flush=True)
+    buf = (C.c_longlong * 32)()
+    L.lib.sard_tc_debug_read(buf, 32)
+    t = list(buf)
+    print('   block0 cycles: pdl_wait %d | L1 issue done +%d | d1 ready +%d | epi1 done +%d | L2 issue done +%d | d2 ready +%d | epi2 done +%d | d3 ready +%d | end +%d'
+          % (t[1] - t[0], t[8] - t[1], t[2] - t[1], t[3] - t[1], t[9] - t[1], t[4] - t[1], t[5] - t[1], t[6] - t[1], t[7] - t[1]), flush=True)
     return ok
 
 
