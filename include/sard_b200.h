@@ -150,6 +150,13 @@ int sard_gather_nodes(const SardArena* arena, const SardSel* sel, const SardGath
 int sard_sort_by_index(const int* body, int n, int max_index, int tile_rows, int chunk_rows,
                        int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
                        int* counts, int* scratch, sard_stream_t stream);
+/* As above with every index starting on a tile boundary (what the fused tensor-core JSMLP kernels consume: all
+ * tiles are whole, the unused positions behind an index's rows are padding).  srow has srow_capacity >=
+ * n + (number of present indices) * (tile_rows - 1) entries and is -1 at padding positions; counts[3] = positions
+ * in use; chunk_rows must be a multiple of tile_rows; row_end of a tile / chunk stays the end of the real rows. */
+int sard_sort_by_index_padded(const int* body, int n, int max_index, int tile_rows, int chunk_rows, int srow_capacity,
+                              int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
+                              int* counts, int* scratch, sard_stream_t stream);
 
 /* =====================================================================================
  * RunningNorm  (khrylib/rl/core/running_norm.py:22-42)
@@ -276,6 +283,7 @@ typedef struct {
   float* Hhl[2];                         /* optional [n, 2*hid] pair copies (hi | lo) for the tensor-core weight gradients */
   float* out; float* pre; int ldo;       /* IL3 output after `post`, optional value before it */
   float* ws; long long ws_floats;        /* scratch: pair copies of the live weight slabs and of xs (256-byte aligned) */
+  int padded;                            /* 1: rows follow sard_sort_by_index_padded (n = row capacity, a multiple of 128; srow -1 at padding) */
 } SardJsmlpTc;
 /* 1 when the fused kernels cover JSMLP(in_dim -> h1 -> h2 -> out_dim) with n_il layers. */
 int sard_jsmlp_tc_supported(int in_dim, int h1, int h2, int out_dim, int n_il);
@@ -286,6 +294,26 @@ int sard_jsmlp_tc_presplit(const SardJsmlpTc* a, sard_stream_t stream);
 int sard_jsmlp_tc_split_input(const SardJsmlpTc* a, sard_stream_t stream);
 float* sard_jsmlp_tc_xs_hl(const SardJsmlpTc* a);
 int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream);
+/* Backward of the fused JSMLP (padded row space only; in_dim 256, hid 128).  All pair arrays are [n, hi | lo]. */
+typedef struct {
+  const float* dout; int ld_dout;        /* [rows, ld] gradient w.r.t. IL3's output before `post`, ORIGINAL row order (srow maps) */
+  float* dOs_hl;                         /* [n, 64] scratch: dout at sorted positions, 32 columns hi | 32 lo */
+  float* dZhl[2];                        /* [n, 2*hid] out: gradients w.r.t. the pre-activations of IL1 ([0]) and IL2 ([1]) */
+  float* dxs; int ld_dxs;                /* [n, in_dim] out: gradient w.r.t. the sorted input rows (raw fp32) */
+  const int* chunks; const int* num_chunks; int max_chunks; const int* grp_chunk_ptr;   /* sard_sort_by_index_padded */
+  float* partials;                       /* scratch float[sard_jsmlp_tc_partials_floats(max_chunks)] */
+  float* gW[3]; float* gb[3];            /* compact gradients, accumulated: gW[j][slot][out][in], gb[j][slot][out] */
+} SardJsmlpTcBwd;
+int sard_jsmlp_tc_bwd_supported(int in_dim, int h1, int h2, int out_dim, int n_il);
+long long sard_jsmlp_tc_partials_floats(int max_chunks);
+/* dZ2, dZ1 (pair arrays) and dxs from dout: one launch (+ the small re-ordering kernel for dout). */
+int sard_jsmlp_tc_backward(const SardJsmlpTc* a, const SardJsmlpTcBwd* b, sard_stream_t stream);
+/* dW / db of the three tables for the live body indices: one launch over row chunks + the ordered reduction. */
+int sard_jsmlp_tc_wgrad(const SardJsmlpTc* a, const SardJsmlpTcBwd* b, sard_stream_t stream);
+/* [h[row] | ext[graph(row)]] of the row at every sorted position, split hi | lo, zeros at padding positions
+ * (transform2act_policy.py:204-213 in the operand format of the fused kernels): xs_hl [rows_cap, 2*(Fh+Fe)]. */
+int sard_concat_sorted_split(const float* h, int ld_h, int Fh, const float* ext, int ld_ext, int Fe, const int* srow,
+                             const int* nd_graph, int rows_cap, float* xs_hl, sard_stream_t stream);
 /* Tuning aid: clock64() stamps written by block 0 of the last fused launch (host array of n <= 32 values). */
 int sard_tc_debug_read(long long* out, int n);
 

@@ -106,7 +106,13 @@ class SardJsmlpTc(C.Structure):
     _fields_ = [('n', ci), ('in_dim', ci), ('hid', ci), ('out_dim', ci), ('act', ci), ('post', ci), ('max_index', ci),
                 ('n_slots', ci), ('xs', vp), ('ld_xs', ci), ('W', vp * 3), ('b', vp * 3), ('slot_of_index', vp),
                 ('tiles', vp), ('num_tiles', vp), ('max_tiles', ci), ('srow', vp), ('H', vp * 2), ('ldh', ci),
-                ('Hhl', vp * 2), ('out', vp), ('pre', vp), ('ldo', ci), ('ws', vp), ('ws_floats', cll)]
+                ('Hhl', vp * 2), ('out', vp), ('pre', vp), ('ldo', ci), ('ws', vp), ('ws_floats', cll), ('padded', ci)]
+
+
+class SardJsmlpTcBwd(C.Structure):
+    _fields_ = [('dout', vp), ('ld_dout', ci), ('dOs_hl', vp), ('dZhl', vp * 2), ('dxs', vp), ('ld_dxs', ci),
+                ('chunks', vp), ('num_chunks', vp), ('max_chunks', ci), ('grp_chunk_ptr', vp), ('partials', vp),
+                ('gW', vp * 3), ('gb', vp * 3)]
 
 
 P = C.POINTER
@@ -126,6 +132,7 @@ _PROTOS = {
     'sard_orbit_rep': (ci, [vp, vp, ci, vp, ci, vp, vp, vp]),
     'sard_gather_nodes': (ci, [P(SardArena), P(SardSel), P(SardGatherOut), vp]),
     'sard_sort_by_index': (ci, [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sard_sort_by_index_padded': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sard_norm_moments': (ci, [vp, ci, ci, ci, vp, vp, vp]),
     'sard_norm_update': (ci, [vp, ci, ci, vp, vp, vp, vp, vp, vp]),
     'sard_norm_prepare_eval': (ci, [vp, ci, vp, vp]),
@@ -156,6 +163,11 @@ _PROTOS = {
     'sard_jsmlp_tc_split_input': (ci, [P(SardJsmlpTc), vp]),
     'sard_jsmlp_tc_xs_hl': (vp, [P(SardJsmlpTc)]),
     'sard_jsmlp_tc_forward': (ci, [P(SardJsmlpTc), vp]),
+    'sard_jsmlp_tc_bwd_supported': (ci, [ci, ci, ci, ci, ci]),
+    'sard_jsmlp_tc_partials_floats': (cll, [ci]),
+    'sard_jsmlp_tc_backward': (ci, [P(SardJsmlpTc), P(SardJsmlpTcBwd), vp]),
+    'sard_jsmlp_tc_wgrad': (ci, [P(SardJsmlpTc), P(SardJsmlpTcBwd), vp]),
+    'sard_concat_sorted_split': (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, vp, vp]),
     'sard_tc_debug_read': (ci, [P(cll), ci]),
     'sard_value_workspace': (cll, [P(SardValueNet), ci, ci]),
     'sard_policy_workspace': (cll, [P(SardPolicyNet), ci, ci, ci]),
@@ -189,7 +201,7 @@ def _load():
 
 
 ABI_STRUCTS = (SardArena, SardSel, SardGatherOut, SardGemm, SardWGrad, SardPolicyLoss, SardAdamSeg, SardDense,
-               SardTower, SardValueNet, SardIndexLinear, SardPolicyStage, SardPolicyNet, SardJsmlpTc)
+               SardTower, SardValueNet, SardIndexLinear, SardPolicyStage, SardPolicyNet, SardJsmlpTc, SardJsmlpTcBwd)
 
 lib = _load()
 

@@ -33,7 +33,7 @@ extern "C" int sard_struct_sizes(int* out, int capacity) {
   const int sizes[] = {(int)sizeof(SardArena), (int)sizeof(SardSel), (int)sizeof(SardGatherOut), (int)sizeof(SardGemm),
                        (int)sizeof(SardWGrad), (int)sizeof(SardPolicyLoss), (int)sizeof(SardAdamSeg), (int)sizeof(SardDense),
                        (int)sizeof(SardTower), (int)sizeof(SardValueNet), (int)sizeof(SardIndexLinear),
-                       (int)sizeof(SardPolicyStage), (int)sizeof(SardPolicyNet), (int)sizeof(SardJsmlpTc)};
+                       (int)sizeof(SardPolicyStage), (int)sizeof(SardPolicyNet), (int)sizeof(SardJsmlpTc), (int)sizeof(SardJsmlpTcBwd)};
   const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
   for (int i = 0; i < n && i < capacity; ++i) out[i] = sizes[i];
   return n;

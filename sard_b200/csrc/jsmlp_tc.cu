@@ -58,8 +58,9 @@ int sard_tmap_slab(CUtensorMap* out, const float* base, long long rows, long lon
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
   cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)slabs};
   cuuint32_t estr[3] = {1, 1, 1};
+  // MN-major tf32 operands: the one layout tcgen05 reads them in (tc::smem_desc_mn32)
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return sard_set_error("cuTensorMapEncodeTiled(slab rows=%lld cols=%lld ld=%lld box=%dx%d) failed: %d", rows, cols, ld, box_rows, slabs, (int)r);
   return 0;
@@ -136,7 +137,7 @@ struct JsFwdParams {
   float* H1; float* H2; int ldh;                          // hidden activations, raw fp32 [n, 128] (sorted rows)
   float* H1hl; float* H2hl;                               // optional pair copies [n, 256]
   float* out; float* pre; int ldo; const int* srow;      // final layer, scattered to row srow[p]
-  int in_dim, out_dim, act, post;
+  int in_dim, out_dim, act, post, padded;
 };
 
 // 8 activations; the branch on the activation kind is taken once per call, not once per element
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
       const int r = row_start + trow;
       const bool valid = r < row_end;
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-      const bool slab_full = row_start + q * 32 + 32 <= row_end;       // this warp's 32 rows all belong to the tile
+      const bool slab_full = p.padded || row_start + q * 32 + 32 <= row_end;   // this warp's 32 rows all belong to the tile
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const float* bias = (l == 0 ? p.b1 : p.b2) + (size_t)u * JS_HID;
@@ -399,10 +400,8 @@ __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------ host
-namespace {
-struct JsLayout { int outp[3], kp[3]; long long whl[3], wthl[3], xs_hl, total; };
 // floats; every block 256-byte aligned
-JsLayout js_layout(int n, int in_dim, int out_dim, int n_slots) {
+JsLayout sard_js_layout(int n, int in_dim, int out_dim, int n_slots) {
   JsLayout L;
   const int in[3] = {in_dim, JS_HID, JS_HID};
   L.outp[0] = JS_HID; L.outp[1] = JS_HID; L.outp[2] = 16;
@@ -416,7 +415,7 @@ JsLayout js_layout(int n, int in_dim, int out_dim, int n_slots) {
   (void)out_dim;
   return L;
 }
-}  // namespace
+static inline JsLayout js_layout(int n, int in_dim, int out_dim, int n_slots) { return sard_js_layout(n, in_dim, out_dim, n_slots); }
 
 extern "C" int sard_jsmlp_tc_supported(int in_dim, int h1, int h2, int out_dim, int n_il) {
   return n_il == 3 && h1 == JS_HID && h2 == JS_HID && in_dim % 32 == 0 && in_dim >= 32 && in_dim <= 1024 && out_dim >= 1 && out_dim <= 16;
@@ -472,7 +471,8 @@ extern "C" int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream)
   p.b1 = a->b[0]; p.b2 = a->b[1]; p.b3 = a->b[2];
   p.H1 = a->H[0]; p.H2 = a->H[1]; p.ldh = a->ldh; p.H1hl = a->Hhl[0]; p.H2hl = a->Hhl[1];
   p.out = a->out; p.pre = a->pre; p.ldo = a->ldo; p.srow = a->srow;
-  p.in_dim = a->in_dim; p.out_dim = a->out_dim; p.act = a->act; p.post = a->post;
+  p.in_dim = a->in_dim; p.out_dim = a->out_dim; p.act = a->act; p.post = a->post; p.padded = a->padded;
+  SARD_REQUIRE(!a->padded || a->n % 128 == 0, "jsmlp_tc: a padded row space has a multiple of 128 rows");
   if (a->Hhl[0]) SARD_TRY(sard_tmap_2d(&p.tm_h1, a->Hhl[0], a->n, 2 * JS_HID, 2 * JS_HID, 32, 32));
   if (a->Hhl[1]) SARD_TRY(sard_tmap_2d(&p.tm_h2, a->Hhl[1], a->n, 2 * JS_HID, 2 * JS_HID, 32, 32));
   constexpr size_t smem = JS_SMEM;

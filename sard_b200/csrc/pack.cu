@@ -169,7 +169,7 @@ __global__ void sort_hist_kernel(const int* __restrict__ body, int n, int max_in
 
 // one block of 1024 threads, thread u owns body index u: per-index totals, then block-wide exclusive
 // scans give the row / tile / chunk offsets and every thread writes its own tile and chunk entries
-__global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_index, int tile_rows, int chunk_rows,
+__global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_index, int tile_rows, int chunk_rows, int pad,
                                  int* __restrict__ blockhist, int* __restrict__ cnt, int* __restrict__ grp_ptr,
                                  int4* __restrict__ tiles, int4* __restrict__ chunks, int* __restrict__ grp_chunk_ptr,
                                  int* __restrict__ counts) {
@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_
     cnt[u] = total;
   }
   const int my_t = (total + tile_rows - 1) / tile_rows, my_c = (total + chunk_rows - 1) / chunk_rows;
-  sc[0][u] = total; sc[1][u] = my_t; sc[2][u] = my_c;
+  // pad: every index starts on a tile boundary (sorted positions beyond its rows stay unused: srow = -1)
+  const int span = pad ? my_t * tile_rows : total;
+  sc[0][u] = span; sc[1][u] = my_t; sc[2][u] = my_c;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {          // inclusive Hillis-Steele scan of the three counters
     int v0 = 0, v1 = 0, v2 = 0;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_
     __syncthreads();
   }
   if (u < max_index) {
-    const int run = sc[0][u] - total, t0 = sc[1][u] - my_t, c0 = sc[2][u] - my_c;
+    const int run = sc[0][u] - span, t0 = sc[1][u] - my_t, c0 = sc[2][u] - my_c;
     grp_ptr[u] = run;
     grp_chunk_ptr[u] = c0;
     for (int k = 0; k < my_t; ++k) tiles[t0 + k] = make_int4(run + k * tile_rows, run + min((k + 1) * tile_rows, total), u, 0);
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(int nb, int n, int max_
       grp_chunk_ptr[max_index] = sc[2][u];
       counts[0] = sc[1][u];
       counts[1] = sc[2][u];
+      counts[3] = sc[0][u];                      // sorted positions in use (== n without padding)
     }
   }
 }
@@ -238,10 +241,20 @@ __global__ void sort_scatter_kernel(const int* __restrict__ body, int n, int max
 extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int tile_rows, int chunk_rows,
                                   int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
                                   int* counts, int* scratch, sard_stream_t stream) {
+  return sard_sort_by_index_padded(body, n, max_index, tile_rows, chunk_rows, 0, srow, spos, grp_ptr, tiles, chunks, grp_chunk_ptr,
+                                   counts, scratch, stream);
+}
+
+extern "C" int sard_sort_by_index_padded(const int* body, int n, int max_index, int tile_rows, int chunk_rows, int srow_capacity,
+                                         int* srow, int* spos, int* grp_ptr, int* tiles, int* chunks, int* grp_chunk_ptr,
+                                         int* counts, int* scratch, sard_stream_t stream) {
   SARD_REQUIRE(max_index > 0 && max_index <= 1024, "max_index");
   SARD_REQUIRE(tile_rows > 0 && chunk_rows > 0, "tile/chunk rows");
+  const int pad = srow_capacity > 0;
+  SARD_REQUIRE(!pad || chunk_rows % tile_rows == 0, "padded sort: chunk_rows must be a multiple of tile_rows");
   cudaStream_t st = as_stream(stream);
   SARD_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
+  if (pad) SARD_CUDA(cudaMemsetAsync(srow, 0xff, sizeof(int) * (size_t)srow_capacity, st));
   const int nb = n > 0 ? ceil_div(n, SORT_BLOCK) : 0;
   int* blockhist = scratch;
   int* cnt = scratch + (size_t)nb * max_index;
@@ -249,7 +262,7 @@ extern "C" int sard_sort_by_index(const int* body, int n, int max_index, int til
     sard_launch(sort_hist_kernel, nb, SORT_BLOCK, max_index * sizeof(int), st, body, n, max_index, blockhist, counts);
     SARD_LAUNCH_OK("sort_hist_kernel");
   }
-  sard_launch(sort_scan_kernel, 1, 1024, 0, st, nb, n, max_index, tile_rows, chunk_rows, blockhist, cnt, grp_ptr,
+  sard_launch(sort_scan_kernel, 1, 1024, 0, st, nb, n, max_index, tile_rows, chunk_rows, pad, blockhist, cnt, grp_ptr,
                                       reinterpret_cast<int4*>(tiles), reinterpret_cast<int4*>(chunks),
                                       grp_chunk_ptr, counts);
   SARD_LAUNCH_OK("sort_scan_kernel");

@@ -205,6 +205,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major tf32 operands exist in ONE shared-memory layout: SWIZZLE_128B_BASE32B (layout type 1; TMA swizzle mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 fp32 (128 B) along M/N, atoms of 4 K-rows, the 32-byte piece index
+// XORed with (row & 3).  LBO = bytes between 32-element slabs along M/N, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// byte offset of 32-byte piece j (0..3) of row r inside a SWIZZLE_128B_BASE32B slab of 128-byte rows
+__device__ __forceinline__ uint32_t sw128b32_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 3)) << 5)); }
 __device__ __forceinline__ uint64_t kdesc(uint32_t smem_addr) { return smem_desc_sw128(smem_addr, 16, 1024); }
 
 // D[tmem] (+)= A[smem] * B[smem]
@@ -235,6 +249,12 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // ---------------------------------------------------------------------------------------- host: tensor maps
 // fp32 tensor maps with SWIZZLE_128B.  rank 2: dims {cols, rows}, row pitch ld floats, box {box_cols (<= 32), box_rows}.
 // rank 3 ("slab" maps for MN-major operands): dims {32, rows, cols/32} with strides {ld, 32} floats and box
-// {32, box_rows, slabs}: shared memory receives [slab][row][32 floats], the MN-major SWIZZLE_128B canonical layout.
+// {32, box_rows, slabs}: shared memory receives [slab][row][32 floats] in the MN-major canonical layout of tf32 operands
+// (SWIZZLE_128B_BASE32B: 32-byte pieces XOR row & 3).
 int sard_tmap_2d(CUtensorMap* out, const float* base, long long rows, long long cols, long long ld, int box_rows, int box_cols);
 int sard_tmap_slab(CUtensorMap* out, const float* base, long long rows, long long cols, long long ld, int box_rows, int slabs);
+
+// scratch layout of the fused JSMLP kernels (floats): pair copies of the live weight slabs, forward (whl) and
+// transposed (wthl), and of the sorted input rows
+struct JsLayout { int outp[3], kp[3]; long long whl[3], wthl[3], xs_hl, total; };
+JsLayout sard_js_layout(int n, int in_dim, int out_dim, int n_slots);
