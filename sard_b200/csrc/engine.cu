@@ -505,7 +505,10 @@ struct StageBufs {
   float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2;
   int max_tiles, max_chunks;
   bool tc;                       // fused tcgen05 JSMLP (jsmlp_tc.cu)
+  bool tcb;                      // ... in the padded row space, with the fused backward (jsmlp_tc_bwd.cu)
+  int rows_cap;                  // sorted positions (padded: every body index starts on a 128-row tile boundary)
   float* tcws; long long tcws_floats; float* Hhl[2];
+  float* dOs_hl; float* dZhl[2]; float* tc_partials;
 };
 
 // the fused tensor-core JSMLP serves engine 4 (the default) when the stage's shapes are covered
@@ -517,7 +520,7 @@ bool stage_uses_tc(const SardPolicyStage& s) {
 SardJsmlpTc jsmlp_tc_args(const SardPolicyStage& s, const StageBufs& sb, int n, bool bwd) {
   SardJsmlpTc a;
   memset(&a, 0, sizeof(a));
-  a.n = n; a.in_dim = s.il[0].in; a.hid = s.il[0].out; a.out_dim = s.out_dim; a.act = s.il_act; a.post = s.post;
+  a.n = sb.tcb ? sb.rows_cap : n; a.padded = sb.tcb ? 1 : 0; a.in_dim = s.il[0].in; a.hid = s.il[0].out; a.out_dim = s.out_dim; a.act = s.il_act; a.post = s.post;
   a.max_index = s.max_index; a.n_slots = s.n_live;
   a.xs = sb.xs; a.ld_xs = sb.ldxs;
   for (int j = 0; j < 3; ++j) { a.W[j] = s.il[j].W; a.b[j] = s.il[j].b; }
@@ -525,8 +528,8 @@ SardJsmlpTc jsmlp_tc_args(const SardPolicyStage& s, const StageBufs& sb, int n, 
   a.tiles = sb.tiles; a.num_tiles = sb.counts; a.max_tiles = sb.max_tiles;
   a.srow = sb.srow;
   // the hidden activations only leave the SM when a backward pass follows
-  a.H[0] = bwd ? sb.H[0] : nullptr; a.H[1] = bwd ? sb.H[1] : nullptr; a.ldh = s.il[0].out;
-  a.Hhl[0] = nullptr; a.Hhl[1] = nullptr;
+  a.H[0] = bwd && !sb.tcb ? sb.H[0] : nullptr; a.H[1] = bwd && !sb.tcb ? sb.H[1] : nullptr; a.ldh = s.il[0].out;
+  a.Hhl[0] = bwd && sb.tcb ? sb.Hhl[0] : nullptr; a.Hhl[1] = bwd && sb.tcb ? sb.Hhl[1] : nullptr;
   a.out = sb.out; a.pre = s.post != SARD_POST_NONE ? sb.pre : nullptr; a.ldo = sb.ldo;
   a.ws = sb.tcws; a.ws_floats = sb.tcws_floats;
   return a;
@@ -539,37 +542,47 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
   sb.ext = b.f((long long)B * 3 * SARD_EXT_DIM);
   // every present body index adds at most one partial tile / chunk
   const int live = s.n_live > 0 && s.n_live < s.max_index ? s.n_live : s.max_index;
-  sb.max_tiles = n / IL_TILE + live;
+  sb.tc = stage_uses_tc(s);
+  sb.tcb = sb.tc && WG_CHUNK % IL_TILE == 0 &&
+           sard_jsmlp_tc_bwd_supported(s.il[0].in, s.il[0].out, s.il[1].out, s.out_dim, s.n_il);
+  sb.rows_cap = sb.tcb ? (n + IL_TILE - 1) / IL_TILE * IL_TILE + live * IL_TILE : n;
+  sb.max_tiles = sb.tcb ? sb.rows_cap / IL_TILE : n / IL_TILE + live;
   sb.max_chunks = n / WG_CHUNK + live;
-  sb.srow = b.i(n); sb.spos = b.i(n); sb.grp_ptr = b.i(s.max_index + 1);
+  sb.srow = b.i(sb.rows_cap); sb.spos = b.i(n); sb.grp_ptr = b.i(s.max_index + 1);
   sb.tiles = b.i(4LL * sb.max_tiles); sb.chunks = b.i(4LL * sb.max_chunks);
   sb.grp_chunk_ptr = b.i(s.max_index + 1); sb.counts = b.i(4);
   sb.sort_scratch = b.i((long long)(ceil_div(n > 0 ? n : 1, 256) + 2) * s.max_index);
   const int hL = s.tower.h[s.tower.L];
   sb.ldxs = hL + 3 * SARD_EXT_DIM;
-  sb.xs = b.f((long long)n * sb.ldxs);
+  sb.xs = sb.tcb ? nullptr : b.f((long long)n * sb.ldxs);
   int maxo = 4;
-  for (int j = 0; j < s.n_il - 1; ++j) { sb.H[j] = b.f((long long)n * s.il[j].out); maxo = s.il[j].out > maxo ? s.il[j].out : maxo; }
+  for (int j = 0; j < s.n_il - 1; ++j) { sb.H[j] = sb.tcb ? nullptr : b.f((long long)n * s.il[j].out); maxo = s.il[j].out > maxo ? s.il[j].out : maxo; }
   sb.ldo = r4(s.out_dim);
   sb.out = b.f((long long)n * sb.ldo);
   sb.pre = b.f((long long)n * sb.ldo);
-  sb.tc = stage_uses_tc(s);
   sb.tcws = nullptr; sb.tcws_floats = 0; sb.Hhl[0] = sb.Hhl[1] = nullptr;
+  sb.dOs_hl = sb.dZhl[0] = sb.dZhl[1] = sb.tc_partials = nullptr;
   if (sb.tc) {
-    sb.tcws_floats = sard_jsmlp_tc_workspace(n, s.il[0].in, s.out_dim, s.n_live);
+    sb.tcws_floats = sard_jsmlp_tc_workspace(sb.rows_cap, s.il[0].in, s.out_dim, s.n_live);
     sb.tcws = b.a256(sb.tcws_floats);
-    if (train) for (int j = 0; j < 2; ++j) sb.Hhl[j] = b.a256((long long)n * 2 * s.il[j].out);
+    if (train && sb.tcb) {
+      for (int j = 0; j < 2; ++j) sb.Hhl[j] = b.a256((long long)sb.rows_cap * 2 * s.il[j].out);
+      for (int j = 0; j < 2; ++j) sb.dZhl[j] = b.a256((long long)sb.rows_cap * 2 * s.il[j].out);
+      sb.dOs_hl = b.a256((long long)sb.rows_cap * 64);
+      sb.tc_partials = b.a256(sard_jsmlp_tc_partials_floats(sb.max_chunks));
+    }
   }
   if (train) {
     sb.dout = b.f((long long)n * sb.ldo);
     sb.gstat = b.f((long long)B * (4 + s.out_dim));
-    for (int j = 0; j < s.n_il; ++j) sb.dH[j] = j > 0 ? b.f((long long)n * s.il[j - 1].out) : nullptr;
-    sb.dxs = b.f((long long)n * sb.ldxs);
+    for (int j = 0; j < s.n_il; ++j) sb.dH[j] = j > 0 && !sb.tcb ? b.f((long long)n * s.il[j - 1].out) : nullptr;
+    sb.dxs = sb.tcb ? b.a256((long long)sb.rows_cap * sb.ldxs) : b.f((long long)n * sb.ldxs);
     sb.dext = b.f((long long)B * 3 * SARD_EXT_DIM);
     sb.de1 = b.f((long long)B * SARD_EXT_DIM);
     sb.wg = b.f(tower_wg_need(s.tower, n));                 // side stream 0
     long long need = enc_wg_need(net.enc, B), v;            // side stream 1
-    for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * SARD_WG_LDPART(s.il[j].in); need = v > need ? v : need; }
+    if (!sb.tcb)
+      for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * SARD_WG_LDPART(s.il[j].in); need = v > need ? v : need; }
     sb.wg2 = b.f(need);
   } else {
     sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = sb.wg2 = nullptr;
@@ -622,8 +635,8 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   {
     sard_stream_t s2 = wg_stream(side, st, 1);
     SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, s2));
-    SARD_TRY(sard_sort_by_index(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.srow, sb.spos, sb.grp_ptr, sb.tiles,
-                                sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
+    SARD_TRY(sard_sort_by_index_padded(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.tcb ? sb.rows_cap : 0, sb.srow, sb.spos,
+                                       sb.grp_ptr, sb.tiles, sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
     if (sb.tc) {                   // hi/lo pair copies of the live weight slabs (they change with every optimiser step)
       const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
       SARD_TRY(sard_jsmlp_tc_presplit(&a, s2));
@@ -632,10 +645,20 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   SARD_TRY(tower_forward(tw, P, arena, sel, sb.t, st));
   SARD_TRY(side_join(side));
   const int hL = tw.h[tw.L];
-  SARD_TRY(sard_concat_sorted(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph, n,
-                              sb.xs, sb.ldxs, st));
   SARD_REQUIRE(s.il[0].in == sb.ldxs, "first index-linear input width");
-  if (sb.tc) {
+  if (sb.tcb) {
+    // cat + repeat_interleave written straight into the fused kernels' operand format (sorted, padded, hi | lo)
+    const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
+    SARD_TRY(sard_concat_sorted_split(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph,
+                                      sb.rows_cap, sard_jsmlp_tc_xs_hl(&a), st));
+    site(K_IL, 0);
+    SARD_TRY(sard_jsmlp_tc_forward(&a, st));
+  } else {
+    SARD_TRY(sard_concat_sorted(sb.t.hout, hL, hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM, sb.srow, sb.t.nd_graph, n,
+                                sb.xs, sb.ldxs, st));
+  }
+  if (sb.tcb) {
+  } else if (sb.tc) {
     // the three IndexLinear layers in one tcgen05 launch (jsmlp_tc.cu)
     const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
     SARD_TRY(sard_jsmlp_tc_split_input(&a, st));
@@ -686,6 +709,21 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
 
   // ---- backward through the JSMLP (sorted row space) ----
   const float* dz = sb.dout; int ldz = sb.ldo; const int* dz_rows = sb.srow;
+  if (sb.tcb) {
+    // dZ2, dZ1, dX in one tcgen05 launch; the weight gradients of the three tables in one more (+ ordered reduction)
+    const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
+    SardJsmlpTcBwd bb;
+    memset(&bb, 0, sizeof(bb));
+    bb.dout = sb.dout; bb.ld_dout = sb.ldo; bb.dOs_hl = sb.dOs_hl; bb.dZhl[0] = sb.dZhl[0]; bb.dZhl[1] = sb.dZhl[1];
+    bb.dxs = sb.dxs; bb.ld_dxs = sb.ldxs;
+    bb.chunks = sb.chunks; bb.num_chunks = sb.counts + 1; bb.max_chunks = sb.max_chunks; bb.grp_chunk_ptr = sb.grp_chunk_ptr;
+    bb.partials = sb.tc_partials;
+    for (int j = 0; j < 3; ++j) { bb.gW[j] = s.GT + s.il[j].gW; bb.gb[j] = s.GT + s.il[j].gb; }
+    site(K_IL, 1);
+    SARD_TRY(sard_jsmlp_tc_backward(&a, &bb, st));
+    site(K_IL, 2);
+    SARD_TRY(sard_jsmlp_tc_wgrad(&a, &bb, wg_stream(side, st, 1)));
+  } else
   for (int j = s.n_il - 1; j >= 0; --j) {
     const float* Aj = j == 0 ? sb.xs : sb.H[j - 1];
     const int lda = j == 0 ? sb.ldxs : s.il[j - 1].out;
