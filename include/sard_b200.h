@@ -113,6 +113,7 @@ typedef struct SardArena {
   float* returns;              /* [T] */
   float* advantages;           /* [T] */
   float* fixed_log_probs;      /* [T] (agent :316-325) */
+  int max_nodes;               /* largest graph of the arena (0 = unknown: the fused tower kernels are not used) */
 } SardArena;
 
 /* A run of graphs of the current ordering (one minibatch, or one stage of it). */

@@ -24,7 +24,7 @@ class SardArena(C.Structure):
                 ('obs', vp), ('actions', vp), ('node_ptr', vp), ('stage', vp), ('body_ind', vp),
                 ('in_ptr', vp), ('in_nbr', vp), ('out_ptr', vp), ('out_nbr', vp), ('rep_local', vp),
                 ('ext', vp * 3), ('ext_dim', ci * 3),
-                ('values', vp), ('returns', vp), ('advantages', vp), ('fixed_log_probs', vp)]
+                ('values', vp), ('returns', vp), ('advantages', vp), ('fixed_log_probs', vp), ('max_nodes', ci)]
 
 
 class SardSel(C.Structure):

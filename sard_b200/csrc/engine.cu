@@ -8,6 +8,7 @@
 // the GATHER and COMPUTE phases of a data-parallel step can be separate calls.
 #include "common.cuh"
 #include "encoder.cuh"
+#include "tower_tc.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
@@ -15,6 +16,7 @@
 
 int g_sard_wgrad_overlap = 1;
 extern int g_sard_gemm_engine;
+static const int g_sard_tower_tc = getenv("SARD_TOWER_TC") ? atoi(getenv("SARD_TOWER_TC")) : 1;   // fused tcgen05 tower (tower_tc.cu)
 static const int g_sard_fuse_agg = getenv("SARD_FUSE_AGG") ? atoi(getenv("SARD_FUSE_AGG")) : 1;   // GraphConv neighbour sum inside the GEMM loader
 extern "C" int sard_set_wgrad_overlap(int enabled) { g_sard_wgrad_overlap = enabled ? 1 : 0; return 0; }
 extern "C" int sard_get_wgrad_overlap(void) { return g_sard_wgrad_overlap; }
@@ -134,7 +136,20 @@ struct TowerBufs {
   float* hout;
   float *dz[SARD_MAX_LAYERS + 1], *dxa;      // dz[l]: gradient w.r.t. the pre-activation of layer l (0 = in_fc)
   int maxh;
+  bool tc_shape;                // widths served by the fused tensor-core tower: its scratch is carved
+  bool tc_on;                   // ... and this run's graphs are small enough (set per run from arena->max_nodes)
+  TowerTcBufs tc;
 };
+
+// the fused tower serves the default engine when the widths fit (every layer 64 wide, D <= 127, <= 3 layers)
+bool tower_tc_shape(const SardTower& tw) { return g_sard_tower_tc && g_sard_gemm_engine == 4 && sard_tower_tc_supported(tw, 1); }
+// per run: graphs must fit whole into a 128-row tile with room to pack (max_nodes <= 64)
+void tower_tc_select(TowerBufs& t, const SardTower& tw, const SardArena* arena, int n) {
+  t.tc_on = t.tc_shape && sard_tower_tc_supported(tw, arena->max_nodes);
+  if (!t.tc_on) return;
+  t.tc.span = sard_tower_tc_span(arena->max_nodes);
+  t.tc.num_tiles = ceil_div(n, t.tc.span);
+}
 
 void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBufs& t) {
   t.ldx = r4(tw.D);
@@ -151,6 +166,27 @@ void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBu
   } else {
     for (int l = 0; l <= tw.L; ++l) t.dz[l] = nullptr;
     t.dxa = nullptr;
+  }
+  t.tc_shape = tower_tc_shape(tw);
+  t.tc_on = false;
+  memset(&t.tc, 0, sizeof(t.tc));
+  if (t.tc_shape) {
+    const int nn = n > 0 ? n : 1;
+    t.tc.wsplit = b.a256(sard_tower_tc_wsplit_floats(tw.L));
+    t.tc.tile_first = b.i(ceil_div(nn, sard_tower_tc_span(TT_MAX_NODES)) + 2);
+    t.tc.tab_in = reinterpret_cast<unsigned long long*>(b.a256(2LL * nn));
+    t.tc.tab_out = reinterpret_cast<unsigned long long*>(b.a256(2LL * nn));
+    t.tc.chunk_rows = sard_tower_tc_chunk_rows(nn);
+    t.tc.num_chunks = ceil_div(nn, t.tc.chunk_rows);
+    if (train) {
+      t.tc.XH = b.a256((long long)nn * 256);
+      for (int l = 0; l < tw.L; ++l) {
+        t.tc.PH[l] = b.a256((long long)nn * 128); t.tc.PA[l] = b.a256((long long)nn * 256);
+        t.tc.mask[l] = reinterpret_cast<unsigned*>(b.a256(2LL * nn));
+      }
+      t.tc.PZ0 = b.a256((long long)nn * 128);
+      t.tc.partials = b.a256(sard_tower_tc_partials_floats(t.tc.num_chunks));
+    }
   }
 }
 
@@ -172,13 +208,23 @@ int tower_gather(const SardTower& tw, const SardArena* arena, const SardSel* sel
   o.lead = lead; o.tail = tail; o.nconst = nconst; o.onehot = onehot; o.consts = consts;
   o.x = t.x; o.ldx = t.ldx; o.nd_graph = t.nd_graph; o.nd_arena = t.nd_arena; o.body = t.body; o.root_row = t.root_row;
   SARD_REQUIRE(lead + tail + nconst + (onehot ? 3 : 0) == tw.D, "tower input width != column program");
-  return sard_gather_nodes(arena, sel, &o, st);
+  SARD_TRY(sard_gather_nodes(arena, sel, &o, st));
+  tower_tc_select(t, tw, arena, sel->n);
+  if (t.tc_on) SARD_TRY(sard_tower_tc_tiles(arena, sel, t.tc, t.nd_graph, t.nd_arena, st));
+  return 0;
 }
 
 // normalise + in_fc + GraphConv layers
 int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, const SardSel* sel, TowerBufs& t,
                   sard_stream_t st) {
   const int n = sel->n;
+  tower_tc_select(t, tw, arena, n);
+  if (t.tc_on) {
+    // normalise + in_fc + every GraphConv layer in one tcgen05 launch (tower_tc.cu); t.x stays un-normalised
+    SARD_TRY(sard_tower_tc_presplit(tw, P, t.tc.wsplit, st));
+    site(K_GCONV, 0);
+    return sard_tower_tc_forward(tw, P, arena, sel, t.tc, t.x, t.ldx, t.nd_graph, t.nd_arena, t.hout, t.dz[tw.L] != nullptr, st);
+  }
   SARD_TRY(sard_norm_apply(t.x, t.ldx, n, tw.D, tw.mean, tw.inv, tw.count, 5.0f, st));
   {
     SardGemm g = gemm0();
@@ -217,6 +263,14 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
 int tower_backward(const SardTower& tw, const float* P, float* G, const SardArena* arena, const SardSel* sel,
                    TowerBufs& t, float* wg_scratch, SideCtx* side, sard_stream_t st) {
   const int n = sel->n;
+  if (t.tc_on) {
+    (void)P; (void)wg_scratch;
+    site(K_GCONV, 1);
+    SARD_TRY(sard_tower_tc_backward(tw, arena, sel, t.tc, t.dz[tw.L], t.nd_graph, t.nd_arena, st));
+    site(K_GCONV, 2);
+    SARD_TRY(sard_tower_tc_wgrad(tw, sel, t.tc, G, wg_stream(side, st, 0)));
+    return side_join(side);
+  }
   for (int l = tw.L; l >= 1; --l) {
     const int hi = tw.h[l - 1], ho = tw.h[l];
     float* dz = t.dz[l];

@@ -35,6 +35,13 @@ class Comm:
     def allreduce(self, t: torch.Tensor):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def min_int(self, v: int, device=None) -> int:
+        """Minimum of a host integer over the ranks (one small collective; host-synchronous)."""
+        dev = device if device is not None else ('cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu')
+        t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(t.item())
+
 
 class _EngineBase:
     def __init__(self, module):

@@ -160,6 +160,7 @@ class PackedRollout:
             a.ext_dim[k] = int(self.ext[k].shape[1])
         a.values, a.returns = ptr(self.values), ptr(self.returns)
         a.advantages, a.fixed_log_probs = ptr(self.advantages), ptr(self.fixed_log_probs)
+        a.max_nodes = int(self.num_nodes_np.max()) if self.T > 0 else 0
         return a
 
     def set_orbits(self, leg_rep: np.ndarray, index_base: int, verify: bool = True):
@@ -233,14 +234,17 @@ class EpochPlan:
     inside the minibatch (the split its ``forward`` does at policy.py:216-231).
     """
 
-    def __init__(self, arena: PackedRollout, perm: np.ndarray, mini_batch_size: int, batch_design: bool):
+    def __init__(self, arena: PackedRollout, perm: np.ndarray, mini_batch_size: int, batch_design: bool,
+                 n_mb: Optional[int] = None):
+        """``n_mb`` caps the number of minibatches (data parallel: the minimum over ranks, so that every rank issues
+        the same collectives when the rank-local rollouts differ in length)."""
         perm = np.asarray(perm, dtype=np.int64)
         if batch_design:
             perm = perm[stage_partition(arena.stage_np[perm])]
         self.perm = perm
         T = len(perm)
         self.M = int(mini_batch_size)
-        self.n_mb = T // self.M
+        self.n_mb = T // self.M if n_mb is None else min(int(n_mb), T // self.M)
         self.value_order = Ordering(arena, perm)
         st = arena.stage_np[perm]
         used = self.n_mb * self.M

@@ -390,6 +390,12 @@ class Transform2ActAgent:
         M = self.mini_batch_size if self.use_mini_batch else T
         batch_design = bool(self.cfg.agent_specs.get('batch_design', False))
         n_mb = T // M
+        if world > 1:
+            # rollouts end on episode boundaries, so T differs between ranks: every rank must run the same number of
+            # minibatch steps (= collectives); the ranks with a longer rollout drop their surplus minibatches
+            n_mb = comm.min_int(n_mb)
+            if n_mb <= 0:
+                raise ValueError('data-parallel update: a rank holds fewer transitions than one minibatch')
         n_steps = self.opt_num_epochs * n_mb
         plans_alive = []
         plog = torch.zeros(max(n_steps, 1), 8, dtype=torch.float32, device=self.device)
@@ -409,7 +415,7 @@ class Transform2ActAgent:
             # like the reference, each epoch permutes the already permuted lists (agent :331-342)
             p = perms[ep] if perms is not None else self.draw_perm(T)
             cur_perm = cur_perm[p]
-            plan = EpochPlan(arena, cur_perm, M, batch_design)
+            plan = EpochPlan(arena, cur_perm, M, batch_design, n_mb=n_mb)
             cur_perm = plan.perm
             h2d += plan.h2d_bytes
             sv.wait_stream(main); sp.wait_stream(main)       # the ordering upload happened on the main stream

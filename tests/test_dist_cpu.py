@@ -62,6 +62,19 @@ def _worker(rank, world, port, out):
             if r is not None:
                 assert np.all(st[r.lo - k * 64:r.hi - k * 64] == s)
                 assert r.n == int(local_counts[k, 3 + s])
+    # 4. unequal rollout lengths (rollouts end on episode boundaries): T // M differs between the ranks, every rank
+    #    must plan the same number of minibatch steps = the same sequence of collectives (the minimum)
+    T_r = 400 + 70 * rank                                   # 6 vs 7 minibatches of 64
+    roll2 = synthetic.generate_rollout(synthetic.ENV_SHAPES['point_nav'], T_r, seed=300 + rank, min_exec=5, max_exec=40)
+    arena2 = HostArena(roll2)
+    n_mb = comm.min_int(arena2.T // 64)
+    assert n_mb == 6
+    perm2 = np.random.default_rng(rank).permutation(arena2.T)
+    plan2 = EpochPlan(arena2, perm2, 64, batch_design=True, n_mb=n_mb)
+    assert plan2.n_mb == 6 and plan2.stage_graphs.shape == (6, 3)
+    c2 = torch.from_numpy(np.concatenate([plan2.stage_graphs, plan2.stage_nodes], axis=1))
+    comm.allreduce(c2)                                      # same shape on every rank: no hang, no corruption
+    assert np.all(c2[:, :3].sum(1).numpy() == 64 * world)
     out.put((rank, perm[:8].tolist(), counts.numpy().tolist()))
     dist.barrier()
     dist.destroy_process_group()
