@@ -167,7 +167,7 @@ extern "C" int sard_tc_debug_read(long long* out, int n) {
 
 __global__ void __launch_bounds__(JS_THREADS, 1) jsmlp_fwd_tc_kernel(const __grid_constant__ JsFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = tc::align1024(smem_raw);
   __shared__ uint64_t bar_full[JS_STAGES], bar_empty[JS_STAGES], bar_d[3], bar_a[2][4];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

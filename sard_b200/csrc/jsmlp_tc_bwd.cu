@@ -100,7 +100,7 @@ struct JsBwdParams {
 
 __global__ void __launch_bounds__(JB_THREADS, 1) jsmlp_bwd_tc_kernel(const __grid_constant__ JsBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = tc::align1024(smem_raw);
   __shared__ uint64_t bar_full[JB_STAGES], bar_empty[JB_STAGES], bar_d[3], bar_a[2][4];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -335,7 +335,7 @@ extern "C" int sard_jw_debug_read(float* out, int n) {
 }
 __global__ void __launch_bounds__(JW_THREADS, 1) jsmlp_wgrad_tc_kernel(const __grid_constant__ JsWgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = tc::align1024(smem_raw);
   uint8_t* ones = base + JW_STAGES * JW_STAGE_BYTES;             // 1 KB of 1.0f: an all-ones operand atom
   __shared__ uint64_t bar_full[JW_STAGES], bar_empty[JW_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -579,7 +579,7 @@ extern "C" int sard_jsmlp_tc_wgrad(const SardJsmlpTc* a, const SardJsmlpTcBwd* b
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
                                                             int N, int a_mn, int b_mn, uint32_t lbo, uint32_t sbo) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = tc::align1024(smem_raw);
   uint8_t* sA = base;                 // 16 KB
   uint8_t* sB = base + 16384;         // 32 KB
   __shared__ uint64_t bar;

@@ -17,6 +17,10 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// first 1024-byte boundary of the dynamic shared memory, computed as pointer + offset so that the compiler keeps the
+// shared state space (LDS / STS instead of generic loads and stores)
+__device__ __forceinline__ uint8_t* align1024(uint8_t* smem) { return smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u); }
+
 // ---------------------------------------------------------------------------------------- split
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
@@ -56,10 +60,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // the thread is suspended up to %3 ns per try
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return;
     if ((spin & 0x3ff) == 0x3ff) {

@@ -99,9 +99,9 @@ bool sard_tower_tc_supported(const SardTower& tw, int max_nodes) {
   return true;
 }
 
-__device__ long long g_tt_dbg[32];
+__device__ long long g_tt_dbg[96];
 extern "C" int sard_tt_debug_read(long long* out, int n) {
-  SARD_CUDA(cudaMemcpyFromSymbol(out, g_tt_dbg, sizeof(long long) * (n < 32 ? n : 32)));
+  SARD_CUDA(cudaMemcpyFromSymbol(out, g_tt_dbg, sizeof(long long) * (n < 96 ? n : 96)));
   return 0;
 }
 #define TT_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_tt_dbg[i] = clock64(); } while (0)
@@ -256,7 +256,7 @@ struct TfParams {
 
 __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const __grid_constant__ TfParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = tc::align1024(smem_raw);
   uint8_t* S = sW + TT_WBYTES;
   __shared__ uint64_t bar_wfull, bar_wfree, bar_mma, bar_a, bar_half;
   __shared__ uint32_t tmem_slot;
@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     }
   } else {
     RowCtx c;
+    TT_STAMP(32);
     row_setup(c, S, warp, lane, row_lo, nrows, p.tab, p.nd_graph, p.nd_arena, p.cum, p.node_base, p.nptr);
     const bool normalise = *p.count > 0;
     const long long r = row_lo + c.trow;
@@ -377,8 +378,10 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     }
     // ---- in_fc epilogue: h_0 = x W^T + b (no activation)
     int mm = 0;
+    TT_STAMP(33);
     tc::mbar_wait(&bar_mma, mm & 1); ++mm;
     tc::tc_fence_after();
+    TT_STAMP(34);
     tc::tmem_ld32(DD + c.lane_off + c.c0, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += __ldg(p.b_in + c.c0 + j);
@@ -394,8 +397,10 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     // ---- GraphConv layers
 #pragma unroll 1
     for (int l = 1; l <= p.L; ++l) {
+      TT_STAMP(35 + 5 * (l - 1));
       tc::mbar_wait(&bar_mma, mm & 1); ++mm;
       tc::tc_fence_after();
+      TT_STAMP(36 + 5 * (l - 1));
       tc::tmem_ld32(DD + c.lane_off + c.c0, v);          // (x W_l^T) of this row: to be summed over the neighbours
       stage_write(S, c, v);
       tc::tmem_ld32(DD + c.lane_off + 64 + c.c0, v);     // x W_r^T
@@ -404,8 +409,10 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bl[l - 1] + c.c0 + j);
       }
+      TT_STAMP(37 + 5 * (l - 1));
       stage_gather(S, c, p.nnbr, v);
       act32(v, p.act);
+      TT_STAMP(38 + 5 * (l - 1));
       if (l < p.L) {
         tmem_put32(tmem, c, v);
         tc::tc_fence_before();
@@ -418,6 +425,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
         }
       }
       tc::named_sync(2, 256);                             // every gather is done: the own region is private again
+      TT_STAMP(39 + 5 * (l - 1));
       if (l < p.L ? p.PH[l] != nullptr : true) {
         own_write(c, v);
         __syncwarp();
@@ -427,6 +435,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
       }
     }
   }
+  TT_STAMP(50);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, 256);
@@ -446,7 +455,7 @@ struct TbParams {
 
 __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const __grid_constant__ TbParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = tc::align1024(smem_raw);
   uint8_t* S = sW + TT_WBYTES;
   __shared__ uint64_t bar_wfull, bar_wfree, bar_mma, bar_a;
   __shared__ uint32_t tmem_slot;
@@ -596,7 +605,7 @@ struct TwParams {
 
 __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __grid_constant__ TwParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = tc::align1024(smem_raw);
   uint8_t* ones = base + TWG_STAGES * TWG_STAGE_BYTES;
   __shared__ uint64_t bar_full[TWG_STAGES], bar_empty[TWG_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -613,7 +622,9 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  TT_STAMP(64);
   pdl_sync();
+  TT_STAMP(65);
 
   const int row_start = blockIdx.x * p.chunk_rows;
   const int row_end = min(p.n, row_start + p.chunk_rows);
@@ -667,8 +678,10 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float* dst = p.partials + ((size_t)blockIdx.x * 128 + q * 32 + lane) * TWG_COLS + half * 224;
+    TT_STAMP(66);
     tc::mbar_wait(&bar_done, 0);
     tc::tc_fence_after();
+    TT_STAMP(67);
 #pragma unroll 1
     for (int c = 0; c < 14; ++c) {
       float v[16];
@@ -678,6 +691,7 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
         *reinterpret_cast<float4*>(dst + c * 16 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
+  TT_STAMP(68);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
