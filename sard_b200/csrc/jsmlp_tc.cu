@@ -71,29 +71,40 @@ int sard_tmap_slab(CUtensorMap* out, const float* base, long long rows, long lon
 //   Whl [slot][outp][hi(in) | lo(in)]     forward B operand  (K-major: k = in);   rows >= out are zero
 //   Wthl[slot][in  ][hi(kp) | lo(kp)]     backward-data B operand (K-major: k = out); k >= out is zero
 // One block per (body index, 64-element stripe); indices without a slot are skipped.
-__global__ void __launch_bounds__(256) jsmlp_presplit_kernel(const float* __restrict__ W, int out, int in, int outp, int kp,
-                                                             const int* __restrict__ slot_of_index,
-                                                             float* __restrict__ Whl, float* __restrict__ Wthl) {
+struct JsPresplitParams {
+  const float* W[3]; int out[3], in[3], outp[3], kp[3];
+  const int* slot_of_index; int max_index;
+  float* Whl[3]; float* Wthl[3];
+};
+// One block per (stripe, slot, table): the body index of the slot is found by scanning slot_of_index.
+__global__ void __launch_bounds__(256) jsmlp_presplit_kernel(const __grid_constant__ JsPresplitParams p) {
   pdl_sync();
-  const int u = blockIdx.y;
-  const int slot = slot_of_index[u];
-  if (slot < 0) return;
-  const float* Wu = W + (size_t)u * out * in;
-  float* F = Whl + (size_t)slot * outp * 2 * in;
-  float* T = Wthl ? Wthl + (size_t)slot * in * 2 * kp : nullptr;
+  __shared__ int s_u;
+  const int slot = blockIdx.y, j = blockIdx.z;
+  if (threadIdx.x == 0) s_u = -1;
+  __syncthreads();
+  for (int u = threadIdx.x; u < p.max_index; u += blockDim.x)
+    if (p.slot_of_index[u] == slot) s_u = u;
+  __syncthreads();
+  const int u = s_u;
+  if (u < 0) return;
+  const int out = p.out[j], in = p.in[j], outp = p.outp[j], kp = p.kp[j];
+  const float* Wu = p.W[j] + (size_t)u * out * in;
+  float* F = p.Whl[j] + (size_t)slot * outp * 2 * in;
+  float* T = p.Wthl[j] + (size_t)slot * in * 2 * kp;
   const int total = outp * in;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int o = e / in, i = e - o * in;
-    const float v = o < out ? Wu[(size_t)o * in + i] : 0.f;
+    const float v = o < out ? __ldg(Wu + (size_t)o * in + i) : 0.f;
     const float h = tc::tf32_hi(v), l = v - h;
     F[(size_t)o * 2 * in + i] = h;
     F[(size_t)o * 2 * in + in + i] = l;
-    if (T && o < kp) {
+    if (o < kp) {
       T[(size_t)i * 2 * kp + o] = h;
       T[(size_t)i * 2 * kp + kp + o] = l;
     }
   }
-  if (T && kp > outp) {                    // zero the k padding beyond the padded rows
+  if (kp > outp) {                         // zero the k padding beyond the padded rows
     const int extra = (kp - outp) * in;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < extra; e += gridDim.x * blockDim.x) {
       const int o = outp + e / in, i = e % in;
@@ -432,12 +443,14 @@ extern "C" int sard_jsmlp_tc_presplit(const SardJsmlpTc* a, sard_stream_t stream
   SARD_REQUIRE((reinterpret_cast<uintptr_t>(a->ws) & 255) == 0, "jsmlp_tc: workspace must be 256-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int in[3] = {a->in_dim, JS_HID, JS_HID}, out[3] = {JS_HID, JS_HID, a->out_dim};
+  JsPresplitParams p;
   for (int j = 0; j < 3; ++j) {
-    dim3 grid(ceil_div((long long)L.outp[j] * in[j], 256 * 8), a->max_index);
-    sard_launch(jsmlp_presplit_kernel, grid, 256, 0, st, a->W[j], out[j], in[j], L.outp[j], L.kp[j], a->slot_of_index,
-                a->ws + L.whl[j], a->ws + L.wthl[j]);
-    SARD_LAUNCH_OK("jsmlp_presplit_kernel");
+    p.W[j] = a->W[j]; p.out[j] = out[j]; p.in[j] = in[j]; p.outp[j] = L.outp[j]; p.kp[j] = L.kp[j];
+    p.Whl[j] = a->ws + L.whl[j]; p.Wthl[j] = a->ws + L.wthl[j];
   }
+  p.slot_of_index = a->slot_of_index; p.max_index = a->max_index;
+  sard_launch(jsmlp_presplit_kernel, dim3(8, a->n_slots, 3), 256, 0, st, p);
+  SARD_LAUNCH_OK("jsmlp_presplit_kernel");
   return 0;
 }
 

@@ -415,21 +415,17 @@ __global__ void __launch_bounds__(JW_THREADS, 1) jsmlp_wgrad_tc_kernel(const __g
         tc::mma_commit(&bar_done);
       }
     } else {
-      // ---- epilogue: thread <-> accumulator row (TMEM lane); two warps per lane quarter, 240 columns each
+      // ---- epilogue: two warps per TMEM lane quarter, 32-column groups 0..7 / 8..14; the pipeline stages are idle by
+      //      now and serve as the warps' transpose scratch (coalesced partial rows)
       const int q = warp & 3, half = (warp - 2) >> 2;
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-      float* dst = p.partials + ((size_t)blockIdx.x * 128 + q * 32 + lane) * JW_COLS + half * 240;
+      uint8_t* scr = base + (warp - 2) * 4096;
+      float* dst = p.partials + ((size_t)blockIdx.x * 128 + q * 32) * JW_COLS;
       tc::mbar_wait(&bar_done, 0);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 15; ++c) {
-        float v[16];
-        tc::tmem_ld16(tmem + lane_off + half * 240 + c * 16, v);
-        if (blockIdx.x == 0 && q == 0 && lane == 0 && c == 0) { g_jw_dbg[30 + half * 4] = v[0]; g_jw_dbg[31 + half * 4] = v[1]; g_jw_dbg[40 + half] = 7.f; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(dst + c * 16 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
+      for (int g = half * 8; g < (half ? 15 : 8); ++g)
+        tc::tmem_block_to_global(tmem + lane_off + g * 32, scr, lane, dst + g * 32, JW_COLS);
     }
   }
   tc::tc_fence_before();

@@ -161,6 +161,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// One warp moves its 32 TMEM lanes x 32 columns (at taddr) to 32 global rows of `ld` floats starting at dst0: the block
+// is transposed through a 4 KB warp-private shared-memory scratch so that every store instruction writes four whole
+// 128-byte rows (a thread storing its own TMEM lane directly would touch 32 different rows per instruction).
+__device__ __forceinline__ void tmem_block_to_global(uint32_t taddr, uint8_t* scr, int lane, float* dst0, size_t ld) {
+  float v[32];
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(scr + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int pc = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int row = 4 * k + (lane >> 3);
+    *reinterpret_cast<float4*>(dst0 + (size_t)row * ld + pc * 4) = *reinterpret_cast<const float4*>(scr + row * 128 + ((pc ^ (row & 7)) << 4));
+  }
+  __syncwarp();
+}
 // named barrier among `threads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {

@@ -675,21 +675,18 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
       tc::mma_commit(&bar_done);
     }
   } else {
+    // two warps per TMEM lane quarter, seven 32-column groups each; the idle pipeline stages are the transpose scratch
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float* dst = p.partials + ((size_t)blockIdx.x * 128 + q * 32 + lane) * TWG_COLS + half * 224;
+    uint8_t* scr = base + (warp - 2) * 4096;
+    float* dst = p.partials + ((size_t)blockIdx.x * 128 + q * 32) * TWG_COLS;
     TT_STAMP(66);
     tc::mbar_wait(&bar_done, 0);
     tc::tc_fence_after();
     TT_STAMP(67);
 #pragma unroll 1
-    for (int c = 0; c < 14; ++c) {
-      float v[16];
-      tc::tmem_ld16(tmem + lane_off + half * 224 + c * 16, v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(dst + c * 16 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    for (int g = half * 7; g < half * 7 + 7; ++g)
+      tc::tmem_block_to_global(tmem + lane_off + g * 32, scr, lane, dst + g * 32, TWG_COLS);
   }
   TT_STAMP(68);
   tc::tc_fence_before();
