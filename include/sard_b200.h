@@ -71,6 +71,12 @@ int sard_prof_collect(double* rows, int n_sites);
 /* Raw timeline of the recorded launches: rows[i*4..] = {site, stream ordinal, start ms, end ms} relative to the
  * first record; returns the number of rows written (<= capacity).  Call before sard_prof_collect. */
 int sard_prof_timeline(double* rows, int capacity);
+/* Every launch of the library by kernel name (diagnostic: events around each launch suppress the programmatic
+ * overlap of consecutive kernels).  sard_prof_kernels_enable(capacity > 0) starts recording, (0) stops.
+ * sard_prof_kernels_collect: names = newline-separated kernel names in id order; rows[i*5..] = {name id, stream
+ * ordinal, start ms, end ms, algorithmic bytes (0 when the wrapper states none)}; returns the row count, clears. */
+int sard_prof_kernels_enable(int capacity);
+int sard_prof_kernels_collect(char* names, int names_len, double* rows, int capacity);
 
 /* =====================================================================================
  * Packing: graph indexing layouts (bit-exact integer work)
@@ -382,6 +388,12 @@ typedef struct {
 #define SARD_CTL_FLOATS 64
 #define SARD_CTL_INTS 32
 #define SARD_MAX_GROUPS 8
+/* OR into active_mask: zero_grad() semantics of torch < 2.0, the reference's pin (README.md:14, torch 1.8): gradients
+ * of a stage absent from a minibatch are zero TENSORS, not None, so once a parameter group has taken one applied step
+ * Adam keeps stepping it from momentum (g = 0, step counter advancing) on every later applied step.  Without the
+ * flag an absent group is skipped (torch >= 2.0, set_to_none=True).  State: ctl_i[2] = groups seen so far,
+ * ctl_i[3] = groups updated by the current step. */
+#define SARD_ADAM_STICKY (1 << 30)
 
 /* sumsq partials of g[n] (ordered two-stage reduction): out[0] = sum g^2.  scratch: float[1024]. */
 int sard_sqnorm(const float* g, long long n, float* scratch, float* out, sard_stream_t stream);

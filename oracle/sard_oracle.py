@@ -351,7 +351,8 @@ class OracleAgent:
 
     def __init__(self, policy_sd, value_sd, spec: Spec, *, gamma=0.995, tau=0.95, clip_epsilon=0.2,
                  policy_lr=5e-5, value_lr=3e-4, mini_batch_size=2048, opt_num_epochs=10,
-                 batch_design=True, policy_grad_clip=40.0, clip_first_step_only=True):
+                 batch_design=True, policy_grad_clip=40.0, clip_first_step_only=True,
+                 zero_grad_to_none=True):
         self.policy_sd, self.value_sd, self.spec = policy_sd, value_sd, spec
         self.gamma, self.tau, self.clip_epsilon = gamma, tau, clip_epsilon
         self.mini_batch_size, self.opt_num_epochs, self.batch_design = mini_batch_size, opt_num_epochs, batch_design
@@ -360,6 +361,9 @@ class OracleAgent:
         # which is exhausted by the first call: only the first policy step of a run is clipped
         # (agent_ppo.py:53-56).  Mirrored here; set False to clip every step.
         self.clip_first_step_only = clip_first_step_only
+        # torch >= 2.0 zero_grad() drops the gradients (a stage absent from a minibatch is skipped by Adam); the
+        # reference pins torch 1.8 (README.md:14) where they stay zero tensors: zero_grad_to_none=False restates that
+        self.zero_grad_to_none = zero_grad_to_none
         self._clip_calls = 0
         self.policy_params = [p for p in policy_sd.values() if p.requires_grad]
         self.value_params = [p for p in value_sd.values() if p.requires_grad]
@@ -379,7 +383,7 @@ class OracleAgent:
         loss, kl, valid = ppo_loss(lp, fixed_log_probs, advantages, self.clip_epsilon)
         log = {'surr_loss': float(loss), 'entropy': float(ent), 'approx_kl': kl}
         if valid:
-            self.optimizer_policy.zero_grad()
+            self.optimizer_policy.zero_grad(set_to_none=self.zero_grad_to_none)
             loss.backward()
             if not (self.clip_first_step_only and self._clip_calls > 0):
                 torch.nn.utils.clip_grad_norm_(self.policy_params, self.policy_grad_clip)

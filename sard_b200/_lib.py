@@ -15,6 +15,7 @@ ACT = {'none': 0, None: 0, 'relu': 1, 'tanh': 2, 'sigmoid': 3}
 POST_NONE, POST_SIN = 0, 1
 PHASE_GATHER, PHASE_COMPUTE, PHASE_ALL = 1, 2, 3
 CTL_FLOATS, CTL_INTS, MAX_GROUPS = 64, 32, 8
+ADAM_STICKY = 1 << 30        # SARD_ADAM_STICKY: zero_grad() keeps zero tensors (torch < 2.0 semantics)
 
 vp, ci, cll, cf, cd = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
@@ -128,6 +129,8 @@ _PROTOS = {
     'sard_prof_enable': (ci, [C.c_uint, ci]),
     'sard_prof_collect': (ci, [P(cd), ci]),
     'sard_prof_timeline': (ci, [P(cd), ci]),
+    'sard_prof_kernels_enable': (ci, [ci]),
+    'sard_prof_kernels_collect': (ci, [C.c_char_p, ci, P(cd), ci]),
     'sard_build_csr': (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     'sard_orbit_rep': (ci, [vp, vp, ci, vp, ci, vp, vp, vp]),
     'sard_gather_nodes': (ci, [P(SardArena), P(SardSel), P(SardGatherOut), vp]),

@@ -26,9 +26,18 @@ struct ProfScope {
       return sard_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
 
+// Per-kernel timing of EVERY launch (sard_prof_kernels_enable): events around each launch on its stream, keyed by the
+// name SARD_LAUNCH_OK reports; sard_prof_bytes() attaches the algorithmic bytes of the next launch (HBM-class kernels).
+extern int g_sard_prof_all;
+void sard_prof_pre(cudaStream_t st);
+void sard_prof_post(cudaStream_t st);
+void sard_prof_label(const char* name);
+void sard_prof_bytes(double bytes);
+
 #define SARD_LAUNCH_OK(name)                                                                 \
   do {                                                                                       \
     ++g_sard_launches;                                                                       \
+    if (g_sard_prof_all) sard_prof_label(name);                                              \
     cudaError_t e__ = cudaGetLastError();                                                    \
     if (e__ != cudaSuccess)                                                                  \
       return sard_set_error("launch %s failed: %s", name, cudaGetErrorString(e__));          \
@@ -61,7 +70,9 @@ static inline void sard_launch(void (*kernel)(P...), dim3 grid, dim3 block, size
   attr[0].val.programmaticStreamSerializationAllowed = g_sard_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (g_sard_prof_all) sard_prof_pre(st);
   cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);   // errors surface through SARD_LAUNCH_OK
+  if (g_sard_prof_all) sard_prof_post(st);
 }
 
 // cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) whether it was applied

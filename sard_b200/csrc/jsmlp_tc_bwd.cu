@@ -83,6 +83,7 @@ extern "C" int sard_concat_sorted_split(const float* h, int ld_h, int Fh, const 
                                         const int* nd_graph, int rows_cap, float* xs_hl, sard_stream_t stream) {
   if (rows_cap <= 0) return 0;
   SARD_REQUIRE(Fh % 4 == 0 && Fe % 4 == 0 && ld_h % 4 == 0 && ld_ext % 4 == 0, "concat_sorted_split: multiples of 4");
+  sard_prof_bytes(4.0 * rows_cap * (3.0 * (Fh + Fe) + 1.0));      // one row read, hi | lo pair row written
   sard_launch(concat_sorted_split_kernel, grid_for((long long)rows_cap * ((Fh + Fe) / 4), 256, 16), 256, 0, as_stream(stream), h, ld_h,
               Fh / 4, ext, ld_ext, Fe / 4, srow, nd_graph, rows_cap, xs_hl);
   SARD_LAUNCH_OK("concat_sorted_split_kernel");

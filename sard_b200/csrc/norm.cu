@@ -110,6 +110,7 @@ extern "C" int sard_norm_moments(const float* x, int ldx, int n, int D, float* p
     int threads = ((D + 31) / 32) * 32;
     if (threads > 256) threads = 256;
     dim3 block(threads, NORM_SUB);
+    sard_prof_bytes(4.0 * n * (double)D);
     sard_launch(norm_moments_kernel, nchunks, block, NORM_SUB * 3 * threads * sizeof(float), st, x, ldx, n, D, partials);
     SARD_LAUNCH_OK("norm_moments_kernel");
   }
@@ -192,6 +193,7 @@ __global__ void norm_apply_kernel(float* __restrict__ x, int ldx, int n, int D, 
 extern "C" int sard_norm_apply(float* x, int ldx, int n, int D, const float* mean, const float* inv,
                                const long long* count, float clip, sard_stream_t stream) {
   if (n <= 0) return 0;
+  sard_prof_bytes(8.0 * n * (double)D);
   sard_launch(norm_apply_kernel, grid_for((long long)n * D, 256), 256, 0, as_stream(stream), x, ldx, n, D, mean, inv, count, clip);
   SARD_LAUNCH_OK("norm_apply_kernel");
   return 0;

@@ -95,6 +95,16 @@ __global__ void adam_prepare_kernel(float* stats, float inv_B, float inv_world, 
   ctl_f[0] = scale;
   ctl_f[1] = (float)valid;
   ctl_i[0] = valid;
+  // SARD_ADAM_STICKY (zero_grad() that keeps zero tensors, torch < 2.0): a group that has once taken a valid step keeps
+  // stepping from its momentum with g = 0 on every later valid step, whether its stage is in the minibatch or not.
+  // ctl_i[2] = groups seen so far, ctl_i[3] = the groups adam_apply_kernel updates in this step.
+  if (active_mask & SARD_ADAM_STICKY) {
+    active_mask &= ~SARD_ADAM_STICKY;
+    const int seen = ctl_i[2];
+    if (valid) ctl_i[2] = seen | active_mask;
+    active_mask |= seen;
+    ctl_i[3] = active_mask;
+  }
   for (int g = 0; g < SARD_MAX_GROUPS; ++g) {
     if (!((active_mask >> g) & 1)) continue;
     int step = ctl_i[8 + g];
@@ -128,6 +138,7 @@ __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr
                                   int zero_grads) {
   pdl_sync();
   const SardAdamSeg s = segs[blockIdx.y];
+  if (active_mask & SARD_ADAM_STICKY) active_mask = ctl_i[3];
   if (ctl_i[0] == 0 || !((active_mask >> s.group) & 1)) {
     if (zero_grads) {
       float* g = const_cast<float*>(s.g);
@@ -200,6 +211,7 @@ extern "C" int sard_adam_update(float* stats, float inv_B, float inv_world, floa
     nb = (int)((n_sq + 1023) / 1024);
     if (nb > SQ_BLOCKS) nb = SQ_BLOCKS;
     if (nb < 2) nb = 2;                              // >= 2 partials so that prepare takes the reduction branch
+    sard_prof_bytes(4.0 * n_sq);
     sard_launch(sqnorm_partial_kernel, nb, 256, 0, st, g_sq, n_sq, sq_scratch);
     SARD_LAUNCH_OK("sqnorm_partial_kernel");
   }

@@ -141,6 +141,8 @@ extern "C" int sard_gather_nodes(const SardArena* arena, const SardSel* sel, con
   p.x = out->x; p.ldx = out->ldx; p.nd_graph = out->nd_graph; p.nd_arena = out->nd_arena; p.body = out->body;
   p.root_row = out->root_row;
   const int threads = 256;
+  // algorithmic bytes: obs columns read + x row written + three index arrays written per node
+  sard_prof_bytes(4.0 * sel->n * ((double)(out->lead + out->tail) + out->ldx + 3.0));
   sard_launch(gather_kernel, ceil_div((long long)sel->B * 32, threads), threads, 0, as_stream(stream), p);
   SARD_LAUNCH_OK("gather_kernel");
   return 0;

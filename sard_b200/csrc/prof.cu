@@ -1,5 +1,6 @@
 // Launch counter and optional per-call-site kernel timing (see sard_prof_* in sard_b200.h).
 #include "common.cuh"
+#include <string>
 #include <vector>
 
 long long g_sard_launches = 0;
@@ -36,6 +37,78 @@ ProfScope::~ProfScope() {
 }
 
 extern "C" long long sard_launch_count(void) { return g_sard_launches; }
+
+// ---------------------------------------------------------------------------------------- every kernel, by name
+int g_sard_prof_all = 0;
+namespace {
+struct KRec { int name; double bytes; cudaEvent_t a, b; cudaStream_t st; };
+std::vector<KRec> g_krecs;
+std::vector<std::string> g_knames;
+int g_kcapacity = 0;
+double g_pending_bytes = 0.0;
+bool g_kopen = false;
+cudaEvent_t pool_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_pool.empty()) { e = g_pool.back(); g_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void sard_prof_bytes(double bytes) { if (g_sard_prof_all) g_pending_bytes = bytes; }
+void sard_prof_pre(cudaStream_t st) {
+  g_kopen = false;
+  if ((int)g_krecs.size() >= g_kcapacity) return;
+  KRec r;
+  r.name = -1; r.bytes = g_pending_bytes; r.st = st; r.a = pool_event(); r.b = pool_event();
+  g_pending_bytes = 0.0;
+  cudaEventRecord(r.a, st);
+  g_krecs.push_back(r);
+  g_kopen = true;
+}
+void sard_prof_post(cudaStream_t st) {
+  if (g_kopen) cudaEventRecord(g_krecs.back().b, st);
+}
+void sard_prof_label(const char* name) {
+  if (!g_kopen) return;
+  g_kopen = false;
+  for (size_t i = 0; i < g_knames.size(); ++i)
+    if (g_knames[i] == name) { g_krecs.back().name = (int)i; return; }
+  g_knames.push_back(name);
+  g_krecs.back().name = (int)g_knames.size() - 1;
+}
+
+extern "C" int sard_prof_kernels_enable(int capacity) {
+  g_sard_prof_all = capacity > 0 ? 1 : 0;
+  g_kcapacity = capacity;
+  if (capacity > 0) g_krecs.reserve(capacity);
+  return 0;
+}
+// names: '\n'-separated kernel names in id order (truncated to names_len); rows[i*5..] = {name id, stream ordinal, start ms,
+// end ms, algorithmic bytes} relative to the first record.  Returns the number of rows and clears the records.
+extern "C" int sard_prof_kernels_collect(char* names, int names_len, double* rows, int capacity) {
+  std::string all;
+  for (const std::string& n : g_knames) { all += n; all += '\n'; }
+  if (names && names_len > 0) { snprintf(names, (size_t)names_len, "%s", all.c_str()); }
+  std::vector<cudaStream_t> streams;
+  int n = 0;
+  for (const KRec& r : g_krecs) {
+    cudaEventSynchronize(r.b);
+    if (n < capacity && r.name >= 0) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, g_krecs[0].a, r.a);
+      cudaEventElapsedTime(&t1, g_krecs[0].a, r.b);
+      int sid = -1;
+      for (size_t k = 0; k < streams.size(); ++k) if (streams[k] == r.st) sid = (int)k;
+      if (sid < 0) { streams.push_back(r.st); sid = (int)streams.size() - 1; }
+      rows[n * 5 + 0] = r.name; rows[n * 5 + 1] = sid; rows[n * 5 + 2] = t0; rows[n * 5 + 3] = t1; rows[n * 5 + 4] = r.bytes;
+      ++n;
+    }
+  }
+  for (const KRec& r : g_krecs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+  g_krecs.clear();
+  return n;
+}
 
 extern "C" int sard_prof_enable(unsigned mask, int capacity) {
   g_mask = mask;

@@ -25,7 +25,7 @@
 #define TT_SBYTES 32768         // staging [128 rows][64 fp32] for the neighbour sums, 16-byte pieces XOR (row & 7)
 #define TT_SMEM (TT_WBYTES + TT_SBYTES + 1024)
 #ifndef TT_MINB
-#define TT_MINB 1
+#define TT_MINB 2
 #endif
 #define TT_WS (64 * 256)        // floats per pre-split weight block
 

@@ -52,6 +52,9 @@ class _EngineBase:
         self.ws = {}
         self.mom_local = {}
         self.mom_all = {}
+        # 'none': zero_grad(set_to_none=True) of torch >= 2 (a stage absent from a minibatch is skipped by Adam);
+        # 'zeros': torch < 2.0, the reference's pin (its gradients stay zero tensors, Adam keeps stepping from momentum)
+        self.zero_grad_semantics = 'none'
 
     def _workspace(self, key, need: int) -> torch.Tensor:
         w = self.ws.get(key)
@@ -473,6 +476,8 @@ class PolicyEngine(_EngineBase):
              fused: bool = False):
         opt = self.opt
         mask = (1 if any(active_global) else 0) | sum((1 << (1 + s)) for s in range(3) if active_global[s])
+        if self.zero_grad_semantics == 'zeros':
+            mask |= _lib.ADAM_STICKY
         st = stream()
         if fused:          # grad-norm partials + gate / clip + Adam in one call; leaves the gradient bucket zeroed
             inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0

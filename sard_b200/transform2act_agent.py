@@ -67,6 +67,10 @@ class Transform2ActAgent:
         self.policy_grad_clip = [(self.policy_net.parameters(), 40)]
         # The reference's clip list holds a generator: only its first use clips (agent_ppo.py:53-56).
         self.clip_first_step_only = True
+        # zero_grad() semantics of the host torch the run is meant to reproduce: 'none' (torch >= 2: gradients of a stage
+        # absent from a minibatch are None and Adam skips its parameters) or 'zeros' (torch < 2.0, the reference's pinned
+        # 1.8: they are zero tensors and Adam keeps stepping those parameters from momentum); see INTEGRATION.md
+        self.zero_grad_semantics = os.environ.get('SARD_ZERO_GRAD', 'none')
         self.value_opt_niter = 1
         self.num_threads = num_threads
         self.noise_rate = 1.0
@@ -304,6 +308,9 @@ class Transform2ActAgent:
     def _prepare(self, arena: PackedRollout):
         self.policy_net.prepare(arena, self.optimizer_policy)
         self.value_net.prepare(self.optimizer_value)
+        if self.zero_grad_semantics not in ('none', 'zeros'):
+            raise ValueError("zero_grad_semantics must be 'none' or 'zeros'")
+        self.policy_net.engine.zero_grad_semantics = self.zero_grad_semantics
 
     def _eval_values(self, arena: PackedRollout):
         order = Ordering(arena, np.arange(arena.T))

@@ -170,8 +170,11 @@ def test_update_policy_run_matches_reference_final_weights(tag, cuda_device):
     assert n > 80
 
 
-def test_full_update_params_against_oracle_on_fresh_rollout(cuda_device):
-    """End to end on new data: pack -> value pre-pass -> GAE -> update_policy, vs the oracle (fp64 CPU)."""
+@pytest.mark.parametrize('zero_grad', ['none', 'zeros'])
+def test_full_update_params_against_oracle_on_fresh_rollout(cuda_device, zero_grad):
+    """End to end on new data: pack -> value pre-pass -> GAE -> update_policy, vs the oracle (fp64 CPU).
+    zero_grad='zeros' is the reference's pinned torch 1.8 behaviour (absent stages keep zero gradient tensors and are
+    stepped from momentum); 'none' is torch >= 2 (they are skipped)."""
     from oracle import sard_oracle as O
     from sard_b200 import synthetic
     from tests.util import small_config, load_sd
@@ -185,6 +188,7 @@ def test_full_update_params_against_oracle_on_fresh_rollout(cuda_device):
     cfg = small_config('K_1>0>K_1>4', M, 2, T)
     torch.manual_seed(5)
     ag = Transform2ActAgent(cfg, torch.float32, 'cuda', 0, 1, env=synthetic.SyntheticEnv(shape))
+    ag.zero_grad_semantics = zero_grad
     with torch.no_grad():
         for nm in ('skel', 'attr', 'control'):
             lin = getattr(ag.policy_net, f'{nm}_ind_mlp').linear
@@ -197,7 +201,7 @@ def test_full_update_params_against_oracle_on_fresh_rollout(cuda_device):
                 v.requires_grad_(True)
     spec = O.Spec(attr_fixed_dim=shape.attr_fixed_dim, index_base=5, embeds=ag.policy_net.group.get_cur_subgroup_embeds().double(),
                   orbits={int(k): [int(x) for x in v] for k, v in ag.policy_net.group.get_cur_orbits().items()})
-    oag = O.OracleAgent(psd, vsd, spec, mini_batch_size=M, opt_num_epochs=2)
+    oag = O.OracleAgent(psd, vsd, spec, mini_batch_size=M, opt_num_epochs=2, zero_grad_to_none=(zero_grad == 'none'))
     rng = np.random.default_rng(0)
     perms = [rng.permutation(T) for _ in range(2)]
     batch = roll.to_traj_batch()
@@ -248,7 +252,21 @@ def test_update_is_deterministic(cuda_device):
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
-def test_full_width_nets_loss_and_gradients_match_oracle_autograd(cuda_device):
+@pytest.fixture
+def gemm_engine(request):
+    from sard_b200 import _lib
+    prev = _lib.lib.sard_get_gemm_engine()
+    _lib.lib.sard_set_gemm_engine(int(request.param))
+    yield int(request.param)
+    _lib.lib.sard_set_gemm_engine(prev)
+
+
+# engine 4 (default): fused tcgen05 tower + JSMLP; 0: fp32 FFMA tiles; 3: mma.sync 3xTF32; 1, 2: per-layer tcgen05 (SS / TS)
+@pytest.mark.parametrize('env_name,gemm_engine', [('manipulation_box', 4), ('locomotion_vt', 4), ('locomotion_ft', 4),
+                                                  ('point_nav', 4), ('manipulation_box', 0), ('locomotion_vt', 0),
+                                                  ('manipulation_box', 3), ('manipulation_box', 1), ('manipulation_box', 2)],
+                         indirect=['gemm_engine'])
+def test_full_width_nets_loss_and_gradients_match_oracle_autograd(cuda_device, env_name, gemm_engine):
     """derl.yml network sizes (GNN 64x3, JSMLP 128x2 over 256 body indices, critic MLP 512/256): this is the
     configuration the aligned fast paths serve (fused neighbour-sum GEMMs, 64x128 weight-gradient tiles, masked in_fc
     tile, skinny layers, fused encoders), which the 16-wide golden nets never reach.  Gradients of one stage-partitioned
@@ -259,7 +277,7 @@ def test_full_width_nets_loss_and_gradients_match_oracle_autograd(cuda_device):
     from sard_b200.packed import Ordering, PackedRollout, stage_partition
     from sard_b200.transform2act_agent import Transform2ActAgent
     torch.cuda.set_device(cuda_device)
-    shape = synthetic.ENV_SHAPES['manipulation_box']
+    shape = synthetic.ENV_SHAPES[env_name]
     T = 300
     roll = synthetic.generate_rollout(shape, T, seed=31, min_exec=6, max_exec=20, dtype=np.float32)
     for f in ('obs', 'hfield', 'obj', 'goal', 'actions', 'rewards', 'masks'):
