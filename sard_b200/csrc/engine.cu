@@ -55,11 +55,12 @@ inline void site(int kind, int pass) { g_sard_site = 3 * kind + pass; }
 // recorded right after dz_l was produced, and the run joins both before returning.  A side stream
 // serialises its weight gradients, so each has ONE partials scratch; dz buffers are per layer (no
 // ping-pong) so the main stream never overwrites one that is still read.
+#define N_SIDE 3
 struct SideCtx {
-  cudaStream_t main, side[2];      // [0]: tower weight gradients, [1]: head / MLP / JSMLP / encoder work
+  cudaStream_t main, side[N_SIDE];   // [0]: tower weight gradients, [1]: head / MLP / JSMLP weight gradients, [2]: ObsEncoders
   cudaEvent_t ev[8];
   int k;
-  bool forked[2];
+  bool forked[N_SIDE];
 };
 std::mutex g_side_mu;
 std::unordered_map<unsigned long long, SideCtx*> g_side;    // key: launching stream handle ^ device (the default stream's handle is 0 on every device)
@@ -71,12 +72,13 @@ SideCtx* side_for(cudaStream_t main) {
   cudaGetDevice(&dev);
   const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(main) ^ ((unsigned long long)(dev + 1) << 56);
   auto it = g_side.find(key);
-  if (it != g_side.end()) { it->second->forked[0] = it->second->forked[1] = false; return it->second; }
+  if (it != g_side.end()) { for (int i = 0; i < N_SIDE; ++i) it->second->forked[i] = false; return it->second; }
   SideCtx* c = new SideCtx();
-  c->main = main; c->k = 0; c->forked[0] = c->forked[1] = false;
+  c->main = main; c->k = 0;
+  for (int i = 0; i < N_SIDE; ++i) c->forked[i] = false;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < N_SIDE; ++i)
     if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
   g_side[key] = c;
@@ -93,7 +95,7 @@ sard_stream_t wg_stream(SideCtx* c, sard_stream_t st, int which) {
 }
 int side_join(SideCtx* c) {
   if (!c) return 0;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < N_SIDE; ++i) {
     if (!c->forked[i]) continue;
     cudaEvent_t e = c->ev[c->k++ & 7];
     SARD_CUDA(cudaEventRecord(e, c->side[i]));
@@ -398,7 +400,7 @@ struct ValueBufs {
   TowerBufs t;
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
-  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* sk; long long sk_floats;
+  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* wg3; float* sk; long long sk_floats;
 };
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
@@ -421,12 +423,13 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
     vb.de1 = b.f((long long)B * SARD_EXT_DIM);
     vb.wg = b.f(tower_wg_need(net.tower, n));               // side stream 0
-    long long need = enc_wg_need(net.enc, B), v;            // side stream 1
+    long long need = 4, v;                                   // side stream 1
     for (int j = 0; j < net.n_mlp; ++j) { v = wg_partials(B, net.mlp[j].out, net.mlp[j].in, WG_CHUNK); need = v > need ? v : need; }
     v = wg_partials(B, 1, vb.ldcat, WG_CHUNK); need = v > need ? v : need;
     vb.wg2 = b.f(need);
+    vb.wg3 = b.f(enc_wg_need(net.enc, B));                   // side stream 2
   } else {
-    vb.dcat = vb.de1 = vb.wg = vb.wg2 = nullptr;
+    vb.dcat = vb.de1 = vb.wg = vb.wg2 = vb.wg3 = nullptr;
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = nullptr;
   }
 }
@@ -472,7 +475,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   // the ObsEncoders only need the arena: they run beside the tower and are joined before the value head
   SideCtx* side = side_for(as_stream(st));
   SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
-                            wg_stream(side, st, 1)));
+                            wg_stream(side, st, 2)));
   SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
   // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
   const int hL = tw.h[tw.L];
@@ -518,7 +521,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   }
   // the encoders' backward ends in weight gradients only: all of it runs beside the MLP / tower backward
   SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
-                             vb.de1, vb.wg2, wg_stream(side, st, 1)));
+                             vb.de1, vb.wg3, wg_stream(side, st, 2)));
   // MLP backward (dz of layer j lives in dzj with leading dimension ldz)
   const float* dzj = vb.dcat; int ldz = vb.ldcat;
   SARD_CUDA(cudaMemsetAsync(vb.t.dz[tw.L], 0, sizeof(float) * (size_t)n * hL, as_stream(st)));
@@ -556,7 +559,7 @@ struct StageBufs {
   float* e1[3]; float* ext;
   int *srow, *spos, *grp_ptr, *tiles, *chunks, *grp_chunk_ptr, *counts, *sort_scratch;
   float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
-  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2;
+  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2; float* wg3;
   int max_tiles, max_chunks;
   bool tc;                       // fused tcgen05 JSMLP (jsmlp_tc.cu)
   bool tcb;                      // ... in the padded row space, with the fused backward (jsmlp_tc_bwd.cu)
@@ -634,12 +637,13 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
     sb.dext = b.f((long long)B * 3 * SARD_EXT_DIM);
     sb.de1 = b.f((long long)B * SARD_EXT_DIM);
     sb.wg = b.f(tower_wg_need(s.tower, n));                 // side stream 0
-    long long need = enc_wg_need(net.enc, B), v;            // side stream 1
+    long long need = 4, v;                                   // side stream 1
     if (!sb.tcb)
       for (int j = 0; j < s.n_il; ++j) { v = (long long)sb.max_chunks * s.il[j].out * SARD_WG_LDPART(s.il[j].in); need = v > need ? v : need; }
     sb.wg2 = b.f(need);
+    sb.wg3 = b.f(enc_wg_need(net.enc, B));                   // side stream 2
   } else {
-    sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = sb.wg2 = nullptr;
+    sb.dout = sb.gstat = sb.dxs = sb.dext = sb.de1 = sb.wg = sb.wg2 = sb.wg3 = nullptr;
     for (int j = 0; j < s.n_il; ++j) sb.dH[j] = nullptr;
   }
 }
@@ -676,6 +680,9 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
       double* rec = moments_local ? moments_local : sb.rec;
       SARD_TRY(sard_norm_moments(sb.t.x, sb.t.ldx, n, tw.D, sb.t.partials, rec, st));
     }
+    // the body-index sort only needs the gathered run: it belongs to the (prefetched) gather phase
+    SARD_TRY(sard_sort_by_index_padded(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.tcb ? sb.rows_cap : 0, sb.srow, sb.spos,
+                                       sb.grp_ptr, sb.tiles, sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, st));
   }
   if (!(phase & SARD_PHASE_COMPUTE)) return 0;
   if (upd) {
@@ -684,17 +691,13 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   } else {
     SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
   }
-  // the ObsEncoders and the body-index sort only need the gathered run: they run beside the tower
+  // the ObsEncoders only need the arena and the hi/lo pair copies of the live weight slabs only the weights (they change
+  // with every optimiser step): both run beside the tower
   SideCtx* side = side_for(as_stream(st));
-  {
-    sard_stream_t s2 = wg_stream(side, st, 1);
-    SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, s2));
-    SARD_TRY(sard_sort_by_index_padded(sb.t.body, n, s.max_index, IL_TILE, WG_CHUNK, sb.tcb ? sb.rows_cap : 0, sb.srow, sb.spos,
-                                       sb.grp_ptr, sb.tiles, sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, s2));
-    if (sb.tc) {                   // hi/lo pair copies of the live weight slabs (they change with every optimiser step)
-      const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
-      SARD_TRY(sard_jsmlp_tc_presplit(&a, s2));
-    }
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, wg_stream(side, st, 2)));
+  if (sb.tc) {
+    const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
+    SARD_TRY(sard_jsmlp_tc_presplit(&a, wg_stream(side, st, 1)));
   }
   SARD_TRY(tower_forward(tw, P, arena, sel, sb.t, st));
   SARD_TRY(side_join(side));
@@ -803,6 +806,6 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   SARD_TRY(sard_unsort_grad(sb.dxs, sb.ldxs, sb.spos, sel->cum, sel->node_base, B, sb.t.hout, hL, hL,
                             tw.L > 0 ? tw.act : SARD_ACT_NONE, sb.t.dz[tw.L], hL, sb.ext, 3 * SARD_EXT_DIM, 3 * SARD_EXT_DIM,
                             sb.dext, 3 * SARD_EXT_DIM, st));
-  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg2, wg_stream(side, st, 1)));
+  SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, sb.e1, sb.dext, 3 * SARD_EXT_DIM, sb.de1, sb.wg3, wg_stream(side, st, 2)));
   return tower_backward(tw, P, G, arena, sel, sb.t, sb.wg, side, st);
 }

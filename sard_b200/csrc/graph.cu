@@ -96,19 +96,40 @@ __global__ void unsort_grad_kernel(const float* __restrict__ dxs, int ld_dxs, co
   const int g = (int)(idx / W4), c = (int)(idx - (long long)g * W4) * 4;
   if (g >= B) return;
   const int r0 = cum[g] - node_base, r1 = cum[g + 1] - node_base;
+  // four nodes at a time: the position loads, then the row loads, are in flight together (a rolled loop pays two
+  // dependent memory latencies per node)
   if (c < Fh) {
-    for (int r = r0; r < r1; ++r) {
-      float4 v = *reinterpret_cast<const float4*>(dxs + (size_t)__ldg(spos + r) * ld_dxs + c);
-      const float4 y = *reinterpret_cast<const float4*>(h + (size_t)r * ld_h + c);
-      v.x *= act_grad_from_output(y.x, h_act); v.y *= act_grad_from_output(y.y, h_act);
-      v.z *= act_grad_from_output(y.z, h_act); v.w *= act_grad_from_output(y.w, h_act);
-      *reinterpret_cast<float4*>(dh + (size_t)r * ld_dh + c) = v;
+    for (int rb = r0; rb < r1; rb += 4) {
+      int pos[4];
+      float4 v[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pos[u] = rb + u < r1 ? __ldg(spos + rb + u) : 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (rb + u < r1) {
+          v[u] = *reinterpret_cast<const float4*>(dxs + (size_t)pos[u] * ld_dxs + c);
+          y[u] = *reinterpret_cast<const float4*>(h + (size_t)(rb + u) * ld_h + c);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (rb + u < r1) {
+          v[u].x *= act_grad_from_output(y[u].x, h_act); v[u].y *= act_grad_from_output(y[u].y, h_act);
+          v[u].z *= act_grad_from_output(y[u].z, h_act); v[u].w *= act_grad_from_output(y[u].w, h_act);
+          *reinterpret_cast<float4*>(dh + (size_t)(rb + u) * ld_dh + c) = v[u];
+        }
     }
   } else {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-      const float4 v = *reinterpret_cast<const float4*>(dxs + (size_t)__ldg(spos + r) * ld_dxs + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int rb = r0; rb < r1; rb += 4) {
+      int pos[4];
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pos[u] = rb + u < r1 ? __ldg(spos + rb + u) : 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = rb + u < r1 ? *reinterpret_cast<const float4*>(dxs + (size_t)pos[u] * ld_dxs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }   // node order kept
     }
     const int ce = c - Fh;
     const float4 e = *reinterpret_cast<const float4*>(ext + (size_t)g * ld_ext + ce);

@@ -92,17 +92,39 @@ __global__ void __launch_bounds__(256) jsmlp_presplit_kernel(const __grid_consta
   const float* Wu = p.W[j] + (size_t)u * out * in;
   float* F = p.Whl[j] + (size_t)slot * outp * 2 * in;
   float* T = p.Wthl[j] + (size_t)slot * in * 2 * kp;
-  const int total = outp * in;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int o = e / in, i = e - o * in;
-    const float v = o < out ? __ldg(Wu + (size_t)o * in + i) : 0.f;
-    const float h = tc::tf32_hi(v), l = v - h;
-    F[(size_t)o * 2 * in + i] = h;
-    F[(size_t)o * 2 * in + in + i] = l;
-    if (o < kp) {
-      T[(size_t)i * 2 * kp + o] = h;
-      T[(size_t)i * 2 * kp + kp + o] = l;
+  // 32 x 32 tiles (o, i): rows of W are read and rows of F written 128 bytes at a time, the transposed copy goes through
+  // shared memory so its rows are written whole too; the four loads of a thread are in flight together
+  __shared__ float th[32][33], tl[32][33];
+  const int tiles_i = in >> 5, n_tiles = ((outp + 31) >> 5) * tiles_i;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int o0 = (t / tiles_i) << 5, i0 = (t % tiles_i) << 5;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = o0 + w + 8 * q;
+      v[q] = o < out ? __ldg(Wu + (size_t)o * in + i0 + lane) : 0.f;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ol = w + 8 * q, o = o0 + ol;
+      const float h = tc::tf32_hi(v[q]), l = v[q] - h;
+      if (o < outp) {
+        F[(size_t)o * 2 * in + i0 + lane] = h;
+        F[(size_t)o * 2 * in + in + i0 + lane] = l;
+      }
+      th[ol][lane] = h; tl[ol][lane] = l;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int il = w + 8 * q, o = o0 + lane;
+      if (o < kp && o < outp) {
+        T[(size_t)(i0 + il) * 2 * kp + o] = th[lane][il];
+        T[(size_t)(i0 + il) * 2 * kp + kp + o] = tl[lane][il];
+      }
+    }
+    __syncthreads();
   }
   if (kp > outp) {                         // zero the k padding beyond the padded rows
     const int extra = (kp - outp) * in;
@@ -449,7 +471,7 @@ extern "C" int sard_jsmlp_tc_presplit(const SardJsmlpTc* a, sard_stream_t stream
     p.Whl[j] = a->ws + L.whl[j]; p.Wthl[j] = a->ws + L.wthl[j];
   }
   p.slot_of_index = a->slot_of_index; p.max_index = a->max_index;
-  sard_launch(jsmlp_presplit_kernel, dim3(8, a->n_slots, 3), 256, 0, st, p);
+  sard_launch(jsmlp_presplit_kernel, dim3(32, a->n_slots, 3), 256, 0, st, p);
   SARD_LAUNCH_OK("jsmlp_presplit_kernel");
   return 0;
 }

@@ -138,8 +138,12 @@ __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr
                                   int zero_grads) {
   pdl_sync();
   const SardAdamSeg s = segs[blockIdx.y];
+  if ((long long)blockIdx.x * blockDim.x >= s.n) return;              // short segment: nothing for this block
   if (active_mask & SARD_ADAM_STICKY) active_mask = ctl_i[3];
-  if (ctl_i[0] == 0 || !((active_mask >> s.group) & 1)) {
+  // a group outside the mask received no gradient in this step: its slice of the bucket is still zero from the last time
+  // it was used, so there is nothing to apply and nothing to clear
+  if (!((active_mask >> s.group) & 1)) return;
+  if (ctl_i[0] == 0) {                                                  // gated step: drop the gradients
     if (zero_grads) {
       float* g = const_cast<float*>(s.g);
       const bool vec = ((uintptr_t)g & 15) == 0;
@@ -190,7 +194,7 @@ extern "C" int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max
                                float beta2, float eps, int active_mask, const float* ctl_f, const int* ctl_i,
                                sard_stream_t stream) {
   if (n_seg <= 0 || max_seg_len <= 0) return 0;
-  int gx = (int)((max_seg_len + 255) / 256);
+  int gx = (int)((max_seg_len + 1023) / 1024);       // one float4 per thread and pass
   if (gx > 256) gx = 256;
   dim3 grid(gx, n_seg);
   sard_launch(adam_apply_kernel, grid, 256, 0, as_stream(stream), segs, lr, beta1, beta2, eps, active_mask, ctl_f, ctl_i, 0);
@@ -219,7 +223,7 @@ extern "C" int sard_adam_update(float* stats, float inv_B, float inv_world, floa
               max_norm, first_only, use_gate, active_mask, beta1, beta2, ctl_f, ctl_i, log_row, 1);
   SARD_LAUNCH_OK("adam_prepare_kernel");
   if (n_seg <= 0 || max_seg_len <= 0) return 0;
-  int gx = (int)((max_seg_len + 255) / 256);
+  int gx = (int)((max_seg_len + 1023) / 1024);
   if (gx > 256) gx = 256;
   dim3 grid(gx, n_seg);
   sard_launch(adam_apply_kernel, grid, 256, 0, st, segs, lr, (float)beta1, (float)beta2, eps, active_mask, ctl_f, ctl_i, 1);

@@ -94,12 +94,12 @@ __global__ void gather_kernel(const GatherP p) {
   const int c_tail = p.lead, c_const = p.lead + p.tail, c_hot = c_const + p.nconst;
   const int c_end = c_hot + (p.onehot ? 3 : 0);
   const int total = N * p.ldx;
-  // 4 independent loads in flight per lane: the rows of one graph are scattered over a 100+ MB arena, so
+  // 8 independent loads in flight per lane: the rows of one graph are scattered over a 100+ MB arena, so
   // this kernel is pure DRAM latency if the loads are taken one at a time
-  for (int base = lane; base < total; base += 128) {
-    float v[4];
+  for (int base = lane; base < total; base += 256) {
+    float v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int idx = base + 32 * u;
       const int i = idx / p.ldx, c = idx - i * p.ldx;
       float t = 0.f;
@@ -112,7 +112,7 @@ __global__ void gather_kernel(const GatherP p) {
       v[u] = t;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int idx = base + 32 * u;
       if (idx < total) {
         const int i = idx / p.ldx, c = idx - i * p.ldx;

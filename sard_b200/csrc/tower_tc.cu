@@ -87,7 +87,7 @@ int sard_tower_tc_presplit(const SardTower& tw, const float* P, float* wsplit, s
   TtSplitParams p;
   p.P = P; p.in_w = tw.in_w; p.D = tw.D; p.L = tw.L; p.out = wsplit;
   for (int l = 0; l < tw.L; ++l) { p.wl[l] = tw.wl[l]; p.wr[l] = tw.wr[l]; }
-  sard_launch(tower_presplit_kernel, dim3(8, 1 + 2 * tw.L), 256, 0, as_stream(stream), p);
+  sard_launch(tower_presplit_kernel, dim3(32, 1 + 2 * tw.L), 256, 0, as_stream(stream), p);   // one element per thread: no rolled load -> store loop
   SARD_LAUNCH_OK("tower_presplit_kernel");
   return 0;
 }

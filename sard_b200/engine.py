@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import (ACT, EXT_DIM, PHASE_ALL, PHASE_COMPUTE, PHASE_GATHER, POST_NONE, POST_SIN, SardIndexLinear,
                    SardPolicyNet, SardValueNet, check, lib, ptr, stream)
-from .nets import (AdamState, FlatStore, STAGE_NAMES, _dense, _encoders, _params_of, _tower, dense_segments)
+from .nets import (AdamState, FlatStore, SEG_MAX, STAGE_NAMES, _dense, _encoders, _params_of, _tower, dense_segments)
 from .packed import PackedRollout, Run
 
 N_STATS = 16
@@ -348,8 +348,10 @@ class PolicyEngine(_EngineBase):
                 rw, rb = t.out_dim * t.input_dim, t.out_dim
                 for k, u in enumerate(live):
                     u = int(u)
-                    segs.append((t.W.data.data_ptr() + 4 * u * rw, mW.data_ptr() + 4 * u * rw, vW.data_ptr() + 4 * u * rw,
-                                 st.GT + 4 * (st.il[j].gW + k * rw), rw, 1 + s))
+                    for o in range(0, rw, SEG_MAX):          # <= SEG_MAX elements per segment (one block row each)
+                        n = min(SEG_MAX, rw - o)
+                        segs.append((t.W.data.data_ptr() + 4 * (u * rw + o), mW.data_ptr() + 4 * (u * rw + o),
+                                     vW.data_ptr() + 4 * (u * rw + o), st.GT + 4 * (st.il[j].gW + k * rw + o), n, 1 + s))
                     segs.append((t.b.data.data_ptr() + 4 * u * rb, mb.data_ptr() + 4 * u * rb, vb.data_ptr() + 4 * u * rb,
                                  st.GT + 4 * (st.il[j].gb + k * rb), rb, 1 + s))
         opt.set_segments(segs, self.device)

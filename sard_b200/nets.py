@@ -24,7 +24,7 @@ from ._lib import (ACT, EXT_DIM, MAX_IL, MAX_LAYERS, MAX_MLP, SardAdamSeg, SardD
                    SardPolicyNet, SardPolicyStage, SardTower, SardValueNet, check, lib, ptr, stream)
 
 STAGE_NAMES = ('skel', 'attr', 'control')
-SEG_MAX = 32768
+SEG_MAX = 4096        # elements per Adam segment: one block row of adam_apply_kernel covers it in one float4 pass
 
 
 class RunningNorm(nn.Module):
