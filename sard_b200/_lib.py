@@ -8,7 +8,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libsard_b200.so')
+LIB_PATH = os.environ.get('SARD_LIB') or os.path.join(HERE, 'libsard_b200.so')      # SARD_LIB: a tuning build (tools/)
 
 MAX_LAYERS, MAX_MLP, MAX_IL, ACTION_DIM, EXT_DIM = 8, 4, 4, 8, 64
 ACT = {'none': 0, None: 0, 'relu': 1, 'tanh': 2, 'sigmoid': 3}

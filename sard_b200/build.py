@@ -32,6 +32,26 @@ def build_hostpack() -> str:
     return HOSTPACK
 
 
+def build_variant(tag: str, defines) -> str:
+    """A tuning build with extra -D flags into libsard_b200_<tag>.so (selected at run time with SARD_LIB)."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    out_dir = os.path.join(HERE, 'build', tag)
+    os.makedirs(out_dir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace('.cu', '.o'))
+        objs.append(obj)
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f not in ('--use_fast_math=false', '-Xptxas', '-v')] + [f'-D{d}' for d in defines] + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+    lib = os.path.join(HERE, f'libsard_b200_{tag}.so')
+    subprocess.check_call([nvcc, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB

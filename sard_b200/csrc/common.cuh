@@ -36,7 +36,7 @@ void sard_prof_bytes(double bytes);
 
 #define SARD_LAUNCH_OK(name)                                                                 \
   do {                                                                                       \
-    ++g_sard_launches;                                                                       \
+    __atomic_fetch_add(&g_sard_launches, 1LL, __ATOMIC_RELAXED);   /* two host threads issue */ \
     if (g_sard_prof_all) sard_prof_label(name);                                              \
     cudaError_t e__ = cudaGetLastError();                                                    \
     if (e__ != cudaSuccess)                                                                  \

@@ -269,8 +269,11 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
     (void)P; (void)wg_scratch;
     site(K_GCONV, 1);
     SARD_TRY(sard_tower_tc_backward(tw, arena, sel, t.tc, t.dz[tw.L], t.nd_graph, t.nd_arena, st));
+    // the adjoint chain is the last thing on the launching stream and the optimiser waits for these weight gradients:
+    // they stay on it (a fork + join through a side stream costs two event hops, ~15 us, and buys no overlap here)
     site(K_GCONV, 2);
-    SARD_TRY(sard_tower_tc_wgrad(tw, sel, t.tc, G, wg_stream(side, st, 0)));
+    static const int wg_side = getenv("SARD_TOWER_WG_SIDE") ? atoi(getenv("SARD_TOWER_WG_SIDE")) : 0;
+    SARD_TRY(sard_tower_tc_wgrad(tw, sel, t.tc, G, wg_side ? wg_stream(side, st, 0) : st));
     return side_join(side);
   }
   for (int l = tw.L; l >= 1; --l) {

@@ -310,7 +310,9 @@ __global__ void __launch_bounds__(JB_THREADS, 1) jsmlp_bwd_tc_kernel(const __gri
 
 // ------------------------------------------------------------------------------------------ weight gradients
 #define JW_ROWS 8                   // rows (= reduction steps) per pipeline stage: one 8-deep tf32 MMA
+#ifndef JW_STAGES
 #define JW_STAGES 4
+#endif
 #define JW_OFF_DZ1 0                // [8 slabs: 4 hi | 4 lo] x 8 rows x 128 B
 #define JW_OFF_XS 8192              // [16 slabs: 8 hi | 8 lo]
 #define JW_OFF_DZ2 24576

@@ -1,5 +1,6 @@
 // Launch counter and optional per-call-site kernel timing (see sard_prof_* in sard_b200.h).
 #include "common.cuh"
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -15,11 +16,13 @@ unsigned g_mask = 0;
 int g_capacity = 0;
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
+std::mutex g_prof_mu;          // the critic and the policy are issued from two host threads
 }  // namespace
 
 ProfScope::ProfScope(cudaStream_t stream, double flops, double bytes) : slot(-1), st(stream) {
   const int site = g_sard_site;
   if (g_mask == 0 || site < 0 || site >= SARD_PROF_SITES || !((g_mask >> site) & 1u)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if ((int)g_recs.size() >= g_capacity) return;
   Rec r;
   r.site = site; r.flops = flops; r.bytes = bytes; r.st = stream;
@@ -33,7 +36,9 @@ ProfScope::ProfScope(cudaStream_t stream, double flops, double bytes) : slot(-1)
 }
 
 ProfScope::~ProfScope() {
-  if (slot >= 0) cudaEventRecord(g_recs[slot].b, st);
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  cudaEventRecord(g_recs[slot].b, st);
 }
 
 extern "C" long long sard_launch_count(void) { return g_sard_launches; }
@@ -45,8 +50,8 @@ struct KRec { int name; double bytes; cudaEvent_t a, b; cudaStream_t st; };
 std::vector<KRec> g_krecs;
 std::vector<std::string> g_knames;
 int g_kcapacity = 0;
-double g_pending_bytes = 0.0;
-bool g_kopen = false;
+thread_local double g_pending_bytes = 0.0;
+thread_local int g_kopen = -1;           // index of this thread's record awaiting its end event / label
 cudaEvent_t pool_event() {
   cudaEvent_t e = nullptr;
   if (!g_pool.empty()) { e = g_pool.back(); g_pool.pop_back(); }
@@ -57,25 +62,29 @@ cudaEvent_t pool_event() {
 
 void sard_prof_bytes(double bytes) { if (g_sard_prof_all) g_pending_bytes = bytes; }
 void sard_prof_pre(cudaStream_t st) {
-  g_kopen = false;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_kopen = -1;
   if ((int)g_krecs.size() >= g_kcapacity) return;
   KRec r;
   r.name = -1; r.bytes = g_pending_bytes; r.st = st; r.a = pool_event(); r.b = pool_event();
   g_pending_bytes = 0.0;
   cudaEventRecord(r.a, st);
   g_krecs.push_back(r);
-  g_kopen = true;
+  g_kopen = (int)g_krecs.size() - 1;
 }
 void sard_prof_post(cudaStream_t st) {
-  if (g_kopen) cudaEventRecord(g_krecs.back().b, st);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_kopen >= 0) cudaEventRecord(g_krecs[g_kopen].b, st);
 }
 void sard_prof_label(const char* name) {
-  if (!g_kopen) return;
-  g_kopen = false;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_kopen < 0) return;
+  const int k = g_kopen;
+  g_kopen = -1;
   for (size_t i = 0; i < g_knames.size(); ++i)
-    if (g_knames[i] == name) { g_krecs.back().name = (int)i; return; }
+    if (g_knames[i] == name) { g_krecs[k].name = (int)i; return; }
   g_knames.push_back(name);
-  g_krecs.back().name = (int)g_knames.size() - 1;
+  g_krecs[k].name = (int)g_knames.size() - 1;
 }
 
 extern "C" int sard_prof_kernels_enable(int capacity) {

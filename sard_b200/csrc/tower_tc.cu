@@ -234,8 +234,10 @@ __device__ __forceinline__ void act32(float* v, int act) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (act == SARD_ACT_TANH) {
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    // SFU form (tc::tanh_fast, absolute error < 5e-7) as in the fused JSMLP: libdevice tanhf is ~40 instructions with
+    // divergent branches, and 32 of them per row and layer were 60 % of a GraphConv layer's epilogue
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tc::tanh_fast(v[j]);
   } else if (act == SARD_ACT_SIGMOID) {
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
   uint8_t* S = sW + TT_WBYTES;
   __shared__ uint64_t bar_wfull, bar_wfree, bar_mma, bar_a, bar_half;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_mean[128], s_inv[128], s_bias[1 + TT_MAXL][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 1) tc::tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
@@ -339,28 +342,55 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     row_setup(c, S, warp, lane, row_lo, nrows, p.tab, p.nd_graph, p.nd_arena, p.cum, p.node_base, p.nptr);
     const bool normalise = *p.count > 0;
     const long long r = row_lo + c.trow;
+    // RunningNorm statistics and every bias go to shared memory once (read back as broadcast float4)
+    {
+      const int wt = tid - 64;
+      if (wt < 128) {
+        s_mean[wt] = (normalise && wt < p.D) ? __ldg(p.mean + wt) : 0.f;
+        s_inv[wt] = (normalise && wt < p.D) ? __ldg(p.inv + wt) : 1.f;
+      } else {
+        const int b = wt - 128, l = b >> 6, j = b & 63;        // l = 0: in_fc, 1: GraphConv layer 1
+        s_bias[l][j] = l == 0 ? __ldg(p.b_in + j) : (p.L >= 1 && p.bl[0] ? __ldg(p.bl[0] + j) : 0.f);
+        if (TT_MAXL >= 2) s_bias[2 + l][j] = (p.L >= 2 + l && p.bl[1 + l]) ? __ldg(p.bl[1 + l] + j) : 0.f;
+      }
+      tc::named_sync(3, 256);
+    }
     float v[32];
-    // ---- in_fc operand: normalised + clamped input row, 64 columns of K per pass
+    // ---- in_fc operand: normalised + clamped input row, 64 columns of K per pass.  The warp's 32 x 32 block of x is
+    // read with whole-row (128-byte) transactions into the warp's own staging region and picked up one row per lane.
     for (int h = 0; h < 2; ++h) {
       if (h >= nhalf && !p.XH) break;
       const int k0 = h * 64 + c.c0;
+      {
+        const int pc = lane & 7, kcol = k0 + pc * 4;
+        float4 t4[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int row = 4 * k + (lane >> 3);
+          t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < c.nv && kcol < p.ldx) t4[k] = *reinterpret_cast<const float4*>(p.x + (size_t)(c.row0 + row) * p.ldx + kcol);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int row = 4 * k + (lane >> 3);
+          *reinterpret_cast<float4*>(c.own + row * 256 + ((pc ^ (row & 7)) << 4)) = t4[k];
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = k0 + 4 * j;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.valid && k < p.D) xv = *reinterpret_cast<const float4*>(p.x + (size_t)r * p.ldx + k);
-        float t4[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float4 xv = *reinterpret_cast<const float4*>(c.own + lane * 256 + ((j ^ (lane & 7)) << 4));
+        const float4 mu = *reinterpret_cast<const float4*>(s_mean + (k & 127)), iv = *reinterpret_cast<const float4*>(s_inv + (k & 127));
+        float t4[4] = {(xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int kk = k + i;
-          float t = 0.f;
-          if (kk < p.D) {
-            t = t4[i];
-            if (normalise) t = fminf(fmaxf((t - __ldg(p.mean + kk)) * __ldg(p.inv + kk), -p.clip), p.clip);
-          }
-          v[4 * j + i] = t;
+          float t = t4[i];
+          if (normalise) t = fminf(fmaxf(t, -p.clip), p.clip);
+          v[4 * j + i] = (k + i < p.D) ? t : 0.f;
         }
       }
+      __syncwarp();
       if (h < nhalf) {
         if (h == 1) { tc::mbar_wait(&bar_half, 0); tc::tc_fence_after(); }
         tmem_put32(tmem, c, v);
@@ -384,7 +414,10 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     TT_STAMP(34);
     tc::tmem_ld32(DD + c.lane_off + c.c0, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.b_in + c.c0 + j);
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[0][c.c0 + 4 * j]);
+      v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+    }
     tmem_put32(tmem, c, v);
     tc::tc_fence_before();
     tc::mbar_arrive(&bar_a);
@@ -405,9 +438,10 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
       stage_write(S, c, v);
       tc::tmem_ld32(DD + c.lane_off + 64 + c.c0, v);     // x W_r^T
       tc::named_sync(1, 256);
-      if (p.bl[l - 1]) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bl[l - 1] + c.c0 + j);
+      for (int j = 0; j < 8; ++j) {                       // zero when the layer has no bias
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[l][c.c0 + 4 * j]);
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
       }
       TT_STAMP(37 + 5 * (l - 1));
       stage_gather(S, c, p.nnbr, v);
@@ -517,12 +551,28 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const
     TT_STAMP(1);
     const long long r = row_lo + c.trow;
     float v[32];
-    // ---- dz_L
+    // ---- dz_L: the warp's 32 x 32 block read with whole 128-byte row pieces through its own staging region
+    {
+      const int pc = lane & 7;
+      float4 t4[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c.valid) t = *reinterpret_cast<const float4*>(p.dzL + (size_t)r * TT_H + c.c0 + 4 * j);
-      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      for (int k = 0; k < 8; ++k) {
+        const int row = 4 * k + (lane >> 3);
+        t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < c.nv) t4[k] = *reinterpret_cast<const float4*>(p.dzL + (size_t)(c.row0 + row) * TT_H + c.c0 + pc * 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = 4 * k + (lane >> 3);
+        *reinterpret_cast<float4*>(c.own + row * 256 + ((pc ^ (row & 7)) << 4)) = t4[k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(c.own + lane * 256 + ((j ^ (lane & 7)) << 4));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+      __syncwarp();
     }
 #pragma unroll 1
     for (int i = 0; i < p.L; ++i) {
@@ -589,7 +639,9 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const
 
 // ------------------------------------------------------------------------------------------ weight gradients
 #define TWG_ROWS 8
+#ifndef TWG_STAGES
 #define TWG_STAGES 4
+#endif
 #define TWG_OFF_A(l) ((l) * 12288)             // layer l = 1..3 at slot l-1: [A^T dz | dz] 8 slabs (hi 4 | lo 4) then h_{l-1} 4 slabs (hi 2 | lo 2)
 #define TWG_OFF_X 36864                        // x pair 8 slabs, then dz_0 pair 4 slabs
 #define TWG_STAGE_BYTES 49152

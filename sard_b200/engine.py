@@ -183,32 +183,35 @@ class ValueEngine(_EngineBase):
 
     # -- software-pipelined single-GPU step: the gather + RunningNorm moments of minibatch k+1 (they read only the
     #    arena) are issued on a gather stream into the other of two workspaces while minibatch k computes
-    def prefetch(self, arena: PackedRollout, run: Run, slot: int, comm: Optional[Comm] = None):
-        """GATHER phase (+ the moments all-gather when data parallel) into workspace `slot`."""
+    def prefetch(self, arena: PackedRollout, run: Run, slot: int, comm: Optional[Comm] = None, st: Optional[int] = None):
+        """GATHER phase (+ the moments all-gather when data parallel) into workspace `slot`.  ``st``: raw stream handle
+        (default: torch's current stream; the update loop passes handles to keep the per-launch host cost down)."""
         net = self.net
         world = comm.world if comm is not None else 1
         ws = self._workspace(('v', slot), lib.sard_value_workspace(C.byref(net), run.n, run.B))
         ml, ma = self._moments(('v', slot), net.tower.D, world)
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, ptr(ml), None, 1,
-                                 self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+                                 self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), st if st is not None else stream()))
         if world > 1:
             comm.allgather(ml, ma)
 
-    def compute_prefetched(self, arena: PackedRollout, run: Run, B_global: int, slot: int, world: int = 1):
+    def compute_prefetched(self, arena: PackedRollout, run: Run, B_global: int, slot: int, world: int = 1,
+                           st: Optional[int] = None):
         """COMPUTE phase on a prefetched workspace.  The gradient bucket must be zero on entry: ``adam(fused=True)``
         leaves it zeroed, the agent clears it once before the first step."""
         net = self.net
         ws, ml, ma = self.ws[('v', slot)], self.mom_local[('v', slot)], self.mom_all.get(('v', slot))
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, 1.0 / B_global, ptr(ml),
-                                 ptr(ma) if world > 1 else None, world, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), stream()))
+                                 ptr(ma) if world > 1 else None, world, self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(),
+                                 st if st is not None else stream()))
 
-    def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int):
-        self.compute_prefetched(arena, run, B_global, slot)
-        self.adam(B_global, log_row, fused=True)
+    def train_step_prefetched(self, arena: PackedRollout, run: Run, B_global: int, log_row, slot: int, st: Optional[int] = None):
+        self.compute_prefetched(arena, run, B_global, slot, st=st)
+        self.adam(B_global, log_row, fused=True, st=st)
 
-    def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None, fused: bool = False):
+    def adam(self, B_global: int, log_row: Optional[torch.Tensor] = None, fused: bool = False, st: Optional[int] = None):
         opt = self.opt
-        st = stream()
+        st = st if st is not None else stream()
         if fused:          # one call: gate + Adam, and the gradient bucket is left zeroed for the next step
             check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0, 0.0, None, 0, None, -1.0, 0, 0, 1, opt.betas[0],
                                        opt.betas[1], ptr(opt.ctl_f), ptr(opt.ctl_i), ptr(log_row), ptr(opt.segs), opt.n_seg,
@@ -433,10 +436,11 @@ class PolicyEngine(_EngineBase):
         self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row)
 
     def prefetch(self, arena: PackedRollout, runs: List[Optional[Run]], slot: int, comm: Optional[Comm] = None,
-                 active_global: Optional[Sequence[bool]] = None):
+                 active_global: Optional[Sequence[bool]] = None, st: Optional[int] = None):
         """GATHER phase of every present stage (+ the moments all-gathers when data parallel) into workspace `slot`."""
         net = self.net
         world = comm.world if comm is not None else 1
+        st = st if st is not None else stream()
         for s in (2, 1, 0):
             run = runs[s]
             if run is None:
@@ -450,13 +454,14 @@ class PolicyEngine(_EngineBase):
             ws = self._workspace((s, slot), lib.sard_policy_workspace(C.byref(net), s, run.n, run.B))
             ml, ma = self._moments((s, slot), net.stage[s].tower.D, world)
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, 0.0, ptr(ml),
-                                      None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), stream()))
+                                      None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), st))
             if world > 1:
                 comm.allgather(ml, ma)
 
     def compute_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, clip_eps: float, slot: int,
-                           world: int = 1, active_global: Optional[Sequence[bool]] = None):
+                           world: int = 1, active_global: Optional[Sequence[bool]] = None, st: Optional[int] = None):
         net = self.net                  # gradient bucket zero on entry (see ValueEngine.compute_prefetched)
+        st = st if st is not None else stream()
         for s in (2, 1, 0):
             run = runs[s]
             if run is None:
@@ -466,21 +471,21 @@ class PolicyEngine(_EngineBase):
             ws, ml, ma = self.ws[(s, slot)], self.mom_local[(s, slot)], self.mom_all.get((s, slot))
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, clip_eps,
                                       1.0 / B_global, ptr(ml), ptr(ma) if world > 1 else None, world, ptr(self.GA), None, None,
-                                      ptr(ws), ws.numel(), stream()))
+                                      ptr(ws), ws.numel(), st))
 
     def train_step_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
                               active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
-                              log_row, slot: int):
-        self.compute_prefetched(arena, runs, B_global, clip_eps, slot)
-        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row, fused=True)
+                              log_row, slot: int, st: Optional[int] = None):
+        self.compute_prefetched(arena, runs, B_global, clip_eps, slot, st=st)
+        self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, 1, log_row, fused=True, st=st)
 
     def adam(self, B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row=None,
-             fused: bool = False):
+             fused: bool = False, st: Optional[int] = None):
         opt = self.opt
         mask = (1 if any(active_global) else 0) | sum((1 << (1 + s)) for s in range(3) if active_global[s])
         if self.zero_grad_semantics == 'zeros':
             mask |= _lib.ADAM_STICKY
-        st = stream()
+        st = st if st is not None else stream()
         if fused:          # grad-norm partials + gate / clip + Adam in one call; leaves the gradient bucket zeroed
             inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0
             check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0 / world, inv_cat, self.GA.data_ptr() + 4 * N_STATS,

@@ -87,6 +87,9 @@ class Transform2ActAgent:
         self.prefetch_gather = os.environ.get('SARD_PREFETCH', '1') != '0'
         self._gather_ctx = None
         self.overlap_nets = True          # critic and policy updates of a minibatch on two CUDA streams
+        # ... optionally issued from two host threads (the C++ schedules release the GIL).  Measured SLOWER on one B200
+        # box (119 -> 137 ms/update: the GIL hand-offs cost more than the parallel issue gains), so it is off by default
+        self.two_thread_issue = os.environ.get('SARD_TWO_THREADS', '0') != '0'
         self._streams = None
         if checkpoint != 0:
             self.load_checkpoint(checkpoint)
@@ -415,9 +418,14 @@ class Transform2ActAgent:
         # only ~150-300 CTAs on 148 SMs: run them on two streams so their kernels share the machine.
         main = torch.cuda.current_stream(self.device)
         sv, sp = self._net_streams()
+        sv_h, sp_h = sv.cuda_stream, sp.cuda_stream
         if self.overlap_nets and self.prefetch_gather:
             veng.GA.zero_(); peng.GA.zero_()         # the fused optimiser tail keeps the buckets zeroed from here on
         sv.wait_stream(main); sp.wait_stream(main)
+        if world == 1 and self.overlap_nets and self.prefetch_gather and self.two_thread_issue and n_steps > 0:
+            step, h2d, cur_perm = self._update_two_threads(arena, perms, T, M, batch_design, n_mb, vlog, plog, main, sv, sp)
+            main.wait_stream(sv); main.wait_stream(sp)
+            return self._finish_update(arena, plog, vlog, step, h2d, t_host0, cur_perm)
         for ep in range(self.opt_num_epochs):
             # like the reference, each epoch permutes the already permuted lists (agent :331-342)
             p = perms[ep] if perms is not None else self.draw_perm(T)
@@ -491,15 +499,15 @@ class Transform2ActAgent:
                     if k + 1 < plan.n_mb:
                         self._issue_prefetch(arena, plan, k + 1, slot ^ 1, None)
                     gv, gp, ready, free = self._gather_ctx
-                    with torch.cuda.stream(sv):
-                        sv.wait_event(ready[0][slot])
-                        veng.train_step_prefetched(arena, vrun, B_glob, vlog[step], slot)
-                        free[0][slot].record(sv)
-                    with torch.cuda.stream(sp):
-                        sp.wait_event(ready[1][slot])
-                        peng.train_step_prefetched(arena, pruns, B_glob, skel_nodes, active, self.clip_epsilon,
-                                                   40.0, self.clip_first_step_only, plog[step], slot)
-                        free[1][slot].record(sp)
+                    # raw stream handles, no stream context managers: this loop issues ~16 000 launches per update and
+                    # its Python glue was a third of the host's issue time
+                    sv.wait_event(ready[0][slot])
+                    veng.train_step_prefetched(arena, vrun, B_glob, vlog[step], slot, st=sv_h)
+                    free[0][slot].record(sv)
+                    sp.wait_event(ready[1][slot])
+                    peng.train_step_prefetched(arena, pruns, B_glob, skel_nodes, active, self.clip_epsilon,
+                                               40.0, self.clip_first_step_only, plog[step], slot, st=sp_h)
+                    free[1][slot].record(sp)
                 elif self.overlap_nets:
                     with torch.cuda.stream(sv):
                         veng.train_step(arena, vrun, B_glob, vlog[step], comm)
@@ -515,6 +523,9 @@ class Transform2ActAgent:
                 # the next epoch's plan replaces the ordering tensors the in-flight kernels read
                 plans_alive.append(plan)
         main.wait_stream(sv); main.wait_stream(sp)
+        return self._finish_update(arena, plog, vlog, step, h2d, t_host0, cur_perm)
+
+    def _finish_update(self, arena, plog, vlog, step, h2d, t_host0, cur_perm):
         host_enqueue_s = time.perf_counter() - t_host0        # host time to issue the whole update (no sync inside)
         logs = plog[:step].cpu().numpy()
         vlogs = vlog[:step].cpu().numpy()
@@ -522,6 +533,77 @@ class Transform2ActAgent:
                                   'host_enqueue_s': host_enqueue_s, 'steps': step, 'valid_steps': int(logs[:, 3].sum()) if step else 0,
                                   'value_loss': vlogs[:, 5].copy(), 'policy_log': logs}
         return self._summarise(arena, logs, cur_perm)
+
+    def _update_two_threads(self, arena, perms, T, M, batch_design, n_mb, vlog, plog, main, sv, sp):
+        """The minibatch loop of a single-GPU update with the critic issued from a second host thread.
+
+        The two nets share nothing but the read-only arena and the epoch orderings, so every epoch's plan is built (and
+        its ordering uploaded) first; then each net runs its own loop -- gather of minibatch k+1 on its gather stream,
+        compute + Adam of minibatch k on its compute stream -- for all epochs.  Kernel order per stream, and therefore
+        every result, is identical to the single-thread schedule."""
+        import threading
+        plans = []
+        h2d = 0
+        cur_perm = np.arange(T)
+        for ep in range(self.opt_num_epochs):
+            p = perms[ep] if perms is not None else self.draw_perm(T)          # agent :331-342
+            cur_perm = cur_perm[p]
+            plan = EpochPlan(arena, cur_perm, M, batch_design, n_mb=n_mb)
+            cur_perm = plan.perm
+            h2d += plan.h2d_bytes
+            plans.append(plan)
+        if self._gather_ctx is None or self._gather_ctx[0].device != self.device:
+            ev = lambda: [[torch.cuda.Event() for _ in range(2)] for _ in range(2)]
+            self._gather_ctx = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), ev(), ev())
+        gv, gp, ready, free = self._gather_ctx
+        for st in (sv, sp, gv, gp):
+            st.wait_stream(main)                     # the ordering uploads happened on the main stream
+        veng, peng = self.value_net.engine, self.policy_net.engine
+        clip_eps, first_only = self.clip_epsilon, self.clip_first_step_only
+        errors = []
+
+        def net_loop(net):
+            try:
+                with torch.cuda.device(self.device):
+                    g, cs, eng = (gv, sv, veng) if net == 0 else (gp, sp, peng)
+                    step = 0
+                    for plan in plans:
+                        runs = [plan.value_run(k) if net == 0 else plan.policy_runs(k) for k in range(plan.n_mb)]
+
+                        def prefetch(k, slot):
+                            g.wait_event(free[net][slot])          # the previous user of this workspace has finished
+                            with torch.cuda.stream(g):
+                                eng.prefetch(arena, runs[k], slot)
+                                ready[net][slot].record(g)
+
+                        for k in range(plan.n_mb):
+                            slot = k & 1
+                            if k == 0:
+                                prefetch(0, 0)
+                            if k + 1 < plan.n_mb:
+                                prefetch(k + 1, slot ^ 1)
+                            B_glob = int(plan.stage_graphs[k].sum())
+                            with torch.cuda.stream(cs):
+                                cs.wait_event(ready[net][slot])
+                                if net == 0:
+                                    eng.train_step_prefetched(arena, runs[k], B_glob, vlog[step], slot)
+                                else:
+                                    active = [bool(plan.stage_graphs[k, s] > 0) for s in range(3)]
+                                    eng.train_step_prefetched(arena, runs[k], B_glob, int(plan.stage_nodes[k, 0]), active, clip_eps,
+                                                              40.0, first_only, plog[step], slot)
+                                free[net][slot].record(cs)
+                            step += 1
+            except BaseException as e:                  # noqa: BLE001  (re-raised on the calling thread)
+                errors.append(e)
+
+        th = threading.Thread(target=net_loop, args=(0,), name='sard-critic-issue')
+        th.start()
+        net_loop(1)
+        th.join()
+        if errors:
+            raise errors[0]
+        self._plans_alive = plans                        # the in-flight kernels read the ordering tensors
+        return self.opt_num_epochs * n_mb, h2d, cur_perm
 
     def _issue_prefetch(self, arena: PackedRollout, plan, k: int, slot: int, after, comm=None, active=None):
         """GATHER phase of minibatch k of `plan` for both nets on their gather streams, into workspace `slot`."""
@@ -534,6 +616,13 @@ class Transform2ActAgent:
             if after is not None:
                 g.wait_stream(after)                       # the epoch's ordering upload
             g.wait_event(free[net][slot])                  # the previous user of this workspace has finished
+            if comm is None:                               # raw stream handle: no context switch on the host
+                if net == 0:
+                    eng.prefetch(arena, run, slot, st=g.cuda_stream)
+                else:
+                    eng.prefetch(arena, run, slot, st=g.cuda_stream)
+                ready[net][slot].record(g)
+                continue
             with torch.cuda.stream(g):
                 if net == 0:
                     eng.prefetch(arena, run, slot, comm)
