@@ -73,8 +73,9 @@ int sard_prof_collect(double* rows, int n_sites);
 int sard_prof_timeline(double* rows, int capacity);
 /* Every launch of the library by kernel name (diagnostic: events around each launch suppress the programmatic
  * overlap of consecutive kernels).  sard_prof_kernels_enable(capacity > 0) starts recording, (0) stops.
- * sard_prof_kernels_collect: names = newline-separated kernel names in id order; rows[i*5..] = {name id, stream
- * ordinal, start ms, end ms, algorithmic bytes (0 when the wrapper states none)}; returns the row count, clears. */
+ * sard_prof_kernels_collect: names = newline-separated kernel names in id order; rows[i*6..] = {name id, stream
+ * ordinal, start ms, end ms, algorithmic bytes, algorithmic flops (0 when the wrapper states none)}; returns the row
+ * count, clears. */
 int sard_prof_kernels_enable(int capacity);
 int sard_prof_kernels_collect(char* names, int names_len, double* rows, int capacity);
 

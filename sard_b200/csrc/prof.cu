@@ -16,10 +16,12 @@ unsigned g_mask = 0;
 int g_capacity = 0;
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
-std::mutex g_prof_mu;          // the critic and the policy are issued from two host threads
+std::mutex g_prof_mu;          // the critic and the policy may be issued from two host threads
+thread_local double g_pending_bytes = 0.0, g_pending_flops = 0.0;     // work figures of the next launch (per-kernel table)
 }  // namespace
 
 ProfScope::ProfScope(cudaStream_t stream, double flops, double bytes) : slot(-1), st(stream) {
+  if (g_sard_prof_all) { g_pending_bytes = bytes; g_pending_flops = flops; }      // the per-kernel table gets the same work figures
   const int site = g_sard_site;
   if (g_mask == 0 || site < 0 || site >= SARD_PROF_SITES || !((g_mask >> site) & 1u)) return;
   std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -46,11 +48,10 @@ extern "C" long long sard_launch_count(void) { return g_sard_launches; }
 // ---------------------------------------------------------------------------------------- every kernel, by name
 int g_sard_prof_all = 0;
 namespace {
-struct KRec { int name; double bytes; cudaEvent_t a, b; cudaStream_t st; };
+struct KRec { int name; double bytes, flops; cudaEvent_t a, b; cudaStream_t st; };
 std::vector<KRec> g_krecs;
 std::vector<std::string> g_knames;
 int g_kcapacity = 0;
-thread_local double g_pending_bytes = 0.0;
 thread_local int g_kopen = -1;           // index of this thread's record awaiting its end event / label
 cudaEvent_t pool_event() {
   cudaEvent_t e = nullptr;
@@ -66,8 +67,8 @@ void sard_prof_pre(cudaStream_t st) {
   g_kopen = -1;
   if ((int)g_krecs.size() >= g_kcapacity) return;
   KRec r;
-  r.name = -1; r.bytes = g_pending_bytes; r.st = st; r.a = pool_event(); r.b = pool_event();
-  g_pending_bytes = 0.0;
+  r.name = -1; r.bytes = g_pending_bytes; r.flops = g_pending_flops; r.st = st; r.a = pool_event(); r.b = pool_event();
+  g_pending_bytes = 0.0; g_pending_flops = 0.0;
   cudaEventRecord(r.a, st);
   g_krecs.push_back(r);
   g_kopen = (int)g_krecs.size() - 1;
@@ -93,8 +94,8 @@ extern "C" int sard_prof_kernels_enable(int capacity) {
   if (capacity > 0) g_krecs.reserve(capacity);
   return 0;
 }
-// names: '\n'-separated kernel names in id order (truncated to names_len); rows[i*5..] = {name id, stream ordinal, start ms,
-// end ms, algorithmic bytes} relative to the first record.  Returns the number of rows and clears the records.
+// names: '\n'-separated kernel names in id order (truncated to names_len); rows[i*6..] = {name id, stream ordinal, start ms,
+// end ms, algorithmic bytes, algorithmic flops} relative to the first record.  Returns the number of rows and clears the records.
 extern "C" int sard_prof_kernels_collect(char* names, int names_len, double* rows, int capacity) {
   std::string all;
   for (const std::string& n : g_knames) { all += n; all += '\n'; }
@@ -110,7 +111,7 @@ extern "C" int sard_prof_kernels_collect(char* names, int names_len, double* row
       int sid = -1;
       for (size_t k = 0; k < streams.size(); ++k) if (streams[k] == r.st) sid = (int)k;
       if (sid < 0) { streams.push_back(r.st); sid = (int)streams.size() - 1; }
-      rows[n * 5 + 0] = r.name; rows[n * 5 + 1] = sid; rows[n * 5 + 2] = t0; rows[n * 5 + 3] = t1; rows[n * 5 + 4] = r.bytes;
+      rows[n * 6 + 0] = r.name; rows[n * 6 + 1] = sid; rows[n * 6 + 2] = t0; rows[n * 6 + 3] = t1; rows[n * 6 + 4] = r.bytes; rows[n * 6 + 5] = r.flops;
       ++n;
     }
   }

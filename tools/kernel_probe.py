@@ -21,9 +21,9 @@ from sard_b200.transform2act_agent import Transform2ActAgent  # noqa: E402
 
 def collect(lib, cap):
     names = C.create_string_buffer(1 << 16)
-    rows = (C.c_double * (5 * cap))()
+    rows = (C.c_double * (6 * cap))()
     n = lib.sard_prof_kernels_collect(names, len(names), rows, cap)
-    arr = np.frombuffer(rows, dtype=np.float64)[:5 * n].reshape(n, 5).copy()
+    arr = np.frombuffer(rows, dtype=np.float64)[:6 * n].reshape(n, 6).copy()
     return [s for s in names.value.decode().split('\n') if s], arr
 
 
@@ -89,7 +89,7 @@ def main():
     for sid in sorted(set(sel[:, 1].astype(int))):
         print(f'--- stream {sid}')
         prev = None
-        for nid, _, t0, t1, _b in sel[sel[:, 1] == sid]:
+        for nid, _, t0, t1, _b, _f in sel[sel[:, 1] == sid]:
             gap = (t0 - prev) * 1e3 if prev is not None else 0.0
             print(f'  {(t0 - t_mid) * 1e3:8.1f} us  +{(t1 - t0) * 1e3:6.1f} us  gap {gap:6.1f}  {names[int(nid)]}')
             prev = t1
