@@ -427,6 +427,18 @@ int sard_adam_update(float* stats, float inv_B, float inv_world, float inv_cat_n
                      double beta2, float* ctl_f, int* ctl_i, float* log_row, const SardAdamSeg* segs, int n_seg,
                      long long max_seg_len, float lr, float eps, sard_stream_t stream);
 
+/* Data-parallel gradient SUM over NVLink peer memory (the reference is single-process: this is the
+ * collective the transition-sharded update adds).  bufs_dev / pads_dev: DEVICE arrays of `world` pointers to every
+ * rank's gradient bucket and signal pad (symmetric allocations mapped into this process; the pad needs
+ * sard_allreduce_p2p_pad_bytes() zero-initialised bytes).  Reduces bucket[0:n_floats) in place on every rank:
+ * two-shot (rank r sums slice r in rank order with peer loads, then stores it to every rank), deterministic,
+ * bit-identical on all ranks; one kernel on `stream`, two in-kernel barriers whose expected values are
+ * first_barrier_value and first_barrier_value + 1 (the caller advances it by 2 per call).  Every rank must call it
+ * with the same arguments in the same order. */
+int sard_allreduce_p2p_pad_bytes(void);
+int sard_allreduce_p2p(const void* bufs_dev, const void* pads_dev, int rank, int world, long long n_floats,
+                       unsigned first_barrier_value, sard_stream_t stream);
+
 /* =====================================================================================
  * Network schedules: the whole forward/backward of one net over one run, launched from C++
  * (one host call per minibatch instead of ~100)

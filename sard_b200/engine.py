@@ -35,12 +35,83 @@ class Comm:
     def allreduce(self, t: torch.Tensor):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def lanes(self, n: int):
+        """``n`` more communicators over the same ranks (collective: every rank calls it, in the same order).  NCCL runs the
+        collectives of ONE communicator in issue order on one internal stream; the update issues collectives from four
+        independent chains (critic / policy x moments all-gather of minibatch k+1 / gradient all-reduce of minibatch k),
+        and on a single communicator an all-reduce queues behind an all-gather that is still waiting for its gather."""
+        if getattr(self, '_lanes', None) is None or len(self._lanes) < n:
+            ranks = list(range(self.world)) if self.group is None else self.dist.get_process_group_ranks(self.group)
+            self._lanes = [Comm(self.dist.new_group(ranks=ranks)) for _ in range(n)]
+        return self._lanes[:n]
+
+    def symmetric_bucket(self, n_floats: int, device):
+        """A zeroed fp32 buffer of ``n_floats`` allocated as symmetric memory and mapped into every rank of the group
+        (``torch.distributed._symmetric_memory``: allocation + handle exchange only), wrapped for the library's
+        peer-memory all-reduce.  Collective.  Returns ``(tensor, P2PAllReduce)`` or ``(tensor, None)`` when symmetric
+        memory is unavailable (the gradient all-reduce then goes through NCCL)."""
+        import os
+        if os.environ.get('SARD_P2P_ALLREDUCE', '1') == '0' or self.dist.get_backend(self.group) != 'nccl' or self.world > 8:
+            return torch.zeros(n_floats, dtype=torch.float32, device=device), None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = self.group if self.group is not None else self.dist.group.WORLD
+            name = g.group_name
+            import warnings
+            with warnings.catch_warnings():      # needed by torch < 2.8, a deprecated no-op afterwards
+                warnings.simplefilter('ignore')
+                try:
+                    symm.enable_symm_mem_for_group(name)
+                except Exception:                # noqa: BLE001
+                    pass
+            t = symm.empty(n_floats, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(t, group=name)
+            t.zero_()
+            p2p = P2PAllReduce(t, hdl, self)
+            ok = torch.ones(1, device=device)
+        except Exception as e:                 # noqa: BLE001
+            import warnings
+            warnings.warn(f'sard_b200: symmetric memory unavailable ({e!r}); gradient all-reduce through NCCL')
+            t, p2p, ok = torch.zeros(n_floats, dtype=torch.float32, device=device), None, torch.zeros(1, device=device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)       # all ranks or none
+        if float(ok.item()) < 1.0:
+            p2p = None
+        return t, p2p
+
+    def max_array(self, a: np.ndarray) -> np.ndarray:
+        """Element-wise maximum of a small host integer array over the ranks (host-synchronous)."""
+        dev = 'cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu'
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy()
+
     def min_int(self, v: int, device=None) -> int:
         """Minimum of a host integer over the ranks (one small collective; host-synchronous)."""
         dev = device if device is not None else ('cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu')
         t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return int(t.item())
+
+
+class P2PAllReduce:
+    """The library's peer-memory all-reduce (csrc/p2p.cu) bound to one symmetric gradient bucket."""
+    PAD_OFFSET = 1024          # bytes into the signal pad (the first KB is left to torch's own barrier channels)
+
+    def __init__(self, tensor, hdl, comm: Comm):
+        need = self.PAD_OFFSET + lib.sard_allreduce_p2p_pad_bytes()
+        if hdl.signal_pad_size < need:
+            raise RuntimeError(f'signal pad of {hdl.signal_pad_size} bytes < {need}')
+        self.tensor, self.hdl = tensor, hdl
+        self.rank, self.world = comm.rank, comm.world
+        dev = tensor.device
+        self.bufs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.pads = torch.tensor([int(p) + self.PAD_OFFSET for p in hdl.signal_pad_ptrs], dtype=torch.int64, device=dev)
+        self.seq = 0
+
+    def allreduce(self, n_floats: int, st: int):
+        check(lib.sard_allreduce_p2p(ptr(self.bufs), ptr(self.pads), self.rank, self.world, int(n_floats),
+                                     (2 * self.seq + 1) & 0xffffffff, st))
+        self.seq += 1
 
 
 class _EngineBase:
@@ -55,6 +126,16 @@ class _EngineBase:
         # 'none': zero_grad(set_to_none=True) of torch >= 2 (a stage absent from a minibatch is skipped by Adam);
         # 'zeros': torch < 2.0, the reference's pin (its gradients stay zero tensors, Adam keeps stepping from momentum)
         self.zero_grad_semantics = 'none'
+        self.comm: Optional[Comm] = None       # data parallel: set before the first sync (symmetric gradient bucket)
+        self.p2p: Optional[P2PAllReduce] = None
+
+    def _alloc_bucket(self, n: int, dev) -> torch.Tensor:
+        n = (n + 3) // 4 * 4
+        if self.comm is not None and self.comm.world > 1:
+            t, self.p2p = self.comm.symmetric_bucket(n, dev)
+            return t
+        self.p2p = None
+        return torch.zeros(n, dtype=torch.float32, device=dev)
 
     def _workspace(self, key, need: int) -> torch.Tensor:
         w = self.ws.get(key)
@@ -100,7 +181,7 @@ class ValueEngine(_EngineBase):
         if self.device != dev or not self.store.is_adopted():
             self.device = dev
             self.store.adopt(dev)
-            self.GA = torch.zeros(N_STATS + self.store.size, dtype=torch.float32, device=dev)
+            self.GA = self._alloc_bucket(N_STATS + self.store.size, dev)
             self.ws.clear(); self.mom_local.clear(); self.mom_all.clear()
             rebuilt = True
         m = self.module
@@ -169,8 +250,11 @@ class ValueEngine(_EngineBase):
         _, ma = self._moments('v', self.net.tower.D, world)
         self._call(arena, run, 1, PHASE_COMPUTE, 1.0 / B_global, ma, world)
 
-    def dp_allreduce(self, comm):
-        comm.allreduce(self.GA)
+    def dp_allreduce(self, comm, st: Optional[int] = None):
+        if self.p2p is not None:
+            self.p2p.allreduce(self.GA.numel(), st if st is not None else stream())
+        else:
+            comm.allreduce(self.GA)
 
     def train_step(self, arena: PackedRollout, run: Run, B_global: int, log_row: Optional[torch.Tensor] = None,
                    comm: Optional[Comm] = None):
@@ -178,7 +262,7 @@ class ValueEngine(_EngineBase):
         self.GA.zero_()
         self.run(arena, run, True, 1.0 / B_global, comm)
         if comm is not None and comm.world > 1:
-            comm.allreduce(self.GA)
+            self.dp_allreduce(comm)
         self.adam(B_global, log_row)
 
     # -- software-pipelined single-GPU step: the gather + RunningNorm moments of minibatch k+1 (they read only the
@@ -300,11 +384,16 @@ class PolicyEngine(_EngineBase):
             S = len(live)
             sizes.append(sum(S * (t.out_dim * t.input_dim + t.out_dim) + 8 for t in self._tables(s)))
         self.slot_of_index = torch.from_numpy(slot).to(dev)
-        total = N_STATS + self.store.size
-        for s in range(3):
+        # bucket order: statistics | dense | control tables | attr tables | skel tables.  With batch_design ~23 of 24
+        # minibatches hold execution-stage graphs only, so the data-parallel all-reduce covers the prefix that ends
+        # with the last ACTIVE stage's tables (a third of the bucket) instead of all of it
+        total = (N_STATS + self.store.size + 3) // 4 * 4
+        self.gt_end = [0, 0, 0]
+        for s in (2, 1, 0):
             self.gt_off[s] = total
             total += (sizes[s] + 3) // 4 * 4
-        self.GA = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.gt_end[s] = total
+        self.GA = self._alloc_bucket(total, dev)
         net = SardPolicyNet()
         _encoders(self.store, (m.hfield_enc, m.obj_enc, m.goal_enc), net.enc)
         net.nconst = m.sym_embed_dim if m.enable_infer else 0
@@ -412,8 +501,17 @@ class PolicyEngine(_EngineBase):
                 _, ma = self._moments(s, net.stage[s].tower.D, world)
                 self._empty_norm_update(s, ma, world)
 
-    def dp_allreduce(self, comm):
-        comm.allreduce(self.GA)
+    def dp_allreduce(self, comm, active_global: Optional[Sequence[bool]] = None, st: Optional[int] = None):
+        """SUM all-reduce of the gradient bucket: the prefix up to the last active stage's tables (the rest is zero on
+        every rank: stages absent from the global minibatch wrote nothing)."""
+        if active_global is None or active_global[0] or not any(active_global):
+            end = self.GA.numel()
+        else:
+            end = max(self.gt_end[s] for s in range(3) if active_global[s])
+        if self.p2p is not None:
+            self.p2p.allreduce(end, st if st is not None else stream())
+        else:
+            comm.allreduce(self.GA[:end])
 
     def train_step(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, skel_nodes_global: int,
                    active_global: Sequence[bool], clip_eps: float, max_norm: float, clip_first_only: bool,
@@ -431,7 +529,7 @@ class PolicyEngine(_EngineBase):
                 self._empty_norm_update(s, ma, comm.world)
         world = 1
         if comm is not None and comm.world > 1:
-            comm.allreduce(self.GA)
+            self.dp_allreduce(comm, active_global)
             world = comm.world
         self.adam(B_global, skel_nodes_global, active_global, max_norm, clip_first_only, world, log_row)
 
@@ -466,7 +564,7 @@ class PolicyEngine(_EngineBase):
             run = runs[s]
             if run is None:
                 if world > 1 and active_global[s]:
-                    self._empty_norm_update(s, self.mom_all[(s, slot)], world)
+                    self._empty_norm_update(s, self.mom_all[(s, slot)], world, st)
                 continue
             ws, ml, ma = self.ws[(s, slot)], self.mom_local[(s, slot)], self.mom_all.get((s, slot))
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_COMPUTE, clip_eps,
@@ -502,6 +600,7 @@ class PolicyEngine(_EngineBase):
         check(lib.sard_adam_apply(ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.betas[0], opt.betas[1], opt.eps, mask,
                                   ptr(opt.ctl_f), ptr(opt.ctl_i), st))
 
-    def _empty_norm_update(self, s, ma, world):
+    def _empty_norm_update(self, s, ma, world, st=None):
         tw = self.net.stage[s].tower
-        check(lib.sard_norm_update(ptr(ma), world, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, stream()))
+        check(lib.sard_norm_update(ptr(ma), world, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv,
+                                   st if st is not None else stream()))

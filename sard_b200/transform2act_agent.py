@@ -309,7 +309,8 @@ class Transform2ActAgent:
                              self.device, pin=True)
 
     def _prepare(self, arena: PackedRollout):
-        self.policy_net.prepare(arena, self.optimizer_policy)
+        self.policy_net.engine.comm = self.value_net.engine.comm = self.comm
+        self.policy_net.prepare(arena, self.optimizer_policy, comm=self.comm)
         self.value_net.prepare(self.optimizer_value)
         if self.zero_grad_semantics not in ('none', 'zeros'):
             raise ValueError("zero_grad_semantics must be 'none' or 'zeros'")
@@ -419,6 +420,7 @@ class Transform2ActAgent:
         main = torch.cuda.current_stream(self.device)
         sv, sp = self._net_streams()
         sv_h, sp_h = sv.cuda_stream, sp.cuda_stream
+        lanes = comm.lanes(4) if (world > 1 and os.environ.get('SARD_COMM_LANES', '1') != '0') else [comm] * 4
         if self.overlap_nets and self.prefetch_gather:
             veng.GA.zero_(); peng.GA.zero_()         # the fused optimiser tail keeps the buckets zeroed from here on
         sv.wait_stream(main); sp.wait_stream(main)
@@ -445,29 +447,35 @@ class Transform2ActAgent:
                 vrun, pruns = plan.value_run(k), plan.policy_runs(k)
                 skel_nodes = int(counts[k, 3])
                 if world > 1 and self.overlap_nets and self.prefetch_gather:
-                    # as below, and the moments all-gathers of minibatch k+1 leave the critical path with the gather;
-                    # every rank issues the same sequence of collectives (NCCL runs them in issue order)
+                    # as below, and the moments all-gathers of minibatch k+1 leave the critical path with the gather.
+                    # Each of the four chains of collectives has its own communicator (Comm.lanes); every rank issues
+                    # the same sequence on each of them.
                     slot = k & 1
                     act_of = lambda j: [bool(counts[j, s] > 0) for s in range(3)]
+                    c_vr, c_pr, c_vg, c_pg = lanes
                     if k == 0:
-                        self._issue_prefetch(arena, plan, 0, 0, main, comm, act_of(0))
+                        self._issue_prefetch(arena, plan, 0, 0, main, (c_vg, c_pg), act_of(0))
                     if k + 1 < plan.n_mb:
-                        self._issue_prefetch(arena, plan, k + 1, slot ^ 1, None, comm, act_of(k + 1))
+                        self._issue_prefetch(arena, plan, k + 1, slot ^ 1, None, (c_vg, c_pg), act_of(k + 1))
                     gv, gp, ready, free = self._gather_ctx
-                    with torch.cuda.stream(sv):
-                        sv.wait_event(ready[0][slot])
-                        veng.compute_prefetched(arena, vrun, B_glob, slot, world)
-                    with torch.cuda.stream(sp):
-                        sp.wait_event(ready[1][slot])
-                        peng.compute_prefetched(arena, pruns, B_glob, self.clip_epsilon, slot, world, active)
-                    with torch.cuda.stream(sv):
-                        veng.dp_allreduce(comm)
-                        veng.adam(B_glob, vlog[step], fused=True)
-                        free[0][slot].record(sv)
-                    with torch.cuda.stream(sp):
-                        peng.dp_allreduce(comm)
-                        peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step], fused=True)
-                        free[1][slot].record(sp)
+                    sv.wait_event(ready[0][slot])
+                    veng.compute_prefetched(arena, vrun, B_glob, slot, world, st=sv_h)
+                    sp.wait_event(ready[1][slot])
+                    peng.compute_prefetched(arena, pruns, B_glob, self.clip_epsilon, slot, world, active, st=sp_h)
+                    if veng.p2p is not None:                 # one kernel over peer memory on the net's own stream
+                        veng.dp_allreduce(c_vr, st=sv_h)
+                    else:
+                        with torch.cuda.stream(sv):
+                            veng.dp_allreduce(c_vr)
+                    veng.adam(B_glob, vlog[step], fused=True, st=sv_h)
+                    free[0][slot].record(sv)
+                    if peng.p2p is not None:
+                        peng.dp_allreduce(c_pr, active, st=sp_h)
+                    else:
+                        with torch.cuda.stream(sp):
+                            peng.dp_allreduce(c_pr, active)
+                    peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step], fused=True, st=sp_h)
+                    free[1][slot].record(sp)
                 elif world > 1 and self.overlap_nets:
                     # phases interleaved so both nets' collectives are issued back to back (NCCL runs them in
                     # issue order) while their compute overlaps on the two streams
@@ -487,7 +495,7 @@ class Transform2ActAgent:
                         veng.dp_allreduce(comm)
                         veng.adam(B_glob, vlog[step])
                     with torch.cuda.stream(sp):
-                        peng.dp_allreduce(comm)
+                        peng.dp_allreduce(comm, active)
                         peng.adam(B_glob, skel_nodes, active, 40.0, self.clip_first_step_only, world, plog[step])
                 elif self.overlap_nets and self.prefetch_gather:
                     # gather + RunningNorm moments of minibatch k+1 run on the gather streams (second workspace) while
@@ -623,11 +631,12 @@ class Transform2ActAgent:
                     eng.prefetch(arena, run, slot, st=g.cuda_stream)
                 ready[net][slot].record(g)
                 continue
+            c = comm[net] if isinstance(comm, tuple) else comm
             with torch.cuda.stream(g):
                 if net == 0:
-                    eng.prefetch(arena, run, slot, comm)
+                    eng.prefetch(arena, run, slot, c)
                 else:
-                    eng.prefetch(arena, run, slot, comm, active)
+                    eng.prefetch(arena, run, slot, c, active)
                 ready[net][slot].record(g)
 
     def _summarise(self, arena: PackedRollout, logs: np.ndarray, last_perm: np.ndarray) -> dict:

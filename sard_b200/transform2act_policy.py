@@ -128,9 +128,16 @@ class Transform2ActPolicy(nn.Module):
             return 2, 3                      # slices [2:3] and the empty [5:-1]
         return 2, self.attr_action_dim - 1   # slice(2, -1)
 
-    def prepare(self, arena: Optional[PackedRollout] = None, opt=None) -> PolicyEngine:
+    def prepare(self, arena: Optional[PackedRollout] = None, opt=None, comm=None) -> PolicyEngine:
         eng = self.engine
         live = [arena.live_indices(s) for s in range(3)] if arena is not None else None
+        if live is not None and comm is not None and comm.world > 1:
+            # data parallel: the compact table-gradient layout (slot_of_index) must be the same on every rank, so the
+            # live body indices are the union over the ranks' rollouts
+            mask = np.zeros((3, self.max_index), dtype=np.int64)
+            for s in range(3):
+                mask[s, np.asarray(live[s], dtype=np.int64)] = 1
+            live = [np.flatnonzero(m) for m in comm.max_array(mask)]
         eng.sync(opt if opt is not None else eng.opt, live)
         if self.enable_infer:
             eng.set_embeds(self.group.get_cur_subgroup_embeds())
