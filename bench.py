@@ -67,6 +67,10 @@ def parse():
     ap.add_argument('--epochs', type=int, default=10)
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --transitions / --mini-batch per GPU; strong: the global update split 1/N per rank (SURVEY 8e)')
+    ap.add_argument('--sweep-nodes', type=int, default=0,
+                    help='BASELINE config 5: graphs of this many nodes (random trees, execution stage), hidden width 256 '
+                         '(--env names the observation shape); 0 = the env\'s own ant morphologies')
+    ap.add_argument('--sweep-hidden', type=int, default=256)
     ap.add_argument('--ref-sample', type=int, default=2048, help='transitions of the bounded reference / CPU-baseline sample')
     ap.add_argument('--ref-epochs', type=int, default=4)
     ap.add_argument('--kernels-out', default='', help='write the per-kernel table (JSON) here')
@@ -244,7 +248,11 @@ def per_rank(args, world):
 
 def workload_config(args, world):
     t, m = per_rank(args, world)
-    return {'workload': f'{args.env}.yml PPO update_params, synthetic rollouts of the env obs/graph shape',
+    wl = f'{args.env}.yml PPO update_params, synthetic rollouts of the env obs/graph shape'
+    if getattr(args, 'sweep_nodes', 0) > 0:
+        wl = (f'scale sweep: {args.sweep_nodes}-node random-tree graphs (execution stage), hidden {args.sweep_hidden}, '
+              f'{args.env} observation shape')
+    return {'workload': wl, 'sweep_nodes': getattr(args, 'sweep_nodes', 0),
             'env': args.env, 'transitions_per_gpu': t, 'mini_batch_per_gpu': m,
             'optim_epochs': args.epochs, 'global_mini_batch': m * world, 'global_transitions': t * world,
             'transition_updates_per_step_per_gpu': (t // m) * m * args.epochs,
@@ -325,12 +333,18 @@ def run_native(args):
     shape = synthetic.ENV_SHAPES[args.env]
     n_trans, n_mini = per_rank(args, world)          # strong scaling: the global update split 1/N per rank
     d = dict(DERL_YML)
+    if args.sweep_nodes > 0:
+        from sard_b200.config import sweep_yml
+        d = sweep_yml(args.sweep_hidden)
     d.update(min_batch_size=n_trans, mini_batch_size=n_mini, num_optim_epoch=args.epochs)
     cfg = Config(d)
     torch.manual_seed(0)                       # identical initial weights on every rank
     np.random.seed(1234)                       # identical shuffle stream on every rank
     agent = Transform2ActAgent(cfg, torch.float32, dev, 0, 1, env=synthetic.SyntheticEnv(shape), comm=comm)
-    roll = synthetic.generate_rollout(shape, n_trans, seed=1234 + rank, dtype=np.float32)
+    if args.sweep_nodes > 0:
+        roll = synthetic.generate_sweep_rollout(shape, n_trans, args.sweep_nodes, seed=1234 + rank)
+    else:
+        roll = synthetic.generate_rollout(shape, n_trans, seed=1234 + rank, dtype=np.float32)
     upd_per_step = (n_trans // n_mini) * n_mini * args.epochs
 
     def barrier():

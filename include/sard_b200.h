@@ -358,6 +358,14 @@ int sard_cat_loss(const SardPolicyLoss* a, sard_stream_t stream);
  * mean_j(0.5 + 0.5 log 2pi + log_std[j]) is added to stats[4] (policy.py:396,405). */
 int sard_loss_reduce(const float* gstat, int B, int W, float* stats, float* dlogstd, int d,
                      const float* log_std_for_entropy, sard_stream_t stream);
+/* Value head + MSE loss + the head's backward-data, fused (transform2act_critic.py:107-108, agent_pg.py:21-22):
+ * v[b] = cat[b,:K] . w + *bias; values_out[ids[b]] = v (optional); with `returns`: e = v - returns[ids[b]],
+ * dv[b] = 2 e inv_B, sq_err[b] = e^2 and (optional) dcat[b,c] = dv w[c] act'(cat[b,c]) with act' of `act0` on the first
+ * dsplit columns and ReLU' on the rest. */
+int sard_value_head(const float* cat, int ldcat, const float* w, const float* bias, int B, int K, int dsplit, int act0,
+                    const int* ids, const float* returns, float inv_B, float* v, float* dv, float* sq_err,
+                    float* values_out, float* dcat, int ld_dcat, sard_stream_t stream);
+
 /* Critic loss mean((v-R)^2) and dv (khrylib/rl/agents/agent_pg.py:21-22): dv[b] = 2 (v[b]-returns[ids[b]]) inv_B;
  * partial[b] = (v-R)^2; eval mode (returns==NULL) writes values_out[ids[b]] = v[b]. */
 int sard_value_loss(const float* v, const int* ids, int B, const float* returns, float inv_B,

@@ -154,6 +154,7 @@ _PROTOS = {
     'sard_cat_loss': (ci, [P(SardPolicyLoss), vp]),
     'sard_loss_reduce': (ci, [vp, ci, ci, vp, vp, ci, vp, vp]),
     'sard_value_loss': (ci, [vp, vp, ci, vp, cf, vp, vp, vp, vp]),
+    'sard_value_head': (ci, [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, cf, vp, vp, vp, vp, vp, ci, vp]),
     'sard_gae': (ci, [vp, vp, vp, ci, cd, cd, vp, vp, vp, vp]),
     'sard_gae_f64': (ci, [vp, vp, vp, ci, cd, cd, vp, vp, vp, vp]),
     'sard_allreduce_p2p_pad_bytes': (ci, []),

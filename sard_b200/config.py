@@ -79,3 +79,15 @@ def derl_config(**overrides) -> Config:
     d = copy.deepcopy(DERL_YML)
     d.update(overrides)
     return Config(d)
+
+
+def sweep_yml(hidden: int = 256) -> dict:
+    """derl.yml with every hidden width set to ``hidden`` (BASELINE.json config 5: "hidden 256")."""
+    d = copy.deepcopy(DERL_YML)
+    gnn = {'layer_type': 'graph_conv', 'hdims': [hidden] * 3, 'aggr': 'add', 'bias': True}
+    imlp = {'hdims': [hidden, hidden], 'rescale_linear': True, 'max_index': 256}
+    for st in ('skel', 'control', 'attr'):
+        d['policy_specs'][f'{st}_gnn_specs'] = copy.deepcopy(gnn)
+        d['policy_specs'][f'{st}_index_mlp'] = copy.deepcopy(imlp)
+    d['value_specs']['gnn_specs'] = copy.deepcopy(gnn)
+    return d

@@ -141,6 +141,7 @@ struct TowerBufs {
   bool tc_shape;                // widths served by the fused tensor-core tower: its scratch is carved
   bool tc_on;                   // ... and this run's graphs are small enough (set per run from arena->max_nodes)
   TowerTcBufs tc;
+  TowerNormStep norm;           // RunningNorm step of this run, launched with the weight pre-split when tc_on
 };
 
 // the fused tower serves the default engine when the widths fit (every layer 64 wide, D <= 127, <= 3 layers)
@@ -172,6 +173,7 @@ void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBu
   t.tc_shape = tower_tc_shape(tw);
   t.tc_on = false;
   memset(&t.tc, 0, sizeof(t.tc));
+  memset(&t.norm, 0, sizeof(t.norm));
   if (t.tc_shape) {
     const int nn = n > 0 ? n : 1;
     t.tc.wsplit = b.a256(sard_tower_tc_wsplit_floats(tw.L));
@@ -216,6 +218,19 @@ int tower_gather(const SardTower& tw, const SardArena* arena, const SardSel* sel
   return 0;
 }
 
+// RunningNorm step of a compute phase: with the fused tower it rides in the pre-split launch, otherwise its own kernel
+int tower_norm_step(const SardTower& tw, const SardArena* arena, int n, TowerBufs& t, bool upd, const double* recs, int n_records,
+                    sard_stream_t st) {
+  tower_tc_select(t, tw, arena, n);
+  if (t.tc_on) {
+    t.norm.mode = upd ? 1 : 2; t.norm.n_records = n_records; t.norm.records = recs;
+    t.norm.mean = tw.mean; t.norm.var = tw.var; t.norm.std = tw.std; t.norm.inv = tw.inv; t.norm.count = tw.count;
+    return 0;
+  }
+  if (upd) return sard_norm_update(recs, n_records, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, st);
+  return sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st);
+}
+
 // normalise + in_fc + GraphConv layers
 int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, const SardSel* sel, TowerBufs& t,
                   sard_stream_t st) {
@@ -223,7 +238,7 @@ int tower_forward(const SardTower& tw, const float* P, const SardArena* arena, c
   tower_tc_select(t, tw, arena, n);
   if (t.tc_on) {
     // normalise + in_fc + every GraphConv layer in one tcgen05 launch (tower_tc.cu); t.x stays un-normalised
-    SARD_TRY(sard_tower_tc_presplit(tw, P, t.tc.wsplit, st));
+    SARD_TRY(sard_tower_tc_presplit(tw, P, t.tc.wsplit, t.norm, st));
     site(K_GCONV, 0);
     return sard_tower_tc_forward(tw, P, arena, sel, t.tc, t.x, t.ldx, t.nd_graph, t.nd_arena, t.hout, t.dz[tw.L] != nullptr, st);
   }
@@ -469,11 +484,9 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     }
   }
   if (!(phase & SARD_PHASE_COMPUTE)) return 0;
-  if (upd) {
+  {
     const double* recs = moments_all ? moments_all : (moments_local ? moments_local : vb.rec);
-    SARD_TRY(sard_norm_update(recs, moments_all ? n_records : 1, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, st));
-  } else {
-    SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
+    SARD_TRY(tower_norm_step(tw, arena, n, vb.t, upd, recs, moments_all ? n_records : 1, st));
   }
   // the ObsEncoders only need the arena: they run beside the tower and are joined before the value head
   SideCtx* side = side_for(as_stream(st));
@@ -495,32 +508,22 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   }
   SARD_REQUIRE(net->n_mlp > 0, "critic without mlp is not supported");
   SARD_TRY(side_join(side));
-  {
-    SardGemm g = gemm0();
-    g.A = vb.cat; g.lda = vb.ldcat; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat; g.bias = P + net->head.b;
-    g.M = B; g.N = 1; g.R = vb.ldcat; g.Y = vb.v; g.ldy = 1;
-    SARD_REQUIRE(net->head.in == vb.ldcat, "value head width");
-    site(K_HEAD, 0);
-    SARD_TRY(sard_linear_fwd(&g, st));
-  }
-  if (!bwd) return sard_value_loss(vb.v, sel->ids, B, nullptr, 0.f, nullptr, nullptr, arena->values, st);
-
-  SARD_TRY(sard_value_loss(vb.v, sel->ids, B, arena->returns, inv_B_global, vb.dv, vb.sq, nullptr, st));
-  if (sq_err_sum) SARD_TRY(sard_loss_reduce(vb.sq, B, 1, sq_err_sum, nullptr, 0, nullptr, st));
-  // head backward
-  {
+  SARD_REQUIRE(net->head.in == vb.ldcat && net->head.out == 1, "value head width");
+  // value head + loss + the head's backward-data in one launch
+  site(K_HEAD, 0);
+  SARD_TRY(sard_value_head(vb.cat, vb.ldcat, P + net->head.w, P + net->head.b, B, vb.ldcat, vb.ldcat - 3 * SARD_EXT_DIM,
+                           net->mlp[net->n_mlp - 1].act, sel->ids, bwd ? arena->returns : nullptr, inv_B_global, vb.v,
+                           bwd ? vb.dv : nullptr, bwd ? vb.sq : nullptr, bwd ? nullptr : arena->values, bwd ? vb.dcat : nullptr,
+                           vb.ldcat, st));
+  if (!bwd) return 0;
+  // the summed squared error only feeds the log: off the launching stream
+  if (sq_err_sum) SARD_TRY(sard_loss_reduce(vb.sq, B, 1, sq_err_sum, nullptr, 0, nullptr, wg_stream(side, st, 1)));
+  {   // head weight gradient
     SardWGrad w = wgrad0();
     w.P = vb.dv; w.ldp = 1; w.Q = vb.cat; w.ldq = vb.ldcat; w.M = B; w.N1 = 1; w.N2 = vb.ldcat;
     w.dW0 = G + net->head.w; w.ldw0 = vb.ldcat; w.w_split = vb.ldcat; w.db = G + net->head.b; w.partials = vb.wg2;
     site(K_HEAD, 2);
     SARD_TRY(sard_linear_bwd_weight(&w, wg_stream(side, st, 1)));
-    SardGemm g = gemm0();
-    g.A = vb.dv; g.lda = 1; g.B0 = P + net->head.w; g.ldb0 = vb.ldcat; g.b_split = vb.ldcat;
-    g.M = B; g.N = vb.ldcat; g.R = 1; g.Y = vb.dcat; g.ldy = vb.ldcat;
-    g.Dact = vb.cat; g.ldd = vb.ldcat; g.dact0 = net->mlp[net->n_mlp - 1].act; g.dact1 = SARD_ACT_RELU;
-    g.dsplit = vb.ldcat - 3 * SARD_EXT_DIM;
-    site(K_HEAD, 1);
-    SARD_TRY(sard_linear_bwd_data(&g, st));
   }
   // the encoders' backward ends in weight gradients only: all of it runs beside the MLP / tower backward
   SARD_TRY(encoders_backward(net->enc, P, G, arena, sel, vb.e1, vb.dcat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
@@ -688,11 +691,9 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
                                        sb.grp_ptr, sb.tiles, sb.chunks, sb.grp_chunk_ptr, sb.counts, sb.sort_scratch, st));
   }
   if (!(phase & SARD_PHASE_COMPUTE)) return 0;
-  if (upd) {
+  {
     const double* recs = moments_all ? moments_all : (moments_local ? moments_local : sb.rec);
-    SARD_TRY(sard_norm_update(recs, moments_all ? n_records : 1, tw.D, tw.mean, tw.var, tw.std, tw.count, tw.inv, st));
-  } else {
-    SARD_TRY(sard_norm_prepare_eval(tw.std, tw.D, tw.inv, st));
+    SARD_TRY(tower_norm_step(tw, arena, n, sb.t, upd, recs, moments_all ? n_records : 1, st));
   }
   // the ObsEncoders only need the arena and the hi/lo pair copies of the live weight slabs only the weights (they change
   // with every optimiser step): both run beside the tower

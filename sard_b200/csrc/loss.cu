@@ -268,3 +268,54 @@ extern "C" int sard_value_loss(const float* v, const int* ids, int B, const floa
   SARD_LAUNCH_OK("value_loss_kernel");
   return 0;
 }
+
+
+// Value head, loss and the head's backward-data in one launch (one warp per root row):
+//   v = cat . w + b                                   (transform2act_critic.py:107-108, value_head)
+//   e = v - returns[gid],  dv = 2 e / B_global,  sq_err = e^2          (agent_pg.py:21-22, MSE)
+//   dcat[c] = dv * w[c] * act'(cat[c])     act' = act0 on the first dsplit columns (MLP output), ReLU on the rest (ObsEncoders)
+// Replaces three dependent launches (skinny forward, value_loss, skinny backward) on the critic's chain.
+__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ cat, int ldcat, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int K, int dsplit, int act0,
+                                                         const int* __restrict__ ids, const float* __restrict__ returns, float inv_B,
+                                                         float* __restrict__ v_out, float* __restrict__ dv_out, float* __restrict__ sq_err,
+                                                         float* __restrict__ values_out, float* __restrict__ dcat, int ld_dcat) {
+  pdl_sync();
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = cat + (size_t)b * ldcat;
+  float s = 0.f;
+  for (int c = lane; c < K; c += 32) s = fmaf(row[c], __ldg(w + c), s);
+  s = warp_sum(s) + __ldg(bias);
+  const int gid = ids[b];
+  if (lane == 0) {
+    if (v_out) v_out[b] = s;
+    if (values_out) values_out[gid] = s;
+  }
+  if (!returns) return;
+  const float e = s - returns[gid];
+  const float dv = 2.f * e * inv_B;
+  if (lane == 0) {
+    if (dv_out) dv_out[b] = dv;
+    if (sq_err) sq_err[b] = e * e;
+  }
+  if (!dcat) return;
+  float* drow = dcat + (size_t)b * ld_dcat;
+  for (int c = lane; c < K; c += 32) {
+    const float y = row[c];
+    const float g = c < dsplit ? act_grad_from_output(y, act0) : (y > 0.f ? 1.f : 0.f);
+    drow[c] = dv * __ldg(w + c) * g;
+  }
+}
+
+extern "C" int sard_value_head(const float* cat, int ldcat, const float* w, const float* bias, int B, int K, int dsplit, int act0,
+                               const int* ids, const float* returns, float inv_B, float* v, float* dv, float* sq_err,
+                               float* values_out, float* dcat, int ld_dcat, sard_stream_t stream) {
+  if (B <= 0) return 0;
+  SARD_REQUIRE(K > 0 && ldcat >= K && (!dcat || ld_dcat >= K), "value head: widths");
+  sard_prof_bytes(4.0 * B * (double)K * (dcat ? 3.0 : 1.0));
+  sard_launch(value_head_kernel, ceil_div((long long)B * 32, 256), 256, 0, as_stream(stream), cat, ldcat, w, bias, B, K, dsplit, act0,
+              ids, returns, inv_B, v, dv, sq_err, values_out, dcat, ld_dcat);
+  SARD_LAUNCH_OK("value_head_kernel");
+  return 0;
+}

@@ -5,6 +5,7 @@
 // come out with variance exactly 0 like the reference's fp64 var_mean, and are merged with the
 // pairwise (Chan) formula in fp64 in a fixed order -> deterministic and rank-count independent.
 #include "common.cuh"
+#include "norm.cuh"
 
 #define NORM_CHUNK 128
 
@@ -59,17 +60,6 @@ __global__ void norm_moments_kernel(const float* __restrict__ x, int ldx, int n,
   }
 }
 
-struct Mom { double n, mean, m2; };
-__device__ __forceinline__ Mom mom_merge(Mom a, Mom b) {
-  if (b.n == 0.0) return a;
-  if (a.n == 0.0) return b;
-  const double n = a.n + b.n, d = b.mean - a.mean;
-  Mom r;
-  r.n = n;
-  r.mean = a.mean + d * (b.n / n);
-  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / n);
-  return r;
-}
 
 // one warp per column: lanes take chunks round-robin, then a fixed shuffle tree
 __global__ void norm_merge_chunks_kernel(const float* __restrict__ partials, int n, int D, int nchunks,
@@ -123,37 +113,7 @@ __global__ void norm_update_kernel(const double* __restrict__ records, int n_rec
                                    float* __restrict__ mean, float* __restrict__ var, float* __restrict__ std,
                                    long long* __restrict__ count, float* __restrict__ inv) {
   pdl_sync();
-  const long long n_old = *count;
-  const int stride = 1 + 2 * D;
-  double m_total = 0.0;
-  for (int k = 0; k < n_records; ++k) m_total += records[(size_t)k * stride];
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    Mom acc = {0.0, 0.0, 0.0};
-    for (int k = 0; k < n_records; ++k) {
-      Mom b;
-      b.n = records[(size_t)k * stride];
-      b.mean = records[(size_t)k * stride + 1 + c];
-      b.m2 = records[(size_t)k * stride + 1 + D + c];
-      acc = mom_merge(acc, b);
-    }
-    if (acc.n > 0.0) {
-      const double mean_x = acc.mean, var_x = acc.m2 / acc.n;   // biased (unbiased=False)
-      const double w = (double)n_old / (acc.n + (double)n_old);
-      const double mu = (double)mean[c], v = (double)var[c];
-      const double dm = mean_x - mu;
-      const double v_new = w * v + (1.0 - w) * var_x + w * (1.0 - w) * dm * dm;
-      const double mu_new = w * mu + (1.0 - w) * mean_x;
-      const float sd = (float)sqrt(v_new);
-      var[c] = (float)v_new;
-      mean[c] = (float)mu_new;
-      std[c] = sd;
-      inv[c] = 1.0f / (sd + 1e-8f);
-    } else {
-      inv[c] = 1.0f / (std[c] + 1e-8f);
-    }
-  }
-  if (threadIdx.x == 0) *count = n_old + (long long)(m_total + 0.5);
+  norm_update_body(records, n_records, D, mean, var, std, count, inv);
 }
 
 extern "C" int sard_norm_update(const double* records, int n_records, int D, float* mean, float* var, float* std,

@@ -18,6 +18,7 @@
 //   tower_wgrad_reduce_kernel  adds the per-chunk partial products in chunk order (deterministic) into the gradient buffer.
 #include "tc.cuh"
 #include "tower_tc.cuh"
+#include "norm.cuh"
 #include <string.h>
 
 #define TT_THREADS 320          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: row workers (2 per 32-row quarter)
@@ -58,10 +59,20 @@ int sard_tower_tc_tiles(const SardArena* arena, const SardSel* sel, const TowerT
 // ------------------------------------------------------------------------------------------ weights
 // wsplit: block 0 = in_fc W [64][hi 128 | lo 128] (k >= D zero); blocks 1..L = forward GraphConv operands
 // [W_l ; W_r] as [128][hi 64 | lo 64]; blocks 1+L..2L = adjoint operands [W_l^T ; W_r^T] likewise.
-struct TtSplitParams { const float* P; long long in_w, wl[TT_MAXL], wr[TT_MAXL]; int D, L; float* out; };
+struct TtSplitParams { const float* P; long long in_w, wl[TT_MAXL], wr[TT_MAXL]; int D, L; float* out; TowerNormStep norm; };
 __global__ void __launch_bounds__(256) tower_presplit_kernel(const TtSplitParams p) {
   pdl_sync();
   const int blk = blockIdx.y;
+  if (blk == 1 + 2 * p.L) {
+    // the RunningNorm step of this run rides along as one more block row (one launch fewer on the chain): running
+    // update from the moment records (train) or inv = 1 / (std + 1e-8) (eval); the forward kernel follows in stream order
+    if (blockIdx.x != 0) return;
+    const TowerNormStep& q = p.norm;
+    if (q.mode == 1) norm_update_body(q.records, q.n_records, p.D, q.mean, q.var, q.std, q.count, q.inv);
+    else if (q.mode == 2)
+      for (int c = threadIdx.x; c < p.D; c += blockDim.x) q.inv[c] = 1.0f / (q.std[c] + 1e-8f);
+    return;
+  }
   float* o = p.out + (size_t)blk * TT_WS;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TT_WS / 2; e += gridDim.x * blockDim.x) {
     float v;
@@ -83,11 +94,12 @@ __global__ void __launch_bounds__(256) tower_presplit_kernel(const TtSplitParams
   }
 }
 long long sard_tower_tc_wsplit_floats(int L) { return (long long)(1 + 2 * L) * TT_WS; }
-int sard_tower_tc_presplit(const SardTower& tw, const float* P, float* wsplit, sard_stream_t stream) {
+int sard_tower_tc_presplit(const SardTower& tw, const float* P, float* wsplit, const TowerNormStep& norm, sard_stream_t stream) {
   TtSplitParams p;
-  p.P = P; p.in_w = tw.in_w; p.D = tw.D; p.L = tw.L; p.out = wsplit;
+  p.P = P; p.in_w = tw.in_w; p.D = tw.D; p.L = tw.L; p.out = wsplit; p.norm = norm;
   for (int l = 0; l < tw.L; ++l) { p.wl[l] = tw.wl[l]; p.wr[l] = tw.wr[l]; }
-  sard_launch(tower_presplit_kernel, dim3(32, 1 + 2 * tw.L), 256, 0, as_stream(stream), p);   // one element per thread: no rolled load -> store loop
+  // one element per thread (no rolled load -> store loop); + one block row for the RunningNorm step when there is one
+  sard_launch(tower_presplit_kernel, dim3(32, 1 + 2 * tw.L + (norm.mode ? 1 : 0)), 256, 0, as_stream(stream), p);
   SARD_LAUNCH_OK("tower_presplit_kernel");
   return 0;
 }

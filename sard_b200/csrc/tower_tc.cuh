@@ -23,6 +23,14 @@ struct TowerTcBufs {
   float* partials;              // [num_chunks, 128, 448]
 };
 
+// RunningNorm step fused into the pre-split launch: mode 0 none, 1 running update from `records`, 2 eval (inv from std)
+struct TowerNormStep {
+  int mode, n_records;
+  const double* records;
+  float *mean, *var, *std, *inv;
+  long long* count;
+};
+
 bool sard_tower_tc_supported(const SardTower& tw, int max_nodes);
 inline int sard_tower_tc_span(int max_nodes) { return TT_TILE - (max_nodes > 1 ? max_nodes - 1 : 0); }
 long long sard_tower_tc_wsplit_floats(int L);
@@ -31,7 +39,7 @@ int sard_tower_tc_chunk_rows(int n);
 // tile table of a run (gather phase): tile_first[t] for t <= num_tiles
 int sard_tower_tc_tiles(const SardArena* arena, const SardSel* sel, const TowerTcBufs& tb, const int* nd_graph, const int* nd_arena,
                         sard_stream_t stream);
-int sard_tower_tc_presplit(const SardTower& tw, const float* P, float* wsplit, sard_stream_t stream);
+int sard_tower_tc_presplit(const SardTower& tw, const float* P, float* wsplit, const TowerNormStep& norm, sard_stream_t stream);
 // x: gathered, un-normalised node features [n, ldx]; hout: [n, 64] output of the last layer
 int sard_tower_tc_forward(const SardTower& tw, const float* P, const SardArena* arena, const SardSel* sel, const TowerTcBufs& tb,
                           const float* x, int ldx, const int* nd_graph, const int* nd_arena, float* hout, bool train,

@@ -333,6 +333,7 @@ class PolicyEngine(_EngineBase):
         self.consts = None
         self.sq_scratch = None
         self.sq_out = None
+        self.skip_sqnorm = False       # set per update by the agent: the first-step-only clip is already disarmed
         self._table_ptrs = None
 
     # -- layout ---------------------------------------------------------------------------
@@ -586,7 +587,9 @@ class PolicyEngine(_EngineBase):
         st = st if st is not None else stream()
         if fused:          # grad-norm partials + gate / clip + Adam in one call; leaves the gradient bucket zeroed
             inv_cat = 1.0 / skel_nodes_global if skel_nodes_global > 0 else 0.0
-            check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0 / world, inv_cat, self.GA.data_ptr() + 4 * N_STATS,
+            # once the reference's one-shot clip is spent (agent :48, agent_ppo.py:53-56) the gradient norm is not needed
+            g_sq = None if (self.skip_sqnorm and clip_first_only) else self.GA.data_ptr() + 4 * N_STATS
+            check(lib.sard_adam_update(ptr(self.GA), 1.0 / B_global, 1.0 / world, inv_cat, g_sq,
                                        self.GA.numel() - N_STATS, ptr(self.sq_scratch), float(max_norm),
                                        1 if clip_first_only else 0, 1, mask, opt.betas[0], opt.betas[1], ptr(opt.ctl_f),
                                        ptr(opt.ctl_i), ptr(log_row), ptr(opt.segs), opt.n_seg, opt.max_seg, opt.lr, opt.eps, st))

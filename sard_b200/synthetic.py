@@ -283,6 +283,50 @@ def generate_rollout(shape: EnvShape, num_transitions: int, seed: int = 1234, *,
         exps=np.ones(T, dtype=dtype))
 
 
+def make_random_tree(n_nodes: int, rng, max_index: int = 256, fanout_window: int = 6):
+    """A random rooted tree with ``n_nodes`` nodes in the reference's edge layout (``[i,p],[p,i]`` in node order,
+    ``xml_robot.py:624-632``); node i hangs off one of the ``fanout_window`` nodes before it, so degrees stay small like
+    a robot's.  ``body_ind`` cycles through the IndexLinear table (``i % max_index``)."""
+    parent = np.zeros(n_nodes, dtype=np.int64)
+    for i in range(1, n_nodes):
+        parent[i] = int(rng.integers(max(0, i - fanout_window), i))
+    child = np.arange(1, n_nodes, dtype=np.int64)
+    edges = np.empty((2, 2 * (n_nodes - 1)), dtype=np.int64)
+    edges[0, 0::2], edges[1, 0::2] = child, parent[1:]
+    edges[0, 1::2], edges[1, 1::2] = parent[1:], child
+    return edges, np.arange(n_nodes, dtype=np.int64) % max_index
+
+
+def generate_sweep_rollout(shape: EnvShape, num_transitions: int, n_nodes: int, seed: int = 1234, *, n_designs: int = 4,
+                           max_index: int = 256, dtype=np.float32) -> HostRollout:
+    """Scale-sweep rollouts (BASELINE.json config 5: 64-1024-node graphs): ``num_transitions`` EXECUTION-stage
+    transitions (stage 2, the stage that makes up > 95 % of a real rollout; the design stages need leg-structured body
+    names for the orbit tie, which a random tree does not have) over ``n_designs`` random trees of ``n_nodes`` nodes.
+    Episodes are 500 steps long (mask 0 at their last step)."""
+    rng = np.random.default_rng(seed)
+    D, F, S = shape.state_dim, shape.attr_fixed_dim, shape.sim_obs_dim
+    designs = [make_random_tree(n_nodes, rng, max_index) for _ in range(n_designs)]
+    T = num_transitions
+    which = (np.arange(T) // 500) % n_designs
+    obs = np.zeros((T * n_nodes, D), dtype=dtype)
+    obs[:, F:F + S] = rng.standard_normal((T * n_nodes, S), dtype=np.float32).astype(dtype)
+    obs[:, 0] = 1.0
+    actions = np.zeros((T * n_nodes, ACTION_DIM), dtype=dtype)
+    actions[:, 0] = rng.standard_normal(T * n_nodes, dtype=np.float32).astype(dtype)
+    ne = 2 * (n_nodes - 1)
+    edges = np.concatenate([designs[w][0] for w in which], axis=1)
+    body = np.concatenate([designs[w][1] for w in which])
+    masks = np.ones(T, dtype=dtype)
+    masks[499::500] = 0.0
+    masks[-1] = 0.0
+    ext = lambda d: (rng.standard_normal((T, d), dtype=np.float32).astype(dtype) if d > 1 else np.zeros((T, 1), dtype=dtype))
+    return HostRollout(
+        shape=shape, obs=obs, node_ptr=np.arange(T + 1, dtype=np.int64) * n_nodes, edges=edges,
+        edge_ptr=np.arange(T + 1, dtype=np.int64) * ne, stage=np.full(T, 2, dtype=np.int64), body_ind=body,
+        hfield=ext(shape.hfield_dim), obj=ext(shape.obj_dim), goal=ext(shape.goal_dim), actions=actions,
+        rewards=rng.normal(0.01, 0.1, size=T).astype(dtype), masks=masks, exps=np.ones(T, dtype=dtype))
+
+
 class SyntheticEnv:
     """The attributes ``Transform2ActAgent.setup_env`` reads from a DERL env (agent :111-124), for a shape."""
 

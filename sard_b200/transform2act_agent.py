@@ -354,6 +354,11 @@ class Transform2ActAgent:
         outputs), so the policy's runs on the policy stream beside the critic's and the GAE."""
         for m in self.update_modules:
             m.train(False)
+        # the reference clips only the first policy step of a run (its clip list holds a generator, agent :48): once
+        # that step is behind us the gradient norm is dead work.  One 4-byte read while the GPU is idle.
+        opt = self.optimizer_policy
+        armed = True if opt.ctl_i is None else bool(int(opt.ctl_i[1].item()))
+        self.policy_net.engine.skip_sqnorm = bool(self.clip_first_step_only and not armed)
         fixed_ready = False
         if self.overlap_nets:
             main = torch.cuda.current_stream(self.device)

@@ -354,3 +354,92 @@ def test_full_width_nets_loss_and_gradients_match_oracle_autograd(cuda_device, e
         want = vsd[name].grad.numpy()
         got = GV[16 + off:16 + off + p.numel()].reshape(want.shape)
         assert_close(got, want, atol=1e-6 + 2e-5 * float(np.abs(want).max()), what='value ' + name, **GRAD)
+
+
+@pytest.mark.parametrize('n_nodes,gemm_engine', [(256, 4), (300, 0)], indirect=['gemm_engine'])
+def test_sweep_shape_loss_and_gradients_match_oracle_autograd(cuda_device, n_nodes, gemm_engine):
+    """BASELINE.json config 5 shape: graphs of >= 256 nodes (random trees, degree up to ~8), hidden width 256 everywhere
+    (GNN 256x3, JSMLP 256x2): outside the fused 64-wide tensor-core kernels, so this pins the general tiles (fused
+    neighbour-sum GEMMs with long neighbour lists, grouped IndexLinear over all 256 body indices).  Execution-stage
+    minibatch, loss and every gradient against fp64 autograd of the oracle."""
+    from oracle import sard_oracle as O
+    from sard_b200 import synthetic
+    from sard_b200.config import Config, sweep_yml
+    from sard_b200.packed import Ordering, PackedRollout
+    from sard_b200.transform2act_agent import Transform2ActAgent
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['locomotion_ft']
+    T = 24
+    roll = synthetic.generate_sweep_rollout(shape, T, n_nodes, seed=5, n_designs=3)
+    for f in ('obs', 'hfield', 'obj', 'goal', 'actions', 'rewards', 'masks'):
+        setattr(roll, f, getattr(roll, f).astype(np.float64))
+    d = sweep_yml(256); d.update(min_batch_size=T, mini_batch_size=T, num_optim_epoch=1)
+    torch.manual_seed(11)
+    ag = Transform2ActAgent(Config(d), torch.float32, 'cuda', 0, 1, env=synthetic.SyntheticEnv(shape))
+    with torch.no_grad():
+        lin = ag.policy_net.control_ind_mlp.linear
+        lin.b.add_(0.05 * torch.randn_like(lin.b))
+    psd = {k: v.detach().cpu().double().clone() for k, v in ag.policy_net.state_dict().items()}
+    vsd = {k: v.detach().cpu().double().clone() for k, v in ag.value_net.state_dict().items()}
+    for sd in (psd, vsd):
+        for k, v in sd.items():
+            if v.is_floating_point() and not any(k.endswith(s) for s in ('.mean', '.var', '.std')):
+                v.requires_grad_(True)
+    spec = O.Spec(attr_fixed_dim=shape.attr_fixed_dim, index_base=shape.index_base,
+                  embeds=ag.policy_net.group.get_cur_subgroup_embeds().double(),
+                  orbits={int(k): [int(x) for x in v] for k, v in ag.policy_net.group.get_cur_orbits().items()})
+    batch = roll.to_traj_batch()
+    states = [[torch.tensor(x) if i in (0, 1, 5, 6, 7) else x for i, x in enumerate(s)] for s in batch.states]
+    actions = [torch.tensor(a) for a in batch.actions]
+    g = torch.Generator().manual_seed(1)
+    adv = torch.randn(T, 1, dtype=torch.float64, generator=g)
+    ret = torch.randn(T, 1, dtype=torch.float64, generator=g)
+    with torch.no_grad():
+        fixed = O.policy_log_prob(psd, spec, states, actions, training=False) + 0.05 * torch.randn(T, 1, dtype=torch.float64, generator=g)
+    lp = O.policy_log_prob(psd, spec, states, actions, training=True)
+    loss, kl, _ = O.ppo_loss(lp, fixed, adv, 0.2)
+    loss.backward()
+    vloss = (O.value_forward(vsd, spec, states, training=True) - ret).pow(2).mean()
+    vloss.backward()
+
+    arena = PackedRollout(roll, 'cuda')
+    ag._prepare(arena)
+    arena.advantages.copy_(adv.reshape(-1).float()); arena.returns.copy_(ret.reshape(-1).float())
+    arena.fixed_log_probs.copy_(fixed.reshape(-1).float())
+    ag.policy_net.train(); ag.value_net.train()
+    peng, veng = ag.policy_net.engine, ag.value_net.engine
+    order = Ordering(arena, np.arange(T))
+    runs = order.stage_runs(0, T)
+    assert runs[2] is not None and runs[0] is None and runs[1] is None
+    peng.GA.zero_()
+    peng.run_stage(2, arena, runs[2], 1, 0.2, 1.0 / T)
+    GA = peng.GA.cpu().numpy().astype(np.float64)
+    assert_close(-GA[0] / T, float(loss), rtol=1e-4, atol=1e-6, what='surr loss')
+    assert_close(GA[1] / T, kl, rtol=1e-4, atol=1e-6, what='approx kl')
+    for name, p, off, grp in peng.store.entries:
+        if psd[name].grad is None:
+            continue                                   # skel / attr parameters: no gradient in an execution-only batch
+        want = psd[name].grad.numpy()
+        got = GA[16 + off:16 + off + p.numel()].reshape(want.shape)
+        assert_close(got, want, atol=1e-6 + 2e-5 * float(np.abs(want).max()), what='policy ' + name, **GRAD)
+    live = np.flatnonzero(peng.ever_live[2])
+    assert len(live) == min(n_nodes, 256)
+    st = peng.net.stage[2]
+    tabs = ag.policy_net.control_ind_mlp.layers()
+    base = peng.gt_off[2]
+    for j, t in enumerate(tabs):
+        pre = 'control_ind_mlp.' + (f'affine_layers.{j}.' if j < len(tabs) - 1 else 'linear.')
+        wW, wb = psd[pre + 'W'].grad.numpy(), psd[pre + 'b'].grad.numpy()
+        rw = t.out_dim * t.input_dim
+        gW = GA[base + st.il[j].gW: base + st.il[j].gW + len(live) * rw].reshape(len(live), t.out_dim, t.input_dim)
+        gb = GA[base + st.il[j].gb: base + st.il[j].gb + len(live) * t.out_dim].reshape(len(live), t.out_dim)
+        assert_close(gW, wW[live], atol=1e-6 + 2e-5 * float(np.abs(wW).max()), what=pre + 'W', **GRAD)
+        assert_close(gb, wb[live], atol=1e-6 + 2e-5 * float(np.abs(wb).max()), what=pre + 'b', **GRAD)
+    veng.GA.zero_()
+    veng.run(arena, order.run(0, T), 1, 1.0 / T)
+    GV = veng.GA.cpu().numpy().astype(np.float64)
+    assert_close(GV[5] / T, float(vloss), rtol=1e-4, atol=1e-6, what='value loss')
+    for name, p, off, grp in veng.store.entries:
+        want = vsd[name].grad.numpy()
+        got = GV[16 + off:16 + off + p.numel()].reshape(want.shape)
+        assert_close(got, want, atol=1e-6 + 2e-5 * float(np.abs(want).max()), what='value ' + name, **GRAD)
