@@ -240,3 +240,191 @@ int sard_enc_bwd_launch(const EncBwdP& p, cudaStream_t st) {
   SARD_LAUNCH_OK("enc_bwd_reduce_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------- wide first layer
+// First ObsEncoder layer with a WIDE input (height field: K = 1410 in locomotion_vt / escape, jsmlp.py:7-20):
+//   e1[b, j] = relu(b1[j] + sum_k x[ids[b], k] W1[j, k]),   M = B (2048) rows, N = 64, K = 1410.
+// K is neither a multiple of 16 nor are the rows 16-byte aligned, so the aligned GEMM tiles do not apply, and the
+// generic tile kernel sees 16-32 CTAs for the whole product (86 us).  Here the reduction is split over CTAs:
+// grid (B / 32 row tiles, WIDE_SPLITS k-ranges), partial sums in split order (deterministic), a finishing kernel adds
+// bias + ReLU.  The weight gradient splits the other way: grid (k tiles of 64, row chunks of 256).
+#define WIDE_H 64
+#define WIDE_KT 64
+#define WIDE_ROWS 32
+#define WIDE_SPLITS 6
+#define WIDE_WG_ROWS 256
+
+#define WIDE_LD 68               // shared-memory row stride: 16-byte aligned rows, float4 reads along k without bank conflicts
+__global__ void __launch_bounds__(256, 2) enc_wide_fwd_kernel(const float* __restrict__ src, int K, const int* __restrict__ ids, int B,
+                                                              const float* __restrict__ w1, float* __restrict__ partials) {
+  pdl_sync();
+  __shared__ __align__(16) float xs[WIDE_ROWS][WIDE_LD];
+  __shared__ __align__(16) float ws[WIDE_H][WIDE_LD];
+  const int r0 = blockIdx.x * WIDE_ROWS, tid = threadIdx.x;
+  const int per = ((K + WIDE_SPLITS - 1) / WIDE_SPLITS + WIDE_KT - 1) / WIDE_KT * WIDE_KT;     // k-range of a split, multiple of the k tile
+  const int k_lo = blockIdx.y * per, k_hi = min(K, k_lo + per);
+  const int tr = tid >> 4, tc = tid & 15;                // rows 2 tr, 2 tr + 1; output columns tc + 16 a
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[i][a] = 0.f;
+  // this thread's 8 input rows (fixed over the k loop): the arena row is looked up once
+  const float* xrow[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int r = (u * 256 + tid) >> 6;
+    xrow[u] = (r0 + r < B) ? src + (size_t)__ldg(ids + r0 + r) * K : nullptr;
+  }
+  const int cc = tid & 63;
+  float xv[8], wv[16];
+  auto fetch = [&](int k0) {                             // 32 x 64 input tile and 64 x 64 weight tile, consecutive threads along k
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = (xrow[u] && k0 + cc < k_hi) ? __ldg(xrow[u] + k0 + cc) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = (u * 256 + tid) >> 6;
+      wv[u] = (k0 + cc < k_hi) ? __ldg(w1 + (size_t)r * K + k0 + cc) : 0.f;
+    }
+  };
+  if (k_lo < k_hi) fetch(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += WIDE_KT) {
+    __syncthreads();                                     // the previous tile has been consumed
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int e = u * 256 + tid; xs[e >> 6][e & 63] = xv[u]; }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int e = u * 256 + tid; ws[e >> 6][e & 63] = wv[u]; }
+    __syncthreads();
+    if (k0 + WIDE_KT < k_hi) fetch(k0 + WIDE_KT);        // the next tile's loads fly under this tile's math
+#pragma unroll 4
+    for (int c = 0; c < WIDE_KT; c += 4) {
+      float4 x[2], w[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) x[i] = *reinterpret_cast<const float4*>(&xs[2 * tr + i][c]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) w[a] = *reinterpret_cast<const float4*>(&ws[tc + 16 * a][c]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          acc[i][a] = fmaf(x[i].x, w[a].x, acc[i][a]); acc[i][a] = fmaf(x[i].y, w[a].y, acc[i][a]);
+          acc[i][a] = fmaf(x[i].z, w[a].z, acc[i][a]); acc[i][a] = fmaf(x[i].w, w[a].w, acc[i][a]);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = r0 + 2 * tr + i;
+    if (r < B) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) partials[((size_t)blockIdx.y * B + r) * WIDE_H + tc + 16 * a] = acc[i][a];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) enc_wide_finish_kernel(const float* __restrict__ partials, int B, const float* __restrict__ b1,
+                                                              float* __restrict__ e1) {
+  pdl_sync();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * WIDE_H) return;
+  float s = __ldg(b1 + (e & 63));
+#pragma unroll
+  for (int sp = 0; sp < WIDE_SPLITS; ++sp) s += partials[(size_t)sp * B * WIDE_H + e];
+  e1[e] = s > 0.f ? s : 0.f;
+}
+
+// dW1[j, k] partial over one chunk of rows: de1 is the gradient w.r.t. the layer's pre-activation (relu' applied)
+__global__ void __launch_bounds__(256) enc_wide_wgrad_kernel(const float* __restrict__ src, int K, const int* __restrict__ ids, int B,
+                                                             const float* __restrict__ de1, float* __restrict__ partials) {
+  pdl_sync();
+  __shared__ __align__(16) float ds[WIDE_ROWS][WIDE_LD];
+  __shared__ __align__(16) float xs[WIDE_ROWS][WIDE_LD];
+  const int k0 = blockIdx.x * WIDE_KT, chunk = blockIdx.y, tid = threadIdx.x;
+  const int r_lo = chunk * WIDE_WG_ROWS, r_hi = min(B, r_lo + WIDE_WG_ROWS);
+  const int tj = (tid >> 4) * 4, tk = (tid & 15) * 4;   // 4 x 4 outputs per thread: rows j = tj.., columns k = tk..
+  float acc[4][4], bsum = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float dv[8], xv[8];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = u * 256 + tid, r = e >> 6, c = e & 63;
+      const bool ok = r0 + r < r_hi;
+      dv[u] = ok ? de1[(size_t)(r0 + r) * WIDE_H + c] : 0.f;
+      xv[u] = (ok && k0 + c < K) ? __ldg(src + (size_t)__ldg(ids + r0 + r) * K + k0 + c) : 0.f;
+    }
+  };
+  if (r_lo < r_hi) fetch(r_lo);
+  for (int r0 = r_lo; r0 < r_hi; r0 += WIDE_ROWS) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int e = u * 256 + tid; ds[e >> 6][e & 63] = dv[u]; xs[e >> 6][e & 63] = xv[u]; }
+    __syncthreads();
+    if (r0 + WIDE_ROWS < r_hi) fetch(r0 + WIDE_ROWS);    // next step's loads under this step's math
+#pragma unroll 8
+    for (int r = 0; r < WIDE_ROWS; ++r) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&ds[r][tj]), x4 = *reinterpret_cast<const float4*>(&xs[r][tk]);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(d[a], x[b], acc[a][b]);
+    }
+    if (blockIdx.x == 0 && tid < WIDE_H) {               // bias gradient: column sums of de1
+#pragma unroll 8
+      for (int r = 0; r < WIDE_ROWS; ++r) bsum += ds[r][tid];
+    }
+  }
+  const int ldp = K + 1;                                 // partial row: K weight columns + the bias column
+  float* part = partials + (size_t)chunk * WIDE_H * ldp;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (k0 + tk + b < K) part[(size_t)(tj + a) * ldp + k0 + tk + b] = acc[a][b];
+  if (blockIdx.x == 0 && tid < WIDE_H) part[(size_t)tid * ldp + K] = bsum;
+}
+
+__global__ void __launch_bounds__(256) enc_wide_wgrad_reduce_kernel(const float* __restrict__ partials, int n_chunks, int K,
+                                                                    float* __restrict__ gw1, float* __restrict__ gb1) {
+  pdl_sync();
+  const int ldp = K + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= WIDE_H * ldp) return;
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += partials[(size_t)c * WIDE_H * ldp + e];      // chunk order: deterministic
+  const int jrow = e / ldp, k = e - jrow * ldp;
+  if (k < K) gw1[(size_t)jrow * K + k] += s;
+  else gb1[jrow] += s;
+}
+
+int sard_enc_wide_ok(int K, int h1) { return K > 128 && h1 == WIDE_H; }
+long long sard_enc_wide_partials_floats(int B, int K) {
+  const long long fwd = (long long)WIDE_SPLITS * B * WIDE_H, bwd = (long long)ceil_div(B, WIDE_WG_ROWS) * WIDE_H * (K + 1);
+  return fwd > bwd ? fwd : bwd;
+}
+int sard_enc_wide_fwd(const float* src, int K, const int* ids, int B, const float* w1, const float* b1, float* e1, float* partials,
+                      cudaStream_t st) {
+  if (B <= 0) return 0;
+  sard_prof_bytes(4.0 * ((double)B * K + 64.0 * K + 64.0 * B));
+  sard_launch(enc_wide_fwd_kernel, dim3(ceil_div(B, WIDE_ROWS), WIDE_SPLITS), 256, 0, st, src, K, ids, B, w1, partials);
+  SARD_LAUNCH_OK("enc_wide_fwd_kernel");
+  sard_launch(enc_wide_finish_kernel, ceil_div((long long)B * WIDE_H, 256), 256, 0, st, (const float*)partials, B, b1, e1);
+  SARD_LAUNCH_OK("enc_wide_finish_kernel");
+  return 0;
+}
+int sard_enc_wide_wgrad(const float* src, int K, const int* ids, int B, const float* de1, float* gw1, float* gb1, float* partials,
+                        cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int n_chunks = ceil_div(B, WIDE_WG_ROWS);
+  sard_prof_bytes(4.0 * ((double)B * K + 64.0 * K + 64.0 * B));
+  sard_launch(enc_wide_wgrad_kernel, dim3(ceil_div(K, WIDE_KT), n_chunks), 256, 0, st, src, K, ids, B, de1, partials);
+  SARD_LAUNCH_OK("enc_wide_wgrad_kernel");
+  sard_launch(enc_wide_wgrad_reduce_kernel, ceil_div((long long)WIDE_H * (K + 1), 256), 256, 0, st, (const float*)partials, n_chunks, K,
+              gw1, gb1);
+  SARD_LAUNCH_OK("enc_wide_wgrad_reduce_kernel");
+  return 0;
+}

@@ -21,3 +21,11 @@ int sard_enc_fused_ok(int K, int h1, int h2);
 long long sard_enc_partials_floats(int B, int n_enc);
 int sard_enc_fwd_launch(const EncFwdP& p, cudaStream_t st);
 int sard_enc_bwd_launch(const EncBwdP& p, cudaStream_t st);
+
+// first layer with a wide input (K > 128, e.g. the 1410-sample height field): split-K kernels, encoder.cu
+int sard_enc_wide_ok(int K, int h1);
+long long sard_enc_wide_partials_floats(int B, int K);
+int sard_enc_wide_fwd(const float* src, int K, const int* ids, int B, const float* w1, const float* b1, float* e1, float* partials,
+                      cudaStream_t st);
+int sard_enc_wide_wgrad(const float* src, int K, const int* ids, int B, const float* de1, float* gw1, float* gb1, float* partials,
+                        cudaStream_t st);

@@ -333,7 +333,7 @@ int tower_backward(const SardTower& tw, const float* P, float* G, const SardAren
 
 // ext[B, 3*64] written at `ext` with leading dimension ld_ext; e1[k]: [B,64] hidden activations
 int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena* arena, const SardSel* sel,
-                     float* const e1[3], float* ext, int ld_ext, sard_stream_t st) {
+                     float* const e1[3], float* ext, int ld_ext, float* wide_scratch, sard_stream_t st) {
   site(K_ENC, 0);
   EncFwdP fp;
   memset(&fp, 0, sizeof(fp));
@@ -349,12 +349,17 @@ int encoders_forward(const SardDense enc[3][2], const float* P, const SardArena*
   SARD_TRY(sard_enc_fwd_launch(fp, as_stream(st)));
   for (int k = 0; k < 3; ++k) {
     if (sard_enc_fused_ok(enc[k][0].in, enc[k][0].out, enc[k][1].out)) continue;
-    SardGemm g = gemm0();
-    g.A = arena->ext[k]; g.lda = arena->ext_dim[k]; g.a_rows = sel->ids;
-    g.B0 = P + enc[k][0].w; g.ldb0 = enc[k][0].in; g.b_split = enc[k][0].in; g.bias = P + enc[k][0].b;
-    g.M = sel->B; g.N = enc[k][0].out; g.R = enc[k][0].in; g.act = SARD_ACT_RELU; g.Y = e1[k]; g.ldy = enc[k][0].out;
     SARD_REQUIRE(enc[k][0].in == arena->ext_dim[k], "encoder input dim != arena ext dim");
-    SARD_TRY(sard_linear_fwd(&g, st));
+    if (wide_scratch && sard_enc_wide_ok(enc[k][0].in, enc[k][0].out)) {
+      SARD_TRY(sard_enc_wide_fwd(arena->ext[k], enc[k][0].in, sel->ids, sel->B, P + enc[k][0].w, P + enc[k][0].b, e1[k], wide_scratch,
+                                 as_stream(st)));
+    } else {
+      SardGemm g = gemm0();
+      g.A = arena->ext[k]; g.lda = arena->ext_dim[k]; g.a_rows = sel->ids;
+      g.B0 = P + enc[k][0].w; g.ldb0 = enc[k][0].in; g.b_split = enc[k][0].in; g.bias = P + enc[k][0].b;
+      g.M = sel->B; g.N = enc[k][0].out; g.R = enc[k][0].in; g.act = SARD_ACT_RELU; g.Y = e1[k]; g.ldy = enc[k][0].out;
+      SARD_TRY(sard_linear_fwd(&g, st));
+    }
     SardGemm h = gemm0();
     h.A = e1[k]; h.lda = enc[k][0].out; h.B0 = P + enc[k][1].w; h.ldb0 = enc[k][1].in; h.b_split = enc[k][1].in;
     h.bias = P + enc[k][1].b; h.M = sel->B; h.N = enc[k][1].out; h.R = enc[k][1].in; h.act = SARD_ACT_RELU;
@@ -394,6 +399,11 @@ int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const
     site(K_ENC, 1);
     SARD_TRY(sard_linear_bwd_data(&g, st));
     site(K_ENC, 2);
+    if (sard_enc_wide_ok(enc[k][0].in, enc[k][0].out)) {
+      SARD_TRY(sard_enc_wide_wgrad(arena->ext[k], enc[k][0].in, sel->ids, sel->B, de1, G + enc[k][0].w, G + enc[k][0].b, wg_scratch,
+                                   as_stream(st)));
+      continue;
+    }
     SardWGrad w1 = wgrad0();
     w1.P = de1; w1.ldp = enc[k][0].out; w1.Q = arena->ext[k]; w1.ldq = arena->ext_dim[k]; w1.q_rows = sel->ids;
     w1.M = sel->B; w1.N1 = enc[k][0].out; w1.N2 = enc[k][0].in;
@@ -403,8 +413,24 @@ int encoders_backward(const SardDense enc[3][2], const float* P, float* G, const
   return 0;
 }
 
+// forward scratch of the wide-input first layers (split-K partials); 0 when no encoder is wide
+long long enc_wide_fwd_need(const SardDense enc[3][2], int B) {
+  long long need = 0;
+  for (int k = 0; k < 3; ++k)
+    if (sard_enc_wide_ok(enc[k][0].in, enc[k][0].out)) {
+      const long long v = sard_enc_wide_partials_floats(B, enc[k][0].in);
+      need = v > need ? v : need;
+    }
+  return need;
+}
+
 long long enc_wg_need(const SardDense enc[3][2], int B) {
   long long need = sard_enc_partials_floats(B, 3);
+  for (int k = 0; k < 3; ++k)
+    if (sard_enc_wide_ok(enc[k][0].in, enc[k][0].out)) {
+      const long long v = sard_enc_wide_partials_floats(B, enc[k][0].in);
+      need = v > need ? v : need;
+    }
   for (int k = 0; k < 3; ++k)
     for (int j = 0; j < 2; ++j) {
       long long v = wg_partials(B, enc[k][j].out, enc[k][j].in, WG_CHUNK);
@@ -418,7 +444,7 @@ struct ValueBufs {
   TowerBufs t;
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
-  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* wg3; float* sk; long long sk_floats;
+  float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* wg3; float* encw; float* sk; long long sk_floats;
 };
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
@@ -436,6 +462,7 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
   vb.v = b.f(B); vb.dv = b.f(B); vb.sq = b.f(B);
   vb.sk_floats = 1024LL * B;                                 // split-K partial tiles of the MLP GEMMs: S*N <= 1024 columns
   vb.sk = b.f(vb.sk_floats);
+  { const long long w = enc_wide_fwd_need(net.enc, B); vb.encw = w > 0 ? b.f(w) : nullptr; }
   if (train) {
     vb.dcat = b.f((long long)B * vb.ldcat);
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
@@ -490,7 +517,7 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   }
   // the ObsEncoders only need the arena: they run beside the tower and are joined before the value head
   SideCtx* side = side_for(as_stream(st));
-  SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat,
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat, vb.encw,
                             wg_stream(side, st, 2)));
   SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
   // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
@@ -565,7 +592,7 @@ struct StageBufs {
   float* e1[3]; float* ext;
   int *srow, *spos, *grp_ptr, *tiles, *chunks, *grp_chunk_ptr, *counts, *sort_scratch;
   float* xs; int ldxs; float* H[SARD_MAX_IL]; float* out; float* pre; int ldo;
-  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2; float* wg3;
+  float* dout; float* gstat; float* dH[SARD_MAX_IL]; float* dxs; float* dext; float* de1; float* wg; float* wg2; float* wg3; float* encw;
   int max_tiles, max_chunks;
   bool tc;                       // fused tcgen05 JSMLP (jsmlp_tc.cu)
   bool tcb;                      // ... in the padded row space, with the fused backward (jsmlp_tc_bwd.cu)
@@ -603,6 +630,7 @@ void carve_stage(Bump& b, const SardPolicyNet& net, const SardPolicyStage& s, in
   sb.rec = reinterpret_cast<double*>(b.f(2 * (1 + 2 * s.tower.D) + 2));
   for (int k = 0; k < 3; ++k) sb.e1[k] = b.f((long long)B * net.enc[k][0].out);
   sb.ext = b.f((long long)B * 3 * SARD_EXT_DIM);
+  { const long long w = enc_wide_fwd_need(net.enc, B); sb.encw = w > 0 ? b.f(w) : nullptr; }
   // every present body index adds at most one partial tile / chunk
   const int live = s.n_live > 0 && s.n_live < s.max_index ? s.n_live : s.max_index;
   sb.tc = stage_uses_tc(s);
@@ -698,7 +726,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   // the ObsEncoders only need the arena and the hi/lo pair copies of the live weight slabs only the weights (they change
   // with every optimiser step): both run beside the tower
   SideCtx* side = side_for(as_stream(st));
-  SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, wg_stream(side, st, 2)));
+  SARD_TRY(encoders_forward(net->enc, P, arena, sel, sb.e1, sb.ext, 3 * SARD_EXT_DIM, sb.encw, wg_stream(side, st, 2)));
   if (sb.tc) {
     const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
     SARD_TRY(sard_jsmlp_tc_presplit(&a, wg_stream(side, st, 1)));
