@@ -183,12 +183,12 @@ void carve_tower(Bump& b, const SardTower& tw, int n, int B, bool train, TowerBu
     t.tc.chunk_rows = sard_tower_tc_chunk_rows(nn);
     t.tc.num_chunks = ceil_div(nn, t.tc.chunk_rows);
     if (train) {
-      t.tc.XH = b.a256((long long)nn * 256);
+      t.tc.XH = b.a256((long long)nn * 128);
       for (int l = 0; l < tw.L; ++l) {
-        t.tc.PH[l] = b.a256((long long)nn * 128); t.tc.PA[l] = b.a256((long long)nn * 256);
+        t.tc.PH[l] = b.a256((long long)nn * 64); t.tc.PA[l] = b.a256((long long)nn * 128);
         t.tc.mask[l] = reinterpret_cast<unsigned*>(b.a256(2LL * nn));
       }
-      t.tc.PZ0 = b.a256((long long)nn * 128);
+      t.tc.PZ0 = b.a256((long long)nn * 64);
       t.tc.partials = b.a256(sard_tower_tc_partials_floats(t.tc.num_chunks));
     }
   }

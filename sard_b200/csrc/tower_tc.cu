@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
         for (int j = 0; j < 32; ++j) v[j] = (k0 + j == p.D) ? 1.f : v[j];
         own_write(c, v);
         __syncwarp();
-        pair_store_own(c, p.XH, 256, k0, 128);
+        store_from_own<0>(c, p.XH + (size_t)c.row0 * 128 + k0, 128);
         __syncwarp();
       }
     }
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     if (p.PH[0]) {                                       // under the next GEMM
       own_write(c, v);
       __syncwarp();
-      pair_store_own(c, p.PH[0], 128, c.c0, 64);
+      store_from_own<0>(c, p.PH[0] + (size_t)c.row0 * TT_H + c.c0, TT_H);
       __syncwarp();
     }
     // ---- GraphConv layers
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
       if (l < p.L ? p.PH[l] != nullptr : true) {
         own_write(c, v);
         __syncwarp();
-        if (l < p.L) pair_store_own(c, p.PH[l], 128, c.c0, 64);                             // under the next GEMM
+        if (l < p.L) store_from_own<0>(c, p.PH[l] + (size_t)c.row0 * TT_H + c.c0, TT_H);    // under the next GEMM
         else store_from_own<0>(c, p.hout + (size_t)c.row0 * TT_H + c.c0, TT_H);
         __syncwarp();
       }
@@ -600,11 +600,11 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const
       stage_gather(S, c, p.nnbr, v);                      // A^T dz_l
       TT_STAMP(3 + 6 * i);
       tc::named_sync(2, 256);                             // every gather is done: the own region (= dz_l) is private again
-      pair_store_own(c, p.PA[l - 1], 256, 64 + c.c0, 128);
+      store_from_own<0>(c, p.PA[l - 1] + (size_t)c.row0 * 128 + 64 + c.c0, 128);
       __syncwarp();
       own_write(c, v);
       __syncwarp();
-      pair_store_own(c, p.PA[l - 1], 256, c.c0, 128);
+      store_from_own<0>(c, p.PA[l - 1] + (size_t)c.row0 * 128 + c.c0, 128);
       __syncwarp();
       // ---- dz_l [W_l | W_r]: first half is summed over the out-neighbours, second half is the self term
       TT_STAMP(4 + 6 * i);
@@ -625,12 +625,12 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (m >> j) & 1u ? v[j] : 0.f;
           } else {
-            const float* hp = p.PH[l - 1] + (size_t)r * 128 + c.c0;
+            const float* hp = p.PH[l - 1] + (size_t)r * TT_H + c.c0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 hh = __ldg(reinterpret_cast<const float4*>(hp + 4 * j)), hl = __ldg(reinterpret_cast<const float4*>(hp + 64 + 4 * j));
-              v[4 * j] *= act_grad_from_output(hh.x + hl.x, p.act); v[4 * j + 1] *= act_grad_from_output(hh.y + hl.y, p.act);
-              v[4 * j + 2] *= act_grad_from_output(hh.z + hl.z, p.act); v[4 * j + 3] *= act_grad_from_output(hh.w + hl.w, p.act);
+              const float4 hh = __ldg(reinterpret_cast<const float4*>(hp + 4 * j));
+              v[4 * j] *= act_grad_from_output(hh.x, p.act); v[4 * j + 1] *= act_grad_from_output(hh.y, p.act);
+              v[4 * j + 2] *= act_grad_from_output(hh.z, p.act); v[4 * j + 3] *= act_grad_from_output(hh.w, p.act);
             }
           }
         }
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_bwd_tc_kernel(const
         tc::named_sync(2, 256);
         own_write(c, v);
         __syncwarp();
-        pair_store_own(c, p.PZ0, 128, c.c0, 64);
+        store_from_own<0>(c, p.PZ0 + (size_t)c.row0 * TT_H + c.c0, TT_H);
       }
     }
   }
@@ -671,12 +671,12 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = tc::align1024(smem_raw);
   uint8_t* ones = base + TWG_STAGES * TWG_STAGE_BYTES;
-  __shared__ uint64_t bar_full[TWG_STAGES], bar_empty[TWG_STAGES], bar_done;
+  __shared__ uint64_t bar_full[TWG_STAGES], bar_ready[TWG_STAGES], bar_empty[TWG_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    for (int s = 0; s < TWG_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TWG_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_ready[s], TWG_THREADS - 64); tc::mbar_init(&bar_empty[s], 1); }
     tc::mbar_init(&bar_done, 1);
     tc::mbar_fence_init();
   }
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
   const int row_start = blockIdx.x * p.chunk_rows;
   const int row_end = min(p.n, row_start + p.chunk_rows);
   const int nks = (row_end - row_start + TWG_ROWS - 1) / TWG_ROWS;      // rows past n are zero-filled by TMA
-  const uint32_t stage_bytes = (uint32_t)p.L * 12288 + 12288;
+  const uint32_t stage_bytes = ((uint32_t)p.L * 12288 + 12288) / 2;    // TMA brings the fp32 operands; their lo halves are made on the SM
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < nks; ++it) {
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
       const uint64_t one_k = tc::smem_desc_sw128(tc::smem_u32(ones), 16, 0);
       for (int it = 0; it < nks; ++it) {
         const int s = it % TWG_STAGES;
-        tc::mbar_wait(&bar_full[s], (it / TWG_STAGES) & 1);
+        tc::mbar_wait(&bar_ready[s], (it / TWG_STAGES) & 1);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(base + s * TWG_STAGE_BYTES);
         const uint32_t acc = it ? 1u : 0u;
@@ -739,6 +739,30 @@ __global__ void __launch_bounds__(TWG_THREADS, 1) tower_wgrad_tc_kernel(const __
       tc::mma_commit(&bar_done);
     }
   } else {
+    // ---- operand split: the operands are stored once, as fp32 (half the HBM traffic of hi|lo pair arrays: this kernel
+    // was DRAM-bound on them); TMA lands them in the "hi" slabs of a stage and these eight warps rewrite every value v in
+    // place as hi = tf32(v) and put lo = v - hi into the matching "lo" slab (same swizzled position: the split is
+    // element-wise, so the layout never has to be decoded), then hand the stage to the MMA warp
+    {
+      const int st_t = tid - 64;                          // 0 .. 255
+      const int n4 = (p.L + 1) * 384;                     // float4 per stage: per layer block 256 ([A^T dz | dz] or x) + 128 (h or dz_0)
+      for (int it = 0; it < nks; ++it) {
+        const int s = it % TWG_STAGES;
+        tc::mbar_wait(&bar_full[s], (it / TWG_STAGES) & 1);
+        uint8_t* stg = base + s * TWG_STAGE_BYTES;
+        for (int i = st_t; i < n4; i += TWG_THREADS - 64) {
+          const int blk = i / 384, j = i - blk * 384;
+          uint8_t* src = stg + (blk < p.L ? TWG_OFF_A(blk) : TWG_OFF_X) + (j < 256 ? j * 16 : 8192 + (j - 256) * 16);
+          const float4 v = *reinterpret_cast<const float4*>(src);
+          float4 h, l;
+          tc::split4(v, h, l);
+          *reinterpret_cast<float4*>(src) = h;
+          *reinterpret_cast<float4*>(src + (j < 256 ? 4096 : 2048)) = l;
+        }
+        tc::fence_async_smem();                           // generic-proxy writes -> visible to the tensor core's reads
+        tc::mbar_arrive(&bar_ready[s]);
+      }
+    }
     // two warps per TMEM lane quarter, seven 32-column groups each; the idle pipeline stages are the transpose scratch
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -876,11 +900,11 @@ int sard_tower_tc_wgrad(const SardTower& tw, const SardSel* sel, const TowerTcBu
   memset(&p, 0, sizeof(p));
   const int n = sel->n;
   for (int l = 0; l < tw.L; ++l) {
-    SARD_TRY(sard_tmap_slab(&p.tm_pa[l], tb.PA[l], n, 256, 256, TWG_ROWS, 8));
-    SARD_TRY(sard_tmap_slab(&p.tm_ph[l], tb.PH[l], n, 128, 128, TWG_ROWS, 4));
+    SARD_TRY(sard_tmap_slab(&p.tm_pa[l], tb.PA[l], n, 128, 128, TWG_ROWS, 4));
+    SARD_TRY(sard_tmap_slab(&p.tm_ph[l], tb.PH[l], n, 64, 64, TWG_ROWS, 2));
   }
-  SARD_TRY(sard_tmap_slab(&p.tm_xh, tb.XH, n, 256, 256, TWG_ROWS, 8));
-  SARD_TRY(sard_tmap_slab(&p.tm_z0, tb.PZ0, n, 128, 128, TWG_ROWS, 4));
+  SARD_TRY(sard_tmap_slab(&p.tm_xh, tb.XH, n, 128, 128, TWG_ROWS, 4));
+  SARD_TRY(sard_tmap_slab(&p.tm_z0, tb.PZ0, n, 64, 64, TWG_ROWS, 2));
   p.n = n; p.chunk_rows = tb.chunk_rows; p.L = tw.L; p.partials = tb.partials;
   static bool configured[SARD_MAX_DEVICES] = {};
   if (sard_first_use_on_device(configured))

@@ -15,11 +15,11 @@ struct TowerTcBufs {
   unsigned* mask[TT_MAXL];      // [n, 2] ReLU masks of h_l (train)
   int num_tiles, span;          // tile t holds the graphs whose first row lies in [span*t, span*(t+1))
   int chunk_rows, num_chunks;   // weight-gradient row chunks
-  // training only; pair arrays are [rows, hi | lo]
-  float* XH;                    // [n, 256]  normalised input (+ a column of ones at D: the in_fc bias gradient)
-  float* PH[TT_MAXL];           // [n, 128]  h_l, l = 0..L-1
-  float* PA[TT_MAXL];           // [n, 256]  [A^T dz_l | dz_l] of GraphConv layer l = 1..L at index l-1
-  float* PZ0;                   // [n, 128]  dz_0 (gradient w.r.t. in_fc's output)
+  // training only: operands of the weight gradients, fp32 (tower_wgrad_tc_kernel splits them into hi | lo on the SM)
+  float* XH;                    // [n, 128]  normalised input (+ a column of ones at D: the in_fc bias gradient)
+  float* PH[TT_MAXL];           // [n, 64]   h_l, l = 0..L-1
+  float* PA[TT_MAXL];           // [n, 128]  [A^T dz_l | dz_l] of GraphConv layer l = 1..L at index l-1
+  float* PZ0;                   // [n, 64]   dz_0 (gradient w.r.t. in_fc's output)
   float* partials;              // [num_chunks, 128, 448]
 };
 
