@@ -8,8 +8,14 @@
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------ forward / backward-data
+// arrival counters of the split-K output tiles: one row per stream slot (two split-K GEMMs on different streams must not
+// share counters), zero at load, every launch leaves its counters at zero again
+#define SPLITK_SLOTS 8
+#define SPLITK_MAX_TILES 1024
+__device__ unsigned g_splitk_cnt[SPLITK_SLOTS][SPLITK_MAX_TILES];
+
 template <int BN, int TN, bool NT, bool AGG, int MINB, bool SPLITK>
-__global__ void __launch_bounds__(256, MINB) gemm_fast_kernel(const SardGemm g) {
+__global__ void __launch_bounds__(256, MINB) gemm_fast_kernel(const SardGemm g, unsigned* splitk_counters) {
   pdl_sync();
   constexpr int BM = 128, BK = 16, TM = 8;
   constexpr int AS = BK * (BM + 4), BS = BK * (BN + 4);
@@ -177,6 +183,47 @@ __global__ void __launch_bounds__(256, MINB) gemm_fast_kernel(const SardGemm g) 
               make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
       }
     }
+    // The slice that arrives LAST at this output tile finishes it: partial tiles added in slice order (so the result does
+    // not depend on which slice that was) + the epilogue.  One launch instead of two on the critic's chain.
+    if (!splitk_counters) return;                            // finished by splitk_finish_kernel
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    unsigned* cnt = splitk_counters + blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+      const unsigned t = atomicAdd(cnt, 1u);
+      s_last = (t == gridDim.z - 1) ? 1 : 0;
+      if (s_last) *cnt = 0;                                   // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int rows = row_end - row_start;
+    const size_t slice = (size_t)g.M * g.N;
+    for (int idx = tid; idx < rows * (BN / 4); idx += 256) {
+      const int m = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
+      const int grow = row_start + m, gc0 = n0 + c;
+      const float* pp = g.splitk_ws + (size_t)grow * g.N + gc0;
+      float4 v = __ldcg(reinterpret_cast<const float4*>(pp));
+      for (int z = 1; z < (int)gridDim.z; ++z) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(pp + z * slice));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      const long long yrow = g.y_rows ? g.y_rows[grow] : grow;
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gc = gc0 + i;
+        float x = o[i];
+        if (NT) {
+          if (g.bias) x += __ldg(g.bias + gc);
+          x = epi_forward(x, g.act, g.post, g.Ypre ? g.Ypre + yrow * g.ldy + gc : nullptr);
+        } else if (g.Dact) {
+          x *= act_grad_from_output(g.Dact[yrow * g.ldd + gc], gc < g.dsplit ? g.dact0 : g.dact1);
+        }
+        g.Y[yrow * g.ldy + gc] = x;
+      }
+    }
     return;
   }
   float* Cs = smem;                                          // [BM][BN+1]; the operand tiles are dead
@@ -222,7 +269,7 @@ static int launch_fast_mb(const SardGemm* g, cudaStream_t st) {
   const int tiles = g->tiles ? g->max_tiles : ceil_div(g->M, 128);
   if (tiles <= 0) return 0;
   dim3 grid(tiles, g->N / BN);
-  sard_launch(gemm_fast_kernel<BN, TN, NT, AGG, MINB, false>, grid, 256, smem, st, *g);
+  sard_launch(gemm_fast_kernel<BN, TN, NT, AGG, MINB, false>, grid, 256, smem, st, *g, (unsigned*)nullptr);
   SARD_LAUNCH_OK(NT ? "gemm_fast_kernel<fwd>" : "gemm_fast_kernel<bwd_data>");
   return 0;
 }
@@ -269,7 +316,19 @@ static int launch_splitk(const SardGemm* g, int S, cudaStream_t st) {
     SARD_CUDA(cudaFuncSetAttribute(gemm_fast_kernel<BN, 4, NT, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid(ceil_div(g->M, 128), g->N / BN, S);
-  sard_launch(gemm_fast_kernel<BN, 4, NT, false, 3, true>, grid, 256, smem, st, *g);
+  // finishing a tile inside the GEMM launch (last-arriving slice) saves a launch but was measured slower on the update
+  // (112.1 / 112.8 vs 110.0 / 110.2 ms, same box): the fence + arrival atomics and the serial tail cost more
+  static const int fused = getenv("SARD_SPLITK_FUSED") ? atoi(getenv("SARD_SPLITK_FUSED")) : 0;
+  if (fused && (long long)grid.x * grid.y <= SPLITK_MAX_TILES) {
+    // the last-arriving slice of a tile finishes it in the same launch
+    unsigned* base = nullptr;
+    SARD_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_splitk_cnt));
+    const unsigned slot = (unsigned)((reinterpret_cast<uintptr_t>(st) >> 4) * 2654435761u >> 28) & (SPLITK_SLOTS - 1);
+    sard_launch(gemm_fast_kernel<BN, 4, NT, false, 3, true>, grid, 256, smem, st, *g, base + (size_t)slot * SPLITK_MAX_TILES);
+    SARD_LAUNCH_OK("gemm_fast_kernel<splitk>");
+    return 0;
+  }
+  sard_launch(gemm_fast_kernel<BN, 4, NT, false, 3, true>, grid, 256, smem, st, *g, (unsigned*)nullptr);
   SARD_LAUNCH_OK("gemm_fast_kernel<splitk>");
   sard_launch(splitk_finish_kernel<NT>, grid_for((long long)g->M * (g->N / 4), 256), 256, 0, st, *g, S);
   SARD_LAUNCH_OK("splitk_finish_kernel");
