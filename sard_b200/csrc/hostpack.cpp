@@ -101,10 +101,57 @@ bool get_out(PyObject* o, Out& out, int itemsize, std::vector<Py_buffer>& keep) 
 
 struct Item { Src obs, edges, stage, nn, body, hf, ob, go, act; bool has_act; };
 
+// Fast path of collect(): the batch is a list of lists / tuples of numpy arrays (what the reference's sampler produces).
+// The walk only READS object headers (list item pointers, array data pointers, shapes, strides) and touches no reference
+// count, so it is split over threads while the calling thread keeps the GIL: the 450 k array headers of a 50 k-transition
+// batch are scattered over the heap and the single-threaded walk was bound by those cache misses (10 ms -> ~2 ms).
+// Returns false (without setting an error) when anything else is met; the caller then takes the general path.
+bool collect_parallel(PyObject* states, PyObject* actions, std::vector<Item>& items, int nthreads) {
+  if (!PyList_Check(states)) return false;
+  const bool has_act = actions && actions != Py_None;
+  if (has_act && !PyList_Check(actions)) return false;
+  const Py_ssize_t T = PyList_GET_SIZE(states);
+  if (has_act && PyList_GET_SIZE(actions) < T) return false;
+  if (T < 4096 || nthreads < 2) return false;
+  std::vector<char> bad((size_t)nthreads, 0);
+  auto work = [&](int w) {
+    const Py_ssize_t lo = T * w / nthreads, hi = T * (w + 1) / nthreads;
+    for (Py_ssize_t t = lo; t < hi; ++t) {
+      PyObject* st = PyList_GET_ITEM(states, t);
+      PyObject** slot_objs = nullptr;
+      if (PyList_Check(st) && PyList_GET_SIZE(st) == 8) slot_objs = ((PyListObject*)st)->ob_item;
+      else if (PyTuple_Check(st) && PyTuple_GET_SIZE(st) == 8) slot_objs = ((PyTupleObject*)st)->ob_item;
+      if (!slot_objs) { bad[(size_t)w] = 1; return; }
+      Item& it = items[(size_t)t];
+      Src* slots[8] = {&it.obs, &it.edges, &it.stage, &it.nn, &it.body, &it.hf, &it.ob, &it.go};
+      for (int k = 0; k < 8; ++k) {
+        PyObject* o = slot_objs[k];
+        if (!PyArray_Check(o) || !get_src_numpy((PyArrayObject*)o, *slots[k])) { bad[(size_t)w] = 1; return; }
+      }
+      it.has_act = has_act;
+      if (has_act) {
+        PyObject* a = PyList_GET_ITEM(actions, t);
+        if (!PyArray_Check(a) || !get_src_numpy((PyArrayObject*)a, it.act)) { bad[(size_t)w] = 1; return; }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int w = 1; w < nthreads; ++w) th.emplace_back(work, w);
+  work(0);
+  for (auto& x : th) x.join();
+  for (char b : bad) if (b) return false;
+  return true;
+}
+
 bool collect(PyObject* states, PyObject* actions, std::vector<Item>& items, std::vector<Py_buffer>& keep) {
   const Py_ssize_t T = PySequence_Size(states);
   if (T < 0) return false;
   items.resize((size_t)T);
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = hw >= 16 ? 8 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
+    if (collect_parallel(states, actions, items, nt)) return true;
+  }
   const bool has_act = actions && actions != Py_None;
   for (Py_ssize_t t = 0; t < T; ++t) {
     PyObject* st = PySequence_GetItem(states, t);

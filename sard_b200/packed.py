@@ -13,6 +13,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -78,12 +80,50 @@ def host_tensors_from_rollout(host: HostRollout, pin: bool = True) -> dict:
     return out
 
 
-def host_tensors_from_lists(states, actions=None, rewards=None, masks=None, pin: bool = True, nthreads: int = 8):
+class _PinnedPool:
+    """Pinned staging memory reused from one ``update_params`` to the next: page-locking 150 MB per call
+    (cudaHostAlloc) cost 5-10 ms, sometimes hundreds.  One upload is in flight at most: ``wait()`` blocks until the
+    event recorded after the previous upload has passed before the buffers are overwritten."""
+
+    def __init__(self):
+        self.buf = {}
+        self.event = None
+        self.seq = 0
+        self.owner = None          # id() of the host dict whose tensors live in the pool
+
+    def wait(self):
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+        self.seq = 0
+
+    def take(self, shape, dtype):
+        n = int(np.prod(shape)) if len(shape) else 1
+        key = (self.seq, dtype)
+        self.seq += 1
+        b = self.buf.get(key)
+        if b is None or b.numel() < n:
+            b = torch.empty(max(int(n * 1.2), 16), dtype=dtype, pin_memory=True)
+            self.buf[key] = b
+        return b[:n].view(shape)
+
+    def uploaded(self, device):
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(device))
+
+
+_PINNED = _PinnedPool()
+
+
+def host_tensors_from_lists(states, actions=None, rewards=None, masks=None, pin: bool = True, nthreads: int = 0):
     """Same from the reference's list-of-states batch; uses the native packer when it is built."""
     if _hostpack is None or isinstance(states[0][0], torch.Tensor):
         return host_tensors_from_rollout(host_rollout_from_lists(states, actions, rewards, masks), pin)
+    if nthreads <= 0:
+        nthreads = int(os.environ.get('SARD_PACK_THREADS', min(16, os.cpu_count() or 8)))
     handle, T, n, e, d, H, O, G = _hostpack.collect(states, actions)       # one walk over the Python objects
-    mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
+    _PINNED.wait()                                                          # the previous upload from these buffers is over
+    mk = (lambda shape, dt: _PINNED.take(shape, dt)) if pin else (lambda shape, dt: torch.empty(shape, dtype=dt))
     out = {'obs': mk((n, d), torch.float32), 'actions': mk((n, 8), torch.float32), 'node_ptr': mk((T + 1,), torch.int32),
            'edge_ptr': mk((T + 1,), torch.int32), 'esrc': mk((e,), torch.int32), 'edst': mk((e,), torch.int32),
            'stage': mk((T,), torch.int32), 'body_ind': mk((n,), torch.int32), 'hfield': mk((T, H), torch.float32),
@@ -97,6 +137,7 @@ def host_tensors_from_lists(states, actions=None, rewards=None, masks=None, pin:
         else:
             np.copyto(t.numpy(), _np(v).reshape(-1), casting='unsafe')
         out[k] = t
+    _PINNED.owner = id(out) if pin else None
     return out
 
 
@@ -109,6 +150,7 @@ class PackedRollout:
             raise _lib.SardError('PackedRollout needs a CUDA device: the SARD B200 path has no CPU implementation')
         self.device = device
         ht = host if isinstance(host, dict) else host_tensors_from_rollout(host, pin)
+        pooled = isinstance(ht, dict) and _PINNED.owner == id(ht)
         self.T = int(ht['stage'].shape[0])
         self.n_total = int(ht['node_ptr'][-1])
         self.e_total = int(ht['edge_ptr'][-1])
@@ -127,6 +169,8 @@ class PackedRollout:
         self.stage, self.body_ind = up('stage'), up('body_ind')
         self.ext = [up('hfield'), up('obj'), up('goal')]
         self.rewards, self.masks = up('rewards'), up('masks')
+        if pooled:
+            _PINNED.uploaded(device)                        # the pool's buffers may be rewritten once this has passed
         i32 = dict(dtype=torch.int32, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.in_ptr = torch.empty(self.n_total + 1, **i32)
@@ -175,8 +219,14 @@ class PackedRollout:
                                  '(the reference would fail to reshape, transform2act_policy.py:449)')
 
     def live_indices(self, stage: int) -> np.ndarray:
-        node_stage = np.repeat(self.stage_np, self.num_nodes_np)
-        return np.unique(self.body_np[node_stage == stage])
+        if getattr(self, '_live', None) is None:          # one histogram over (stage, body index) for the three stages
+            node_stage = np.repeat(self.stage_np, self.num_nodes_np)
+            hi = int(self.body_np.max()) + 1 if len(self.body_np) else 1
+            if len(self.body_np) and int(self.body_np.min()) < 0:
+                raise _lib.SardError('negative body index')
+            cnt = np.bincount(node_stage * hi + self.body_np, minlength=3 * hi).reshape(3, hi)
+            self._live = [np.flatnonzero(cnt[s]) for s in range(3)]
+        return self._live[stage]
 
 
 class Run:

@@ -29,3 +29,20 @@ def test_native_packer_rejects_inconsistent_states():
     b.states[3][0] = b.states[3][0][:, :-1]          # wrong observation width
     with pytest.raises(ValueError):
         packed.host_tensors_from_lists(b.states, b.actions, b.rewards, b.masks, pin=False)
+
+
+def test_native_packer_threaded_walk_matches_python_packing():
+    """>= 4096 transitions: the object walk runs on several threads (read-only, under the caller's GIL)."""
+    roll = synthetic.generate_rollout(synthetic.ENV_SHAPES['manipulation_box'], 5000, seed=6, min_exec=5, max_exec=60, dtype=np.float32)
+    b = roll.to_traj_batch()
+    got = packed.host_tensors_from_lists(b.states, b.actions, b.rewards, b.masks, pin=False)
+    want = packed.host_tensors_from_rollout(packed.host_rollout_from_lists(b.states, b.actions, b.rewards, b.masks), pin=False)
+    for k in want:
+        assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), k
+    # a tuple state and a non-numpy slot send the whole batch down the general path: same result
+    b.states[17] = tuple(b.states[17])
+    import array
+    b.states[18][2] = array.array('q', [int(x) for x in np.asarray(b.states[18][2]).reshape(-1)])     # buffer protocol, not numpy
+    got2 = packed.host_tensors_from_lists(b.states, b.actions, b.rewards, b.masks, pin=False)
+    for k in want:
+        assert torch.equal(got2[k], want[k]), k
