@@ -652,12 +652,14 @@ class Transform2ActAgent:
             num_agents = arena.num_nodes_np[attr_ids]
             log2['num_agent_mean'] = float(np.mean(num_agents))
             log2['num_agent_std'] = float(np.std(num_agents))
-            edst = arena.edst.cpu().numpy()
-            eptr = arena.edge_ptr.cpu().numpy()
+            # the packed host copies are still there (pinned staging of this arena): no device round trip for the log
+            host = getattr(arena, '_host', None)
+            edst = host['edst'].numpy() if host is not None else arena.edst.cpu().numpy()
+            eptr = host['edge_ptr'].numpy() if host is not None else arena.edge_ptr.cpu().numpy()
             designs = Counter(tuple(edst[eptr[i]:eptr[i + 1]].tolist()) for i in attr_ids)
             log2['num_designs'] = len(designs)
             log2['num_designs_std'] = float(np.std(list(designs.values())))
-            acts = arena.actions.cpu().numpy()
+            acts = host['actions'].numpy() if host is not None else arena.actions.cpu().numpy()
             a = [np.abs(acts[arena.node_ptr_np[i]:arena.node_ptr_np[i + 1], 1:3]).mean() for i in attr_ids]
             log2['attr_mean'] = float(np.mean(a))
             log2['attr_std'] = float(np.std(a))
