@@ -17,7 +17,13 @@ from __future__ import annotations
 from collections import OrderedDict, defaultdict
 from typing import Dict, List
 
+import os
+
 import numpy as np
+
+# SARD_REFERENCE_RNG=1 (or group_action.REFERENCE_RNG = True before constructing the agent): consume the global numpy RNG
+# exactly like the reference's constructors do, for seed-for-seed comparable runs (off: construction draws nothing)
+REFERENCE_RNG = os.environ.get('SARD_REFERENCE_RNG', '0') != '0'
 import torch
 
 
@@ -99,6 +105,17 @@ class DihedralSubgroup:
         self.orbits = OrderedDict()
         self.orbits_trans_matrix = OrderedDict()
         self.reprentative_set_defaults = OrderedDict()
+        if REFERENCE_RNG:
+            # The reference decides "is the orientation ambiguous" with 100 random probes per visited leg
+            # (group_action.py:118-121) where this module compares the matrices exactly.  The outcome is the same, but
+            # the reference's probes advance the global numpy RNG that later shuffles the minibatches (agent :333) and
+            # drives the subgroup exploration: replay the same draws so a seeded run follows the reference's stream.
+            not_chosen = np.ones(n, dtype=np.int64)
+            for i in range(n):
+                if np.any(not_chosen):              # sic: "any leg left", not "this leg left" (group_action.py:110)
+                    for _ in range(100):
+                        np.random.randn(2, 1)
+                    not_chosen[self.adj_matrix[i] == 1] = 0
         seen = np.zeros(n, dtype=bool)
         for i in range(n):
             if seen[i]:

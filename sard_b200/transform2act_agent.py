@@ -404,6 +404,11 @@ class Transform2ActAgent:
                 m.train(True)
         T = arena.T
         M = self.mini_batch_size if self.use_mini_batch else T
+        if not self.use_mini_batch:
+            # the reference's full-batch branch (agent :361-367) ignores valid_loss and always steps; the device gate of
+            # this path would skip such a step
+            raise NotImplementedError('mini_batch_size >= min_batch_size (the full-batch branch of update_policy) is not '
+                                      'on the CUDA path: it steps regardless of the KL gate; derl.yml uses minibatches')
         batch_design = bool(self.cfg.agent_specs.get('batch_design', False))
         n_mb = T // M
         if world > 1:

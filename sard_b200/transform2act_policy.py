@@ -56,6 +56,10 @@ class Transform2ActPolicy(nn.Module):
         self.attr_action_dim = agent.attr_design_dim
         self.action_dim = self.control_action_dim + self.attr_action_dim + 1
         self.skel_uniform_prob = cfg.get('skel_uniform_prob', 0.0)
+        if self.skel_uniform_prob > 0:
+            # distributions.py:46-50 mixes a uniform term into the skeleton log-prob; the fused categorical loss kernel
+            # computes the plain log-softmax, so a non-zero value would silently train on the wrong ratios
+            raise NotImplementedError('skel_uniform_prob > 0 is not on the CUDA training path (derl.yml leaves it at 0)')
         self.shared_std_att = 1
         self.shared_std_ctl = 1
         if self.control_action_dim != 1 or self.action_dim != _lib.ACTION_DIM:

@@ -106,3 +106,30 @@ def test_transform_policy_output_matches_reference_goldens():
         np.testing.assert_allclose(tie.numpy(), z[f'{i}.tie'], atol=0, err_msg=str(name))
         sk, _ = policy.transform_policy_output(torch.from_numpy(z[f'{i}.skel_in']), body)
         assert np.array_equal(sk.numpy(), z[f'{i}.skel_out']), name
+
+
+def test_reference_rng_mode_consumes_the_same_numpy_draws():
+    """With REFERENCE_RNG the constructors advance the global numpy RNG exactly like the reference's (whose randomised
+    orientation probes sit between np.random.seed and the first minibatch shuffle); needs the staged reference."""
+    import os
+    import numpy as np
+    import pytest
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip('oracle/_ref not staged (no /root/reference on this machine)')
+    ref_runner.install_shims()
+    from design_opt.models.group_action import LearnedGroup as RefGroup
+    from sard_b200 import group_action as ga
+    for ns, name in (([4], 'H_4>0>H_4>4'), ([4], 'K_1>0>K_1>4'), ([3, 4], 'H_3>0>H_3>3')):
+        np.random.seed(7)
+        RefGroup(ns, init_subgroup_name=name)
+        want = np.random.get_state()[1].copy()
+        prev = ga.REFERENCE_RNG
+        ga.REFERENCE_RNG = True
+        try:
+            np.random.seed(7)
+            ga.LearnedGroup(ns, init_subgroup_name=name)
+            got = np.random.get_state()[1].copy()
+        finally:
+            ga.REFERENCE_RNG = prev
+        assert np.array_equal(got, want), (ns, name)
