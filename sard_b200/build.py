@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsard_b200.so')
-SOURCES = ['engine.cu', 'prof.cu', 'pack.cu', 'norm.cu', 'graph.cu', 'gemm.cu', 'gemm_fast.cu', 'gemm_skinny.cu', 'gemm_mma.cu', 'umma.cu', 'jsmlp_tc.cu', 'jsmlp_tc_bwd.cu', 'tower_tc.cu', 'encoder.cu', 'loss.cu', 'gae.cu', 'optim.cu', 'p2p.cu']
+SOURCES = ['engine.cu', 'prof.cu', 'pack.cu', 'norm.cu', 'graph.cu', 'gemm.cu', 'gemm_fast.cu', 'gemm_skinny.cu', 'gemm_mma.cu', 'umma.cu', 'jsmlp_tc.cu', 'jsmlp_tc_bwd.cu', 'tower_tc.cu', 'critic_tc.cu', 'encoder.cu', 'loss.cu', 'gae.cu', 'optim.cu', 'p2p.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "encoder.cuh"
 #include "tower_tc.cuh"
+#include "critic_tc.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
@@ -445,7 +446,16 @@ struct ValueBufs {
   double* rec;
   float* e1[3]; float* cat; int ldcat; float* m[SARD_MAX_MLP]; float* v; float* dv; float* sq;
   float* dcat; float* dm[SARD_MAX_MLP]; float* de1; float* wg; float* wg2; float* wg3; float* encw; float* sk; long long sk_floats;
+  float* cmw;                    // pair copies of the MLP weights for the fused tensor-core forward (critic_tc.cu), or NULL
 };
+
+// the fused tensor-core MLP forward serves the default engine when the shapes are derl.yml's
+static const int g_sard_critic_tc = getenv("SARD_CRITIC_TC") ? atoi(getenv("SARD_CRITIC_TC")) : 1;
+bool critic_uses_tc(const SardValueNet& net) {
+  return g_sard_critic_tc && g_sard_gemm_engine == 4 && net.n_mlp == 2 &&
+         sard_critic_tc_supported(net.mlp[0].in, net.mlp[0].out, net.mlp[1].out, net.n_mlp) && net.mlp[1].in == net.mlp[0].out &&
+         net.mlp[0].act == net.mlp[1].act && net.tower.h[net.tower.L] == net.mlp[0].in;
+}
 
 void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, ValueBufs& vb) {
   carve_tower(b, net.tower, n, B, train, vb.t);
@@ -463,6 +473,7 @@ void carve_value(Bump& b, const SardValueNet& net, int n, int B, bool train, Val
   vb.sk_floats = 1024LL * B;                                 // split-K partial tiles of the MLP GEMMs: S*N <= 1024 columns
   vb.sk = b.f(vb.sk_floats);
   { const long long w = enc_wide_fwd_need(net.enc, B); vb.encw = w > 0 ? b.f(w) : nullptr; }
+  vb.cmw = critic_uses_tc(net) ? b.a256(sard_critic_tc_wsplit_floats()) : nullptr;
   if (train) {
     vb.dcat = b.f((long long)B * vb.ldcat);
     for (int j = 0; j < net.n_mlp; ++j) vb.dm[j] = b.f((long long)B * (maxm > 0 ? maxm : 4));
@@ -519,9 +530,17 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
   SideCtx* side = side_for(as_stream(st));
   SARD_TRY(encoders_forward(net->enc, P, arena, sel, vb.e1, vb.cat + (vb.ldcat - 3 * SARD_EXT_DIM), vb.ldcat, vb.encw,
                             wg_stream(side, st, 2)));
+  if (vb.cmw) SARD_TRY(sard_critic_tc_presplit(P + net->mlp[0].w, P + net->mlp[1].w, vb.cmw, wg_stream(side, st, 1)));
   SARD_TRY(tower_forward(tw, P, arena, sel, vb.t, st));
   // MLP on root rows only: the reference evaluates it on every node and then keeps the roots (critic.py:104-107)
   const int hL = tw.h[tw.L];
+  if (vb.cmw) {
+    // both layers in one tcgen05 launch (critic_tc.cu); h1 is kept for the backward pass only
+    SARD_TRY(side_join(side));
+    site(K_MLP, 0);
+    SARD_TRY(sard_critic_tc_forward(vb.cmw, vb.t.hout, vb.t.root_row, B, P + net->mlp[0].b, P + net->mlp[1].b, net->mlp[0].act,
+                                    bwd ? vb.m[0] : nullptr, vb.cat, vb.ldcat, st));
+  } else
   for (int j = 0; j < net->n_mlp; ++j) {
     SardGemm g = gemm0();
     if (j == 0) { g.A = vb.t.hout; g.lda = hL; g.a_rows = vb.t.root_row; }
