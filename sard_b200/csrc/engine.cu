@@ -597,6 +597,13 @@ extern "C" int sard_value_run(const SardValueNet* net, const SardArena* arena, c
     }
     g.splitk_ws = vb.sk; g.splitk_floats = vb.sk_floats;
     site(K_MLP, 1);
+    if (j == 1 && vb.cmw && ldz % 4 == 0) {
+      // dz1 = (dz2 W2) * act'(h1) in one tcgen05 launch (critic_tc.cu)
+      SARD_TRY(sard_critic_tc_bwd_layer2(vb.cmw, dzj, ldz, vb.m[0], B, net->mlp[0].act, vb.dm[1], st));
+    } else if (j == 0 && vb.cmw && dzj == vb.dm[1]) {
+      // dz_tower[root rows] = (dz1 W1) * act'(hout[root rows]) likewise
+      SARD_TRY(sard_critic_tc_bwd_layer1(vb.cmw, dzj, vb.t.hout, vb.t.root_row, B, tw.L > 0 ? tw.act : SARD_ACT_NONE, vb.t.dz[tw.L], st));
+    } else
     SARD_TRY(sard_linear_bwd_data(&g, st));
     if (j > 0) { dzj = vb.dm[j]; ldz = net->mlp[j - 1].out; }
   }

@@ -342,7 +342,8 @@ static int splitk_slices(const SardGemm* g) {
   const int nkb = g->R / 16;
   int S = 1;
   while (S * 2 <= 8 && S * 2 <= nkb / 4 && ctas * S * 2 <= 296 && (long long)S * 2 * g->M * g->N <= g->splitk_floats) S *= 2;
-  return S;
+  static const int s_min = getenv("SARD_GEMM_SPLITK_MIN") ? atoi(getenv("SARD_GEMM_SPLITK_MIN")) : 4;     // two slices do not pay for the finishing launch
+  return S >= s_min ? S : 1;
 }
 static const int g_wg_minb = getenv("SARD_WG_MINB") ? atoi(getenv("SARD_WG_MINB")) : 3;     // 3 CTAs/SM (80 registers, 32 B of spill): 195.5 -> 191.2 ms
 static const int g_minb = getenv("SARD_GEMM_MINB") ? atoi(getenv("SARD_GEMM_MINB")) : 0;
