@@ -55,6 +55,9 @@ int sard_get_pdl(void);
  * (default 1): forked after each layer's output gradient, joined before the call returns, so the
  * caller's stream semantics are unchanged.  0 = everything on the caller's stream. */
 int sard_set_wgrad_overlap(int enabled);
+/* sard_adam_update without a gradient norm as one launch (gate + bias corrections + Adam) instead of two; bit-identical,
+ * off by default (measured neutral to slightly slower on the bench workload). */
+int sard_set_adam_single_launch(int enabled);
 int sard_get_wgrad_overlap(void);
 
 /* Per-call-site kernel timing for the roofline numbers (CUDA events on the launching stream).
@@ -304,7 +307,8 @@ float* sard_jsmlp_tc_xs_hl(const SardJsmlpTc* a);
 int sard_jsmlp_tc_forward(const SardJsmlpTc* a, sard_stream_t stream);
 /* Backward of the fused JSMLP (padded row space only; in_dim 256, hid 128).  All pair arrays are [n, hi | lo]. */
 typedef struct {
-  const float* dout; int ld_dout;        /* [rows, ld] gradient w.r.t. IL3's output before `post`, ORIGINAL row order (srow maps) */
+  const float* dout; int ld_dout;        /* [rows, ld] gradient w.r.t. IL3's output before `post`, ORIGINAL row order (srow maps);
+                                          * NULL: dOs_hl was already filled by the loss kernel (SardPolicyLoss.dout_sorted_hl) */
   float* dOs_hl;                         /* [n, 64] scratch: dout at sorted positions, 32 columns hi | 32 lo */
   float* dZhl[2];                        /* [n, 2*hid] out: gradients w.r.t. the pre-activations of IL1 ([0]) and IL2 ([1]) */
   float* dxs; int ld_dxs;                /* [n, in_dim] out: gradient w.r.t. the sorted input rows (raw fp32) */
@@ -346,6 +350,10 @@ typedef struct {
   float* dout; int ld_dout;            /* [n, d] gradient w.r.t. the JSMLP output before sin / tie (train), may be NULL */
   float* gstat;                        /* [B, 4+d]: surr, |dlp|, cat-entropy sum, 0, dlogstd[d] per graph (train) */
   float clip_eps, inv_B;               /* 1/global minibatch size */
+  /* optional: the gradient written a second time in the fused JSMLP backward's operand format (sard_jsmlp_tc_backward with
+   * dout == NULL then skips its own formatting launch): dout_sorted_hl[spos[row]] = [hi(32) | lo(32)] (columns >= d zero) and
+   * zero rows at the padding positions (srow[pos] < 0) of the padded body-index sort, pos < rows_cap */
+  float* dout_sorted_hl; const int* spos; const int* srow; int rows_cap; int pad_;
 } SardPolicyLoss;
 /* DiagGaussian.log_prob / entropy (khrylib/rl/core/distributions.py:21-22), per-graph reduction
  * (transform2act_policy.py:390-405), ratio/clip/min (transform2act_agent.py:392-396) and the

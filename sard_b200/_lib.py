@@ -64,7 +64,8 @@ class SardPolicyLoss(C.Structure):
                 ('nd_arena', vp), ('cum', vp), ('node_base', ci), ('ids', vp), ('B', ci),
                 ('actions', vp), ('rep_local', vp), ('advantages', vp), ('fixed_log_probs', vp),
                 ('log_prob_out', vp), ('log_prob_run', vp), ('tied_out', vp), ('dout', vp), ('ld_dout', ci),
-                ('gstat', vp), ('clip_eps', cf), ('inv_B', cf)]
+                ('gstat', vp), ('clip_eps', cf), ('inv_B', cf),
+                ('dout_sorted_hl', vp), ('spos', vp), ('srow', vp), ('rows_cap', ci), ('pad_', ci)]
 
 
 class SardAdamSeg(C.Structure):
@@ -125,6 +126,7 @@ _PROTOS = {
     'sard_set_pdl': (ci, [ci]),
     'sard_get_pdl': (ci, []),
     'sard_set_wgrad_overlap': (ci, [ci]),
+    'sard_set_adam_single_launch': (ci, [ci]),
     'sard_get_wgrad_overlap': (ci, []),
     'sard_prof_enable': (ci, [C.c_uint, ci]),
     'sard_prof_collect': (ci, [P(cd), ci]),

@@ -18,6 +18,8 @@
 int g_sard_wgrad_overlap = 1;
 extern int g_sard_gemm_engine;
 static const int g_sard_tower_tc = getenv("SARD_TOWER_TC") ? atoi(getenv("SARD_TOWER_TC")) : 1;   // fused tcgen05 tower (tower_tc.cu)
+static const int g_sard_fuse_dout = getenv("SARD_FUSE_DOUT") ? atoi(getenv("SARD_FUSE_DOUT")) : 1;   // loss kernel writes the JSMLP backward's operand
+static const int g_sard_side_reduce = getenv("SARD_SIDE_REDUCE") ? atoi(getenv("SARD_SIDE_REDUCE")) : 1; // loss statistics reduced off the chain
 static const int g_sard_fuse_agg = getenv("SARD_FUSE_AGG") ? atoi(getenv("SARD_FUSE_AGG")) : 1;   // GraphConv neighbour sum inside the GEMM loader
 extern "C" int sard_set_wgrad_overlap(int enabled) { g_sard_wgrad_overlap = enabled ? 1 : 0; return 0; }
 extern "C" int sard_get_wgrad_overlap(void) { return g_sard_wgrad_overlap; }
@@ -77,10 +79,17 @@ SideCtx* side_for(cudaStream_t main) {
   SideCtx* c = new SideCtx();
   c->main = main; c->k = 0;
   for (int i = 0; i < N_SIDE; ++i) c->forked[i] = false;
-  int lo = 0, hi = 0;
+  // side streams run `SARD_SIDE_PRIO_DELTA` priority steps below their launching stream (default 1; the least priority of
+  // the device at most): the net whose chain is the critical path is given a high-priority launching stream by the agent
+  int lo = 0, hi = 0, mp = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamGetPriority(main, &mp) != cudaSuccess) { cudaGetLastError(); mp = lo; }
+  static const int delta = getenv("SARD_SIDE_PRIO_DELTA") ? atoi(getenv("SARD_SIDE_PRIO_DELTA")) : 1;
+  int sp = mp + delta;
+  if (sp > lo) sp = lo;
+  if (sp < hi) sp = hi;
   for (int i = 0; i < N_SIDE; ++i)
-    if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, lo) != cudaSuccess) { delete c; return nullptr; }
+    if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, sp) != cudaSuccess) { delete c; return nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
   g_side[key] = c;
   return c;
@@ -813,14 +822,21 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
   if (bwd) {
     L.advantages = arena->advantages; L.fixed_log_probs = arena->fixed_log_probs;
     L.dout = sb.dout; L.ld_dout = sb.ldo; L.gstat = sb.gstat;
+    if (sb.tcb && g_sard_fuse_dout) {
+      // the fused JSMLP backward reads the gradient in its own operand format: the loss kernel writes it there directly
+      L.dout = nullptr;
+      L.dout_sorted_hl = sb.dOs_hl; L.spos = sb.spos; L.srow = sb.srow; L.rows_cap = sb.rows_cap;
+    }
   } else if (!upd) {
     L.log_prob_out = arena->fixed_log_probs;
   }
   if (outputs) SARD_REQUIRE(sb.ldo == s.out_dim || true, "outputs use the padded leading dimension");
   SARD_TRY(stage == SARD_STAGE_SKEL ? sard_cat_loss(&L, st) : sard_gauss_loss(&L, st));
   if (!bwd) return 0;
+  // the column sums (loss statistics, log_std gradients) are only read by the optimiser step: off the chain, on the side
+  // stream the JSMLP weight gradients follow on
   SARD_TRY(sard_loss_reduce(sb.gstat, B, 4 + s.out_dim, stats, s.log_std >= 0 ? G + s.log_std : nullptr, s.out_dim,
-                            s.log_std >= 0 ? P + s.log_std : nullptr, st));
+                            s.log_std >= 0 ? P + s.log_std : nullptr, g_sard_side_reduce ? wg_stream(side, st, 1) : st));
 
   // ---- backward through the JSMLP (sorted row space) ----
   const float* dz = sb.dout; int ldz = sb.ldo; const int* dz_rows = sb.srow;
@@ -829,7 +845,7 @@ extern "C" int sard_policy_run(const SardPolicyNet* net, int stage, const SardAr
     const SardJsmlpTc a = jsmlp_tc_args(s, sb, n, bwd);
     SardJsmlpTcBwd bb;
     memset(&bb, 0, sizeof(bb));
-    bb.dout = sb.dout; bb.ld_dout = sb.ldo; bb.dOs_hl = sb.dOs_hl; bb.dZhl[0] = sb.dZhl[0]; bb.dZhl[1] = sb.dZhl[1];
+    bb.dout = g_sard_fuse_dout ? nullptr : sb.dout; bb.ld_dout = sb.ldo; bb.dOs_hl = sb.dOs_hl; bb.dZhl[0] = sb.dZhl[0]; bb.dZhl[1] = sb.dZhl[1];
     bb.dxs = sb.dxs; bb.ld_dxs = sb.ldxs;
     bb.chunks = sb.chunks; bb.num_chunks = sb.counts + 1; bb.max_chunks = sb.max_chunks; bb.grp_chunk_ptr = sb.grp_chunk_ptr;
     bb.partials = sb.tc_partials;

@@ -513,9 +513,11 @@ extern "C" int sard_jsmlp_tc_backward(const SardJsmlpTc* a, const SardJsmlpTcBwd
   const JsLayout L = sard_js_layout(a->n, a->in_dim, a->out_dim, a->n_slots);
   SARD_REQUIRE(L.total <= a->ws_floats, "jsmlp_tc: workspace too small");
   cudaStream_t st = as_stream(stream);
-  sard_launch(dout_sorted_split_kernel, grid_for((long long)a->n * 8, 256, 8), 256, 0, st, b->dout, b->ld_dout, a->out_dim, a->srow, a->n,
-              b->dOs_hl);
-  SARD_LAUNCH_OK("dout_sorted_split_kernel");
+  if (b->dout) {            // NULL: the loss kernel already wrote dOs_hl (SardPolicyLoss.dout_sorted_hl)
+    sard_launch(dout_sorted_split_kernel, grid_for((long long)a->n * 8, 256, 8), 256, 0, st, b->dout, b->ld_dout, a->out_dim, a->srow, a->n,
+                b->dOs_hl);
+    SARD_LAUNCH_OK("dout_sorted_split_kernel");
+  }
   JsBwdParams p;
   memset(&p, 0, sizeof(p));
   SARD_TRY(sard_tmap_2d(&p.tm_do, b->dOs_hl, a->n, 64, 64, 128, 32));

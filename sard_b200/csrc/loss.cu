@@ -22,8 +22,41 @@ __device__ __forceinline__ float ppo_dlp(float lp, float fixed, float adv, float
   return -inv_B * dr * ratio;      // d(-mean surr)/d lp
 }
 
+
+// Second copy of a row's output gradient in the fused JSMLP backward's operand format (SardPolicyLoss.dout_sorted_hl):
+// 32 columns of TF32-exact high parts | 32 columns of fp32 remainders at the row's position in the padded body-index
+// order; columns >= d are zero.  Saves the separate formatting launch between the loss and the backward kernel.
+__device__ __forceinline__ void store_sorted_hl(float* __restrict__ dst, const float* v /* MAXD */) {
+  float4* p = reinterpret_cast<float4*>(dst);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v[4 * q + 0]) & 0xffffe000u); l.x = v[4 * q + 0] - h.x;
+    h.y = __uint_as_float(__float_as_uint(v[4 * q + 1]) & 0xffffe000u); l.y = v[4 * q + 1] - h.y;
+    h.z = __uint_as_float(__float_as_uint(v[4 * q + 2]) & 0xffffe000u); l.z = v[4 * q + 2] - h.z;
+    h.w = __uint_as_float(__float_as_uint(v[4 * q + 3]) & 0xffffe000u); l.w = v[4 * q + 3] - h.w;
+    p[q] = h; p[8 + q] = l;
+  }
+#pragma unroll
+  for (int q = 2; q < 8; ++q) { p[q] = z; p[8 + q] = z; }
+}
+// blocks past the per-graph ones: zero rows at the padding positions of the sorted order
+__device__ __forceinline__ void zero_sorted_pads(const SardPolicyLoss& a, int first_block) {
+  const int nb = (int)gridDim.x - first_block;
+  const int total = a.rows_cap * 16;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = ((int)blockIdx.x - first_block) * (int)blockDim.x + (int)threadIdx.x; idx < total; idx += nb * (int)blockDim.x) {
+    const int pos = idx >> 4;
+    if (__ldg(a.srow + pos) < 0) reinterpret_cast<float4*>(a.dout_sorted_hl)[idx] = z;
+  }
+}
+#define LOSS_PAD_BLOCKS 64
+
 __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
   pdl_sync();
+  const int graph_blocks = (a.B * 32 + (int)blockDim.x - 1) / (int)blockDim.x;
+  if ((int)blockIdx.x >= graph_blocks) { zero_sorted_pads(a, graph_blocks); return; }
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= a.B) return;
   const int gid = a.ids[g];
@@ -75,9 +108,12 @@ __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
     a.gstat[(size_t)g * W + 2] = 0.f;
     a.gstat[(size_t)g * W + 3] = 0.f;
   }
-  if (!a.dout) return;
+  if (!a.dout && !a.dout_sorted_hl) return;
   for (int j = lane; j < N; j += 32) {
     const int row = r0 + j, an = a.nd_arena[row];
+    float gv[MAXD];
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) gv[c] = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXD; ++c) {
       if (c >= d) break;
@@ -94,8 +130,10 @@ __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
         dmu = coef * (__ldg(a.actions + (size_t)an * SARD_ACTION_DIM + a.act_col + c) - mu) * ivar[c];
       }
       if (a.pre) dmu *= 1.57079632679489662f * cospif(0.5f * a.pre[(size_t)row * a.ld_out + c]);
-      a.dout[(size_t)row * a.ld_dout + c] = dmu;
+      if (a.dout) a.dout[(size_t)row * a.ld_dout + c] = dmu;
+      gv[c] = dmu;
     }
+    if (a.dout_sorted_hl) store_sorted_hl(a.dout_sorted_hl + (size_t)__ldg(a.spos + row) * 64, gv);
   }
 }
 
@@ -103,13 +141,17 @@ extern "C" int sard_gauss_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   if (a->B <= 0) return 0;
   SARD_REQUIRE(a->d >= 1 && a->d <= MAXD, "gauss loss: action dims");
   SARD_REQUIRE(a->log_std != nullptr, "gauss loss: log_std");
-  sard_launch(gauss_loss_kernel, ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream), *a);
+  SARD_REQUIRE(!a->dout_sorted_hl || (a->spos && a->srow && a->rows_cap > 0 && a->advantages), "gauss loss: sorted gradient copy");
+  sard_launch(gauss_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? LOSS_PAD_BLOCKS : 0), 128, 0,
+              as_stream(stream), *a);
   SARD_LAUNCH_OK("gauss_loss_kernel");
   return 0;
 }
 
 __global__ void cat_loss_kernel(const SardPolicyLoss a) {
   pdl_sync();
+  const int graph_blocks = (a.B * 32 + (int)blockDim.x - 1) / (int)blockDim.x;
+  if ((int)blockIdx.x >= graph_blocks) { zero_sorted_pads(a, graph_blocks); return; }
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= a.B) return;
   const int gid = a.ids[g];
@@ -160,10 +202,13 @@ __global__ void cat_loss_kernel(const SardPolicyLoss a) {
     a.gstat[(size_t)g * W + 3] = 0.f;
     for (int c = 0; c < d; ++c) a.gstat[(size_t)g * W + 4 + c] = 0.f;
   }
-  if (!a.dout) return;
+  if (!a.dout && !a.dout_sorted_hl) return;
   for (int j = lane; j < N; j += 32) {
     const int row = r0 + j, an = a.nd_arena[row];
     float l[MAXD], mx = -INFINITY, se = 0.f;
+    float gv[MAXD];
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) gv[c] = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXD; ++c) {
       if (c >= d) break;
@@ -199,15 +244,19 @@ __global__ void cat_loss_kernel(const SardPolicyLoss a) {
       if (tie && c >= a.tie_c0 && c < a.tie_c1) gval = coef * (hot_t[c] - cnt_t * p);
       else gval = coef * ((c == act_j ? 1.f : 0.f) - p);
       (void)self_rep;
-      a.dout[(size_t)row * a.ld_dout + c] = gval;
+      if (a.dout) a.dout[(size_t)row * a.ld_dout + c] = gval;
+      gv[c] = gval;
     }
+    if (a.dout_sorted_hl) store_sorted_hl(a.dout_sorted_hl + (size_t)__ldg(a.spos + row) * 64, gv);
   }
 }
 
 extern "C" int sard_cat_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   if (a->B <= 0) return 0;
   SARD_REQUIRE(a->d >= 2 && a->d <= MAXD, "cat loss: number of actions");
-  sard_launch(cat_loss_kernel, ceil_div((long long)a->B * 32, 128), 128, 0, as_stream(stream), *a);
+  SARD_REQUIRE(!a->dout_sorted_hl || (a->spos && a->srow && a->rows_cap > 0 && a->advantages), "cat loss: sorted gradient copy");
+  sard_launch(cat_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? LOSS_PAD_BLOCKS : 0), 128, 0,
+              as_stream(stream), *a);
   SARD_LAUNCH_OK("cat_loss_kernel");
   return 0;
 }

@@ -133,6 +133,32 @@ extern "C" int sard_adam_prepare(const float* stats, float inv_B, float inv_worl
   return 0;
 }
 
+// torch.optim.Adam's single-tensor update of one element (shared by both kernels below so that they round alike)
+__device__ __forceinline__ void adam_elem(float graw, float scale, float& m, float& v, float& p, float omb1, float omb2,
+                                          float beta2, float step_size, float bc2s, float eps) {
+  // explicit roundings: no contraction choice is left to the compiler, so every kernel that inlines this rounds alike
+  const float g = __fmul_rn(graw, scale);
+  m = __fmaf_rn(__fsub_rn(g, m), omb1, m);                                   // exp_avg.lerp_(grad, 1 - beta1)
+  v = __fmaf_rn(__fmul_rn(omb2, g), g, __fmul_rn(v, beta2));                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
+  p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);
+}
+__device__ __forceinline__ void adam_elem4(const float4 g4, float scale, float4& m4, float4& v4, float4& p4, float omb1,
+                                           float omb2, float beta2, float step_size, float bc2s, float eps) {
+  adam_elem(g4.x, scale, m4.x, v4.x, p4.x, omb1, omb2, beta2, step_size, bc2s, eps);
+  adam_elem(g4.y, scale, m4.y, v4.y, p4.y, omb1, omb2, beta2, step_size, bc2s, eps);
+  adam_elem(g4.z, scale, m4.z, v4.z, p4.z, omb1, omb2, beta2, step_size, bc2s, eps);
+  adam_elem(g4.w, scale, m4.w, v4.w, p4.w, omb1, omb2, beta2, step_size, bc2s, eps);
+}
+__device__ __forceinline__ void zero_segment(const SardAdamSeg& s) {
+  float* g = const_cast<float*>(s.g);
+  const bool vec = ((uintptr_t)g & 15) == 0;
+  const long long n4 = vec ? s.n >> 2 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) g[i] = 0.f;
+}
+
 __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr, float beta1, float beta2, float eps,
                                   int active_mask, const float* __restrict__ ctl_f, const int* __restrict__ ctl_i,
                                   int zero_grads) {
@@ -144,14 +170,7 @@ __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr
   // it was used, so there is nothing to apply and nothing to clear
   if (!((active_mask >> s.group) & 1)) return;
   if (ctl_i[0] == 0) {                                                  // gated step: drop the gradients
-    if (zero_grads) {
-      float* g = const_cast<float*>(s.g);
-      const bool vec = ((uintptr_t)g & 15) == 0;
-      const long long n4 = vec ? s.n >> 2 : 0;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
-        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) g[i] = 0.f;
-    }
+    if (zero_grads) zero_segment(s);
     return;
   }
   const float scale = ctl_f[0];
@@ -162,28 +181,18 @@ __global__ void adam_apply_kernel(const SardAdamSeg* __restrict__ segs, float lr
   const bool vec = (((uintptr_t)s.p | (uintptr_t)s.g | (uintptr_t)s.m | (uintptr_t)s.v) & 15) == 0;
   const long long n4 = vec ? s.n >> 2 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 g4 = reinterpret_cast<const float4*>(s.g)[i], m4 = reinterpret_cast<float4*>(s.m)[i], v4 = reinterpret_cast<float4*>(s.v)[i];
-    float4 p4 = reinterpret_cast<float4*>(s.p)[i];
-    float* g = &g4.x; float* m = &m4.x; float* v = &v4.x; float* pp = &p4.x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gk = g[k] * scale;
-      m[k] = m[k] + (gk - m[k]) * omb1;
-      v[k] = v[k] * beta2 + omb2 * gk * gk;
-      pp[k] = pp[k] - step_size * (m[k] / (sqrtf(v[k]) / bc2s + eps));
-    }
+    const float4 g4 = reinterpret_cast<const float4*>(s.g)[i];
+    float4 m4 = reinterpret_cast<float4*>(s.m)[i], v4 = reinterpret_cast<float4*>(s.v)[i], p4 = reinterpret_cast<float4*>(s.p)[i];
+    adam_elem4(g4, scale, m4, v4, p4, omb1, omb2, beta2, step_size, bc2s, eps);
     reinterpret_cast<float4*>(s.p)[i] = p4;
     reinterpret_cast<float4*>(s.m)[i] = m4;
     reinterpret_cast<float4*>(s.v)[i] = v4;
     if (zero_grads) reinterpret_cast<float4*>(const_cast<float*>(s.g))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
-    const float g = s.g[i] * scale;
-    float m = s.m[i], v = s.v[i];
-    m = m + (g - m) * omb1;                          // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * beta2 + omb2 * g * g;                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    const float denom = sqrtf(v) / bc2s + eps;
-    s.p[i] = s.p[i] - step_size * (m / denom);
+    float m = s.m[i], v = s.v[i], pv = s.p[i];
+    adam_elem(s.g[i], scale, m, v, pv, omb1, omb2, beta2, step_size, bc2s, eps);
+    s.p[i] = pv;
     s.m[i] = m;
     s.v[i] = v;
     if (zero_grads) const_cast<float*>(s.g)[i] = 0.f;
@@ -202,6 +211,126 @@ extern "C" int sard_adam_apply(const SardAdamSeg* segs, int n_seg, long long max
   return 0;
 }
 
+// Gate + bias corrections + Adam in ONE launch (the step without a gradient norm: the critic always, the policy once the
+// reference's one-shot clip is spent).  adam_prepare_kernel's single thread of work is redone by thread 0 of every block
+// that has parameters to update, from the state of the previous step, while the block's other threads already have their
+// loads in flight.  The state stays read-only until every block has passed an arrival counter (ctl_i[4]); the LAST block
+// to arrive publishes the new state (step counters, seen groups, valid flag, log row) and clears the statistics.  Integer
+// atomics only, every block computes from identical inputs: deterministic, bit-identical to prepare + apply.
+struct AdamGate { int valid, mask, seen; float surr_loss, kl, entropy, extra; int steps[SARD_MAX_GROUPS]; };
+__device__ __forceinline__ AdamGate adam_gate_read(const float* stats, const int* ctl_i, float inv_B, float inv_world,
+                                                   float inv_cat_nodes, int use_gate, int active_mask_in) {
+  const volatile float* vs = stats;
+  const volatile int* vi = ctl_i;
+  AdamGate a;
+  const float st0 = vs[0], st1 = vs[1], st2 = vs[2], st4 = vs[4], st5 = vs[5];
+  a.seen = vi[2];
+#pragma unroll
+  for (int g = 0; g < SARD_MAX_GROUPS; ++g) a.steps[g] = vi[8 + g];
+  a.surr_loss = -st0 * inv_B; a.kl = st1 * inv_B; a.entropy = st4 * inv_world + st2 * inv_cat_nodes; a.extra = st5 * inv_B;
+  a.valid = 1;
+  if (use_gate && (a.kl > 0.1f || a.surr_loss > 10.f || !(a.kl == a.kl) || !(a.surr_loss == a.surr_loss))) a.valid = 0;
+  a.mask = active_mask_in;
+  if (a.mask & SARD_ADAM_STICKY) { a.mask &= ~SARD_ADAM_STICKY; a.mask |= a.seen; }
+  return a;
+}
+
+__global__ void __launch_bounds__(256) adam_fused_kernel(const SardAdamSeg* __restrict__ segs, float* stats, float inv_B,
+                                                         float inv_world, float inv_cat_nodes, int use_gate, int active_mask_in,
+                                                         double beta1d, double beta2d, float lr, float eps, float* ctl_f,
+                                                         int* ctl_i, float* log_row) {
+  pdl_sync();
+  __shared__ int sh_i[2];           // valid, mask
+  __shared__ float sh_f[3];         // bc1, bc2s of this block's group, scale (1: no clip on this path)
+  const SardAdamSeg s = segs[blockIdx.y];
+  const bool sticky = (active_mask_in & SARD_ADAM_STICKY) != 0;
+  const bool in_range = (long long)blockIdx.x * blockDim.x < s.n;
+  // can this block have parameters to update?  (sticky: the mask is device state)
+  const bool maybe = in_range && (sticky || ((active_mask_in >> s.group) & 1));
+  const bool vec = (((uintptr_t)s.p | (uintptr_t)s.g | (uintptr_t)s.m | (uintptr_t)s.v) & 15) == 0;
+  const long long n4 = vec ? s.n >> 2 : 0;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  // first pass of the 16-byte path: loads in flight while thread 0 works out the gate
+  const bool pre = maybe && i0 < n4;
+  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = g4, v4 = g4, p4 = g4;
+  if (pre) {
+    g4 = reinterpret_cast<const float4*>(s.g)[i0]; m4 = reinterpret_cast<float4*>(s.m)[i0];
+    v4 = reinterpret_cast<float4*>(s.v)[i0]; p4 = reinterpret_cast<float4*>(s.p)[i0];
+  }
+  if (threadIdx.x == 0) {
+    if (maybe) {
+      const AdamGate a = adam_gate_read(stats, ctl_i, inv_B, inv_world, inv_cat_nodes, use_gate, active_mask_in);
+      const int step = a.steps[s.group & (SARD_MAX_GROUPS - 1)] + (a.valid ? 1 : 0);
+      const double sd = (double)(step > 0 ? step : 1);
+      sh_f[0] = (float)(1.0 - pow(beta1d, sd));
+      sh_f[1] = (float)sqrt(1.0 - pow(beta2d, sd));
+      *reinterpret_cast<volatile float*>(&sh_f[2]) = 1.f;
+      sh_i[0] = a.valid; sh_i[1] = a.mask;
+      __threadfence();                  // the reads above are done before this block counts as arrived
+    }
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(ctl_i + 4), 1u);
+    if (prev == total - 1) {            // every block has read the old state: publish the new one
+      __threadfence();
+      const AdamGate a = adam_gate_read(stats, ctl_i, inv_B, inv_world, inv_cat_nodes, use_gate, active_mask_in);
+      ctl_f[0] = 1.f; ctl_f[1] = (float)a.valid;
+      ctl_i[0] = a.valid;
+      if (sticky) {
+        if (a.valid) ctl_i[2] = a.seen | (active_mask_in & ~SARD_ADAM_STICKY);
+        ctl_i[3] = a.mask;
+      }
+      for (int g = 0; g < SARD_MAX_GROUPS; ++g) {
+        if (!((a.mask >> g) & 1)) continue;
+        const int sg = a.steps[g] + (a.valid ? 1 : 0);
+        ctl_i[8 + g] = sg;
+        const double q = (double)(sg > 0 ? sg : 1);
+        ctl_f[8 + g] = (float)(1.0 - pow(beta1d, q));
+        ctl_f[16 + g] = (float)sqrt(1.0 - pow(beta2d, q));
+      }
+      if (log_row) {
+        log_row[0] = a.surr_loss; log_row[1] = a.entropy; log_row[2] = a.kl; log_row[3] = (float)a.valid;
+        log_row[4] = 0.f; log_row[5] = a.extra;
+      }
+      for (int i = 0; i < 16; ++i) stats[i] = 0.f;
+      ctl_i[4] = 0;
+    }
+  }
+  if (!maybe) return;
+  __syncthreads();
+  if (!((sh_i[1] >> s.group) & 1)) return;
+  if (sh_i[0] == 0) { zero_segment(s); return; }                        // gated step: drop the gradients
+  const float beta1 = (float)beta1d, beta2 = (float)beta2d;
+  const float bc1 = sh_f[0], bc2s = sh_f[1], scale = *reinterpret_cast<volatile float*>(&sh_f[2]);
+  const float step_size = lr / bc1;
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pre) {
+    adam_elem4(g4, scale, m4, v4, p4, omb1, omb2, beta2, step_size, bc2s, eps);
+    reinterpret_cast<float4*>(s.p)[i0] = p4; reinterpret_cast<float4*>(s.m)[i0] = m4; reinterpret_cast<float4*>(s.v)[i0] = v4;
+    reinterpret_cast<float4*>(const_cast<float*>(s.g))[i0] = z4;
+  }
+  for (long long i = i0 + stride; i < n4; i += stride) {
+    g4 = reinterpret_cast<const float4*>(s.g)[i]; m4 = reinterpret_cast<float4*>(s.m)[i];
+    v4 = reinterpret_cast<float4*>(s.v)[i]; p4 = reinterpret_cast<float4*>(s.p)[i];
+    adam_elem4(g4, scale, m4, v4, p4, omb1, omb2, beta2, step_size, bc2s, eps);
+    reinterpret_cast<float4*>(s.p)[i] = p4; reinterpret_cast<float4*>(s.m)[i] = m4; reinterpret_cast<float4*>(s.v)[i] = v4;
+    reinterpret_cast<float4*>(const_cast<float*>(s.g))[i] = z4;
+  }
+  for (long long i = n4 * 4 + i0; i < s.n; i += stride) {
+    float m = s.m[i], v = s.v[i], pv = s.p[i];
+    adam_elem(s.g[i], scale, m, v, pv, omb1, omb2, beta2, step_size, bc2s, eps);
+    s.p[i] = pv; s.m[i] = m; s.v[i] = v;
+    const_cast<float*>(s.g)[i] = 0.f;
+  }
+}
+
+// sard_adam_update without a gradient norm as ONE launch (adam_fused_kernel) instead of prepare + apply.  Measured on the
+// bench workload: 101.8 ms vs 101.0 ms per update (the per-block gate costs what the saved launch gains, and the tails of
+// both nets overlap other work anyway) -> off by default; kept, with its bit-equality test, for schedules where the
+// optimiser tail is exposed.  Env SARD_ADAM_FUSED=1 or sard_set_adam_single_launch(1).
+static int g_sard_adam_single_launch = getenv("SARD_ADAM_FUSED") ? atoi(getenv("SARD_ADAM_FUSED")) : 0;
+extern "C" int sard_set_adam_single_launch(int enabled) { g_sard_adam_single_launch = enabled ? 1 : 0; return 0; }
+
 // Fused optimiser tail: [sum-of-squares partials ->] gate / clip / bias corrections -> Adam, and the gradient bucket
 // (statistics + every segment's gradients) is left zeroed for the next step.  g_sq == NULL: no clipping (critic).
 extern "C" int sard_adam_update(float* stats, float inv_B, float inv_world, float inv_cat_nodes, const float* g_sq,
@@ -210,6 +339,15 @@ extern "C" int sard_adam_update(float* stats, float inv_B, float inv_world, floa
                                 const SardAdamSeg* segs, int n_seg, long long max_seg_len, float lr, float eps,
                                 sard_stream_t stream) {
   cudaStream_t st = as_stream(stream);
+  if (!g_sq && stats && g_sard_adam_single_launch && n_seg > 0 && max_seg_len > 0) {
+    int gx = (int)((max_seg_len + 1023) / 1024);
+    if (gx > 256) gx = 256;
+    dim3 grid(gx, n_seg);
+    sard_launch(adam_fused_kernel, grid, 256, 0, st, segs, stats, inv_B, inv_world, inv_cat_nodes, use_gate, active_mask, beta1, beta2,
+                lr, eps, ctl_f, ctl_i, log_row);
+    SARD_LAUNCH_OK("adam_fused_kernel");
+    return 0;
+  }
   int nb = 0;
   if (g_sq) {
     nb = (int)((n_sq + 1023) / 1024);

@@ -524,3 +524,63 @@ def test_clip_and_adam_match_torch(L):
             assert lg[3] == 0.0
         assert_close(p.cpu(), ref.detach(), rtol=2e-6, atol=5e-7, what=f'params after step {it}')
     assert int(st.ctl_i[8].item()) == 4 and int(st.ctl_i[1].item()) == 0
+
+
+@pytest.mark.parametrize('sticky', [False, True])
+def test_adam_update_single_launch_equals_prepare_plus_apply(L, sticky):
+    """sard_adam_update without a gradient norm runs gate + bias corrections + Adam in ONE launch (adam_fused_kernel);
+    bit-identical to sard_adam_prepare + sard_adam_apply over several steps with three groups, absent groups, a gated
+    step and ragged / unaligned segments, and it leaves statistics and gradients zeroed."""
+    from sard_b200 import _lib
+    from sard_b200.nets import AdamState
+    g = torch.Generator().manual_seed(21)
+    sizes = [(4096, 0), (4096, 0), (1234, 1), (4096, 2), (3, 2), (4095, 1)]
+    n = sum(s for s, _ in sizes) + 8
+    p0 = torch.randn(n, generator=g)
+    states = []
+    for _ in range(2):
+        p = p0.cuda().clone()
+        st = AdamState(3e-4)
+        st.ensure(p)
+        grad = torch.zeros(16 + n, device='cuda')
+        segs, o = [], 0                                   # the first three segments are 16-byte aligned, the rest are not
+        for sz, grp in sizes:
+            segs.append((p.data_ptr() + 4 * o, st.m.data_ptr() + 4 * o, st.v.data_ptr() + 4 * o, grad.data_ptr() + 4 * (16 + o), sz, grp))
+            o += sz
+        st.set_segments(segs, p.device)
+        states.append((p, st, grad, torch.zeros(8, device='cuda')))
+    masks = [0b111, 0b001, 0b011, 0b101, 0b111, 0b001]
+    for it, mask in enumerate(masks):
+        gk = torch.randn(n, generator=g).cuda() * 0.1
+        kl = 0.9 if it == 3 else 0.02                     # step 3 is gated off
+        m = mask | (_lib.ADAM_STICKY if sticky else 0)
+        for which, (p, st, grad, log) in enumerate(states):
+            grad.zero_()
+            o = 0
+            for sz, grp in sizes:                          # only the active groups receive gradients
+                if (mask >> grp) & 1:
+                    grad[16 + o:16 + o + sz] = gk[o:o + sz]
+                o += sz
+            grad[0] = -0.3; grad[1] = kl * 8; grad[2] = 0.7; grad[4] = 1.1; grad[5] = 2.0
+            if which == 0:
+                L.lib.sard_set_adam_single_launch(1)
+                L.check(L.lib.sard_adam_update(L.ptr(grad), 0.125, 1.0, 0.5, None, 0, None, 40.0, 1, 1, m, 0.9, 0.999,
+                                               L.ptr(st.ctl_f), L.ptr(st.ctl_i), L.ptr(log), L.ptr(st.segs), st.n_seg, st.max_seg,
+                                               3e-4, 1e-8, L.stream()))
+                L.lib.sard_set_adam_single_launch(0)
+            else:
+                L.check(L.lib.sard_adam_prepare(L.ptr(grad), 0.125, 1.0, 0.5, None, 40.0, 1, 1, m, 0.9, 0.999, L.ptr(st.ctl_f),
+                                                L.ptr(st.ctl_i), L.ptr(log), L.stream()))
+                L.check(L.lib.sard_adam_apply(L.ptr(st.segs), st.n_seg, st.max_seg, 3e-4, 0.9, 0.999, 1e-8, m, L.ptr(st.ctl_f),
+                                              L.ptr(st.ctl_i), L.stream()))
+        (pa, sa, ga, la), (pb, sb_, gb, lb) = states
+        if not torch.equal(pa, pb):
+            bad = (pa != pb).nonzero().flatten()
+            raise AssertionError(f'parameters differ after step {it}: {bad.numel()} entries, first {bad[:4].tolist()} last {bad[-4:].tolist()}, '
+                                 f'max diff {float((pa - pb).abs().max())}; ctl_i {sa.ctl_i[:16].tolist()} vs {sb_.ctl_i[:16].tolist()}; '
+                                 f'ctl_f {sa.ctl_f[8:11].tolist()} {sa.ctl_f[16:19].tolist()} vs {sb_.ctl_f[8:11].tolist()} {sb_.ctl_f[16:19].tolist()}')
+        assert torch.equal(sa.m, sb_.m) and torch.equal(sa.v, sb_.v)
+        assert torch.equal(la[:6], lb[:6]), (la, lb)
+        ia, ib = sa.ctl_i.cpu(), sb_.ctl_i.cpu()
+        assert torch.equal(ia[8:16], ib[8:16]) and ia[0] == ib[0] and ia[2] == ib[2] and int(ia[4]) == 0
+        assert float(ga.abs().sum()) == 0.0               # statistics and gradients left zeroed

@@ -39,6 +39,7 @@ def main():
     if only:                      # run one net alone: how long is each stream's own chain?
         skip = agent.value_net.engine if only == 'policy' else agent.policy_net.engine
         skip.train_step = lambda *a, **k: None
+        skip.train_step_prefetched = lambda *a, **k: None
     for overlap in (True, False):
         agent.overlap_nets = overlap
         for _ in range(2):
