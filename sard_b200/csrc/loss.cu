@@ -41,17 +41,16 @@ __device__ __forceinline__ void store_sorted_hl(float* __restrict__ dst, const f
 #pragma unroll
   for (int q = 2; q < 8; ++q) { p[q] = z; p[8 + q] = z; }
 }
-// blocks past the per-graph ones: zero rows at the padding positions of the sorted order
+// blocks past the per-graph ones: zero rows at the padding positions of the sorted order (one position per thread: a
+// single dependent load per thread instead of a strided loop of them)
 __device__ __forceinline__ void zero_sorted_pads(const SardPolicyLoss& a, int first_block) {
-  const int nb = (int)gridDim.x - first_block;
-  const int total = a.rows_cap * 16;
+  const int pos = ((int)blockIdx.x - first_block) * (int)blockDim.x + (int)threadIdx.x;
+  if (pos >= a.rows_cap || __ldg(a.srow + pos) >= 0) return;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int idx = ((int)blockIdx.x - first_block) * (int)blockDim.x + (int)threadIdx.x; idx < total; idx += nb * (int)blockDim.x) {
-    const int pos = idx >> 4;
-    if (__ldg(a.srow + pos) < 0) reinterpret_cast<float4*>(a.dout_sorted_hl)[idx] = z;
-  }
+  float4* d = reinterpret_cast<float4*>(a.dout_sorted_hl + (size_t)pos * 64);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) d[q] = z;
 }
-#define LOSS_PAD_BLOCKS 64
 
 __global__ void gauss_loss_kernel(const SardPolicyLoss a) {
   pdl_sync();
@@ -142,7 +141,7 @@ extern "C" int sard_gauss_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   SARD_REQUIRE(a->d >= 1 && a->d <= MAXD, "gauss loss: action dims");
   SARD_REQUIRE(a->log_std != nullptr, "gauss loss: log_std");
   SARD_REQUIRE(!a->dout_sorted_hl || (a->spos && a->srow && a->rows_cap > 0 && a->advantages), "gauss loss: sorted gradient copy");
-  sard_launch(gauss_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? LOSS_PAD_BLOCKS : 0), 128, 0,
+  sard_launch(gauss_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? ceil_div(a->rows_cap, 128) : 0), 128, 0,
               as_stream(stream), *a);
   SARD_LAUNCH_OK("gauss_loss_kernel");
   return 0;
@@ -255,7 +254,7 @@ extern "C" int sard_cat_loss(const SardPolicyLoss* a, sard_stream_t stream) {
   if (a->B <= 0) return 0;
   SARD_REQUIRE(a->d >= 2 && a->d <= MAXD, "cat loss: number of actions");
   SARD_REQUIRE(!a->dout_sorted_hl || (a->spos && a->srow && a->rows_cap > 0 && a->advantages), "cat loss: sorted gradient copy");
-  sard_launch(cat_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? LOSS_PAD_BLOCKS : 0), 128, 0,
+  sard_launch(cat_loss_kernel, ceil_div((long long)a->B * 32, 128) + (a->dout_sorted_hl ? ceil_div(a->rows_cap, 128) : 0), 128, 0,
               as_stream(stream), *a);
   SARD_LAUNCH_OK("cat_loss_kernel");
   return 0;

@@ -371,7 +371,9 @@ __global__ void __launch_bounds__(TT_THREADS, TT_MINB) tower_fwd_tc_kernel(const
     // ---- in_fc operand: normalised + clamped input row, 64 columns of K per pass.  The warp's 32 x 32 block of x is
     // read with whole-row (128-byte) transactions into the warp's own staging region and picked up one row per lane.
     for (int h = 0; h < 2; ++h) {
-      if (h >= nhalf && !p.XH) break;
+      // D < 64: the second 64 columns of XH are all zero (the column of ones sits at D) and are not stored at all -- the
+      // weight-gradient kernel's tensor map ends at column 64 and TMA zero-fills the rest of its box
+      if (h >= nhalf && (!p.XH || p.D < 64)) break;
       const int k0 = h * 64 + c.c0;
       {
         const int pc = lane & 7, kcol = k0 + pc * 4;
@@ -905,7 +907,9 @@ int sard_tower_tc_wgrad(const SardTower& tw, const SardSel* sel, const TowerTcBu
     SARD_TRY(sard_tmap_slab(&p.tm_pa[l], tb.PA[l], n, 128, 128, TWG_ROWS, 4));
     SARD_TRY(sard_tmap_slab(&p.tm_ph[l], tb.PH[l], n, 64, 64, TWG_ROWS, 2));
   }
-  SARD_TRY(sard_tmap_slab(&p.tm_xh, tb.XH, n, 128, 128, TWG_ROWS, 4));
+  // D < 64: only the first two 32-column slabs of XH exist (forward kernel); the out-of-bounds slabs of the box are
+  // zero-filled by TMA (and still count towards the stage's transaction bytes)
+  SARD_TRY(sard_tmap_slab(&p.tm_xh, tb.XH, n, tw.D < 64 ? 64 : 128, 128, TWG_ROWS, 4));
   SARD_TRY(sard_tmap_slab(&p.tm_z0, tb.PZ0, n, 64, 64, TWG_ROWS, 2));
   p.n = n; p.chunk_rows = tb.chunk_rows; p.L = tw.L; p.partials = tb.partials;
   static bool configured[SARD_MAX_DEVICES] = {};
