@@ -455,6 +455,16 @@ int sard_allreduce_p2p_pad_bytes(void);
 int sard_allreduce_p2p(const void* bufs_dev, const void* pads_dev, int rank, int world, long long n_floats,
                        unsigned first_barrier_value, sard_stream_t stream);
 
+/* All-gather of one small record (RunningNorm moments of a run, record_doubles = 1 + 2D) over peer memory: rank r's record
+ * is stored into every rank's symmetric board at chunk_offset_doubles + r * record_doubles, between two in-kernel barriers
+ * ("every rank is ready to receive" / "every record has landed").  boards_dev / pads_dev: DEVICE arrays of `world`
+ * pointers to every rank's board and signal pad (sard_allgather_p2p_pad_bytes() bytes, zero-initialised, used by this
+ * chain of all-gathers only); first_barrier_value: 1, 3, 5, ... per call on that pad.  Replaces the NCCL all-gather of the
+ * prefetched gather phase (the reference is single-process: SURVEY.md 8e). */
+int sard_allgather_p2p_pad_bytes(void);
+int sard_allgather_p2p(const void* boards_dev, const void* pads_dev, int rank, int world, long long chunk_offset_doubles,
+                       const double* local_record, int record_doubles, unsigned first_barrier_value, sard_stream_t stream);
+
 /* =====================================================================================
  * Network schedules: the whole forward/backward of one net over one run, launched from C++
  * (one host call per minibatch instead of ~100)

@@ -161,6 +161,8 @@ _PROTOS = {
     'sard_gae_f64': (ci, [vp, vp, vp, ci, cd, cd, vp, vp, vp, vp]),
     'sard_allreduce_p2p_pad_bytes': (ci, []),
     'sard_allreduce_p2p': (ci, [vp, vp, ci, ci, cll, C.c_uint, vp]),
+    'sard_allgather_p2p_pad_bytes': (ci, []),
+    'sard_allgather_p2p': (ci, [vp, vp, ci, ci, cll, vp, ci, C.c_uint, vp]),
     'sard_sqnorm': (ci, [vp, cll, vp, vp, vp]),
     'sard_adam_prepare': (ci, [vp, cf, cf, cf, vp, cf, ci, ci, ci, cd, cd, vp, vp, vp, vp]),
     'sard_adam_apply': (ci, [vp, ci, cll, cf, cf, cf, cf, ci, vp, vp, vp]),

@@ -78,19 +78,63 @@ class Comm:
             p2p = None
         return t, p2p
 
+    def symmetric_board(self, n_doubles: int, device):
+        """A zeroed fp64 symmetric buffer for the peer-memory moments all-gather (``P2PAllGather``), or None when symmetric
+        memory is unavailable (the all-gathers then go through NCCL).  Collective."""
+        import os
+        if os.environ.get('SARD_P2P_ALLGATHER', '1') == '0' or self.dist.get_backend(self.group) != 'nccl' or self.world > 8:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = self.group if self.group is not None else self.dist.group.WORLD
+            t = symm.empty(n_doubles, dtype=torch.float64, device=device)
+            hdl = symm.rendezvous(t, group=g.group_name)
+            t.zero_()
+            board = P2PAllGather(t, hdl, self)
+            ok = torch.ones(1, device=device)
+        except Exception as e:                 # noqa: BLE001
+            import warnings
+            warnings.warn(f'sard_b200: symmetric memory unavailable ({e!r}); moments all-gather through NCCL')
+            board, ok = None, torch.zeros(1, device=device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)       # all ranks or none
+        return board if float(ok.item()) >= 1.0 else None
+
+    def _host_group(self):
+        """Group for small HOST arrays (counts, live indices): gloo over the same ranks, so that host metadata never
+        takes a device round trip through the training streams.  Created on first use (collective); None when gloo is
+        unavailable (the arrays then go through the device group)."""
+        if getattr(self, '_hg', None) is None:
+            if self.dist.get_backend(self.group) != 'nccl':
+                self._hg = (self.group,)
+            else:
+                try:
+                    ranks = list(range(self.world)) if self.group is None else self.dist.get_process_group_ranks(self.group)
+                    self._hg = (self.dist.new_group(ranks=ranks, backend='gloo'),)
+                except Exception:               # noqa: BLE001
+                    self._hg = ('device',)
+        return self._hg[0]
+
+    def _host_allreduce(self, a: np.ndarray, op) -> np.ndarray:
+        g = self._host_group()
+        if isinstance(g, str):                  # no gloo: device round trip
+            t = torch.from_numpy(np.ascontiguousarray(a)).to('cuda')
+            self.dist.all_reduce(t, op=op, group=self.group)
+            return t.cpu().numpy()
+        t = torch.from_numpy(np.array(a, copy=True))
+        self.dist.all_reduce(t, op=op, group=g)
+        return t.numpy()
+
+    def sum_array(self, a: np.ndarray) -> np.ndarray:
+        """Element-wise sum of a small host integer array over the ranks (host-synchronous)."""
+        return self._host_allreduce(a, self.dist.ReduceOp.SUM)
+
     def max_array(self, a: np.ndarray) -> np.ndarray:
         """Element-wise maximum of a small host integer array over the ranks (host-synchronous)."""
-        dev = 'cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu'
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
-        return t.cpu().numpy()
+        return self._host_allreduce(a, self.dist.ReduceOp.MAX)
 
     def min_int(self, v: int, device=None) -> int:
         """Minimum of a host integer over the ranks (one small collective; host-synchronous)."""
-        dev = device if device is not None else ('cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu')
-        t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
-        return int(t.item())
+        return int(self._host_allreduce(np.array([int(v)], dtype=np.int64), self.dist.ReduceOp.MIN)[0])
 
 
 class P2PAllReduce:
@@ -114,6 +158,43 @@ class P2PAllReduce:
         self.seq += 1
 
 
+class P2PAllGather:
+    """The library's peer-memory all-gather of RunningNorm moment records (csrc/p2p.cu) over one symmetric board:
+    ``[slot][key][world][rec_max]`` doubles, ``key`` < N_KEYS (the critic's tower, or the policy's three stages)."""
+    PAD_OFFSET = 1024
+    N_KEYS, N_SLOTS = 4, 2
+
+    def __init__(self, tensor, hdl, comm: Comm):
+        need = self.PAD_OFFSET + lib.sard_allgather_p2p_pad_bytes()
+        if hdl.signal_pad_size < need:
+            raise RuntimeError(f'signal pad of {hdl.signal_pad_size} bytes < {need}')
+        self.tensor, self.hdl = tensor, hdl
+        self.rank, self.world = comm.rank, comm.world
+        self.rec_max = tensor.numel() // (self.N_KEYS * self.N_SLOTS * self.world)
+        dev = tensor.device
+        self.bufs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.pads = torch.tensor([int(p) + self.PAD_OFFSET for p in hdl.signal_pad_ptrs], dtype=torch.int64, device=dev)
+        self.seq = 0
+
+    @staticmethod
+    def doubles(world: int, d_max: int) -> int:
+        return P2PAllGather.N_KEYS * P2PAllGather.N_SLOTS * world * (1 + 2 * d_max)
+
+    def offset(self, key: int, slot: int) -> int:
+        return (slot * self.N_KEYS + key) * self.world * self.rec_max
+
+    def chunk(self, key: int, slot: int, rec: int) -> torch.Tensor:
+        """This rank's copy of the gathered records of (key, slot): ``[world * rec]`` doubles."""
+        assert rec <= self.rec_max
+        o = self.offset(key, slot)
+        return self.tensor[o:o + self.world * rec]
+
+    def allgather(self, local: torch.Tensor, key: int, slot: int, st: int):
+        check(lib.sard_allgather_p2p(ptr(self.bufs), ptr(self.pads), self.rank, self.world, self.offset(key, slot), ptr(local),
+                                     local.numel(), (2 * self.seq + 1) & 0xffffffff, st))
+        self.seq += 1
+
+
 class _EngineBase:
     def __init__(self, module):
         self.module = module
@@ -128,6 +209,31 @@ class _EngineBase:
         self.zero_grad_semantics = 'none'
         self.comm: Optional[Comm] = None       # data parallel: set before the first sync (symmetric gradient bucket)
         self.p2p: Optional[P2PAllReduce] = None
+        self.board: Optional[P2PAllGather] = None   # data parallel: moments all-gather of the prefetched gather phase
+        self._board_keys = set()
+
+    def _alloc_board(self, dev, d_max: int = 256):
+        """Collective (every rank, same place: right after the gradient bucket); once per device."""
+        if self.board is not None and self.board.tensor.device == dev:
+            return
+        self.board = None
+        self._board_keys.clear()
+        if self.comm is not None and self.comm.world > 1:
+            self.board = self.comm.symmetric_board(P2PAllGather.doubles(self.comm.world, d_max), dev)
+
+    def _board_key(self, key):
+        """(board key, slot) of a prefetch-path moments key ``('v', slot)`` / ``(stage, slot)``, else None."""
+        if self.board is None or not isinstance(key, tuple):
+            return None
+        k, slot = key
+        return (0 if k == 'v' else int(k)), int(slot)
+
+    def _allgather(self, key, ml, ma, comm, st):
+        if key in self._board_keys:                    # `ma` is this rank's chunk of the board
+            bk = self._board_key(key)
+            self.board.allgather(ml, bk[0], bk[1], st)
+        else:
+            comm.allgather(ml, ma)
 
     def _alloc_bucket(self, n: int, dev) -> torch.Tensor:
         n = (n + 3) // 4 * 4
@@ -154,7 +260,13 @@ class _EngineBase:
         if world > 1:
             ma = self.mom_all.get(key)
             if ma is None or ma.numel() != rec * world:
-                ma = torch.zeros(rec * world, dtype=torch.float64, device=self.device)
+                bk = self._board_key(key)
+                if bk is not None and rec <= self.board.rec_max:
+                    ma = self.board.chunk(bk[0], bk[1], rec)       # the peers store their records straight into it
+                    self._board_keys.add(key)
+                else:
+                    self._board_keys.discard(key)
+                    ma = torch.zeros(rec * world, dtype=torch.float64, device=self.device)
                 self.mom_all[key] = ma
         return ml, ma
 
@@ -183,6 +295,7 @@ class ValueEngine(_EngineBase):
             self.store.adopt(dev)
             self.GA = self._alloc_bucket(N_STATS + self.store.size, dev)
             self.ws.clear(); self.mom_local.clear(); self.mom_all.clear()
+            self._alloc_board(dev)
             rebuilt = True
         m = self.module
         if rebuilt or self.net is None:
@@ -277,7 +390,7 @@ class ValueEngine(_EngineBase):
         check(lib.sard_value_run(C.byref(net), C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, ptr(ml), None, 1,
                                  self.GA.data_ptr() + 4 * 5, ptr(ws), ws.numel(), st if st is not None else stream()))
         if world > 1:
-            comm.allgather(ml, ma)
+            self._allgather(('v', slot), ml, ma, comm, st if st is not None else stream())
 
     def compute_prefetched(self, arena: PackedRollout, run: Run, B_global: int, slot: int, world: int = 1,
                            st: Optional[int] = None):
@@ -395,6 +508,7 @@ class PolicyEngine(_EngineBase):
             total += (sizes[s] + 3) // 4 * 4
             self.gt_end[s] = total
         self.GA = self._alloc_bucket(total, dev)
+        self._alloc_board(dev)
         net = SardPolicyNet()
         _encoders(self.store, (m.hfield_enc, m.obj_enc, m.goal_enc), net.enc)
         net.nconst = m.sym_embed_dim if m.enable_infer else 0
@@ -545,8 +659,9 @@ class PolicyEngine(_EngineBase):
             if run is None:
                 if world > 1 and active_global[s]:         # another rank has graphs of this stage: empty record
                     ml, ma = self._moments((s, slot), net.stage[s].tower.D, world)
-                    ml.zero_()
-                    comm.allgather(ml, ma)
+                    with torch.cuda.stream(torch.cuda.ExternalStream(st, device=self.device)):
+                        ml.zero_()
+                    self._allgather((s, slot), ml, ma, comm, st)
                 continue
             if net.stage[s].tie_c1 > net.stage[s].tie_c0 and not arena.has_orbits:
                 raise _lib.SardError('orbit representatives missing: call PackedRollout.set_orbits first')
@@ -555,7 +670,7 @@ class PolicyEngine(_EngineBase):
             check(lib.sard_policy_run(C.byref(net), s, C.byref(arena.c), C.byref(run.sel), 1, PHASE_GATHER, 0.0, 0.0, ptr(ml),
                                       None, 1, ptr(self.GA), None, None, ptr(ws), ws.numel(), st))
             if world > 1:
-                comm.allgather(ml, ma)
+                self._allgather((s, slot), ml, ma, comm, st)
 
     def compute_prefetched(self, arena: PackedRollout, runs: List[Optional[Run]], B_global: int, clip_eps: float, slot: int,
                            world: int = 1, active_global: Optional[Sequence[bool]] = None, st: Optional[int] = None):

@@ -75,6 +75,30 @@ def test_select_action_batched_equals_per_state(cuda_device):
     ag.policy_net.eval()
     act, act_env = ag.policy_net.select_action(b.states, mean_action=True)
     assert act.shape == (roll.obs.shape[0], 8) and act.dtype == np.float64
+    # oracle side (not the CUDA path against itself): the batched mean actions are the oracle's distribution parameters of
+    # policy_forward -- control means, clamped attribute means (columns the subgroup symmetrizer leaves alone) and the
+    # arg-max of the tied skeleton logits with the root forced to the no-op (policy.py:339-381)
+    O, psd, _, spec = oracle_of(ag, shape)
+    roll64 = [[torch.tensor(np.asarray(x, dtype=np.float64)) if i in (0, 5, 6, 7) else (torch.tensor(x) if i == 1 else x) for i, x in enumerate(s)]
+              for s in b.states]
+    with torch.no_grad():
+        fw = O.policy_forward(psd, spec, roll64, training=False)
+    starts = np.concatenate([[0], np.cumsum(fw['num_nodes'])])
+    rows_of = lambda sid: np.concatenate([np.arange(starts[t], starts[t + 1]) for t in range(len(b.states)) if fw['stage_of'][t] == sid] or [np.zeros(0, int)]).astype(int)
+    cad = ag.policy_net.control_action_dim
+    if fw['control'] is not None:
+        assert_close(act[rows_of(2), :cad], fw['control']['mean'].numpy(), rtol=1e-4, atol=2e-5, what='control mean vs oracle')
+    if fw['attr'] is not None:
+        want = fw['attr']['mean'].clamp(-1, 1).numpy()
+        assert_close(act[rows_of(1), cad + 2:cad + 5], want[:, 2:5], rtol=1e-4, atol=2e-5, what='tied attribute means vs oracle')
+    if fw['skel'] is not None:
+        want = fw['skel']['logits'].argmax(dim=1).numpy().astype(np.float64)
+        want[fw['skel']['body'].numpy() == 0] = 0
+        got = act_env[rows_of(0), -1]
+        lg = fw['skel']['logits'].numpy()
+        top2 = np.sort(lg, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-4                  # rows without a near-tie of the two largest logits
+        assert np.array_equal(got[clear], want[clear]), 'skeleton arg-max vs oracle'
     at = 0
     for t, s in enumerate(b.states):
         a1, e1 = ag.policy_net.select_action([s], mean_action=True)

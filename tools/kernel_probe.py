@@ -28,7 +28,15 @@ def collect(lib, cap):
 
 
 def main():
-    dev = torch.device('cuda', 0)
+    world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    comm = None
+    if world > 1:                                          # under torchrun: the data-parallel schedule, rank 0 reports
+        import torch.distributed as dist
+        from sard_b200.engine import Comm
+        dist.init_process_group('nccl', device_id=dev)
+        comm = Comm()
     T = int(os.environ.get('T', 50000))
     env = os.environ.get('ENV', 'locomotion_ft')
     mode = os.environ.get('MODE', 'serial')
@@ -36,8 +44,8 @@ def main():
     d = dict(DERL_YML)
     d.update(min_batch_size=T, mini_batch_size=int(os.environ.get('M', 2048)), num_optim_epoch=int(os.environ.get('EPOCHS', 2)))
     torch.manual_seed(0); np.random.seed(1234)
-    agent = Transform2ActAgent(Config(d), torch.float32, dev, 0, 1, env=synthetic.SyntheticEnv(shape))
-    roll = synthetic.generate_rollout(shape, T, seed=1234, dtype=np.float32)
+    agent = Transform2ActAgent(Config(d), torch.float32, dev, 0, 1, env=synthetic.SyntheticEnv(shape), comm=comm)
+    roll = synthetic.generate_rollout(shape, T, seed=1234 + rank, dtype=np.float32)
     arena = agent.pack(roll)
     agent._prepare(arena)
     gen = torch.Generator(device=dev).manual_seed(99)
@@ -59,6 +67,11 @@ def main():
     torch.cuda.synchronize()
     names, rows = collect(lib, cap)
     lib.sard_prof_kernels_enable(0)
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     span = rows[:, 3].max()
     print(f'{len(rows)} launches; span {span:.1f} ms; mode {mode}; env {env}')
     dur = rows[:, 3] - rows[:, 2]
