@@ -10,10 +10,17 @@
  *
  * Conventions: plain C; every pointer is caller-owned DEVICE memory unless the comment says
  * "host"; sizes are host integers; `stream` is a cudaStream_t passed as void*; functions only
- * enqueue work on `stream` (no hidden allocation, no synchronisation, no global mutable state
- * beyond the thread-local error string); the return value is 0 on success or a non-zero code,
- * with sard_last_error_string() describing the failure.  fp32 arithmetic unless stated; integer
- * layouts are int32.  All kernels are deterministic (no floating-point atomics).
+ * enqueue work on `stream` (no device allocation, no synchronisation); the return value is 0 on
+ * success or a non-zero code, with sard_last_error_string() describing the failure.  fp32
+ * arithmetic unless stated; integer layouts are int32.  All kernels are deterministic (no
+ * floating-point atomics).
+ *
+ * Process-global state, all of it host side: the scheduling switches set through sard_set_* below
+ * (GEMM engine, programmatic dependent launch, side-stream overlap, single-launch Adam; defaults
+ * from SARD_* environment variables at load), the side streams / events the library creates once
+ * per (device, launching stream) for sard_value_run / sard_policy_run, the per-device kernel
+ * attribute flags, the profiling buffers of sard_prof_*, the launch counter and the thread-local
+ * error string.  None of it changes results.
  */
 #ifndef SARD_B200_H
 #define SARD_B200_H
