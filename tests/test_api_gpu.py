@@ -246,3 +246,61 @@ def test_action_server_serves_the_batched_policy(cuda_device):
     for i, ((a, ae), (wa, wae)) in enumerate(zip(got, want)):
         assert_close(a, wa, rtol=1e-5, atol=1e-6, what=f'action {i}')
         assert_close(ae, wae, rtol=1e-5, atol=1e-6, what=f'action_env {i}')
+
+
+def test_keyed_action_server_serves_each_subgroup_like_the_oracle(cuda_device):
+    """the neighbour subgroups of optimize_policy (agent :244-256) are evaluated concurrently through one
+    action server, every request keyed by its subgroup name.  The rows a keyed client gets must be the oracle's
+    distribution parameters under THAT subgroup (embedding and orbit tie both follow the key), never another one's."""
+    import threading
+    from sard_b200 import synthetic
+    from sard_b200.action_server import ActionServer
+    torch.cuda.set_device(cuda_device)
+    shape = synthetic.ENV_SHAPES['point_nav']
+    names = ['H_4>0>H_4>4', 'K_1>0>K_1>4', 'H_2>0>H_2>4']
+    ag = make_agent(shape, names[0])
+    # all four legs alike: symmetric under every subgroup above
+    roll = synthetic.generate_rollout(shape, 36, seed=5, orbits=synthetic.SYMMETRIC_ORBITS['H_1_0'], min_exec=3, max_exec=6)
+    b = roll.to_traj_batch()
+    ag.policy_net.eval()
+    roll64 = [[torch.tensor(np.asarray(x, dtype=np.float64)) if i in (0, 5, 6, 7) else (torch.tensor(x) if i == 1 else x) for i, x in enumerate(s)]
+              for s in b.states]
+    group = ag.policy_net.group
+    start = group.cur_subgroup_name
+    want = {}
+    for nm in names:                                       # oracle side, one subgroup at a time
+        group.set_cur_subgroup_name(nm)
+        O, psd, _, spec = oracle_of(ag, shape)
+        with torch.no_grad():
+            want[nm] = O.policy_forward(psd, spec, roll64, training=False)
+    group.set_cur_subgroup_name(start)
+    srv = ActionServer(ag.policy_net, max_batch=12, max_wait_ms=10.0)
+    clients = {nm: srv.client(key=nm) for nm in names}
+    got = {nm: [None] * len(b.states) for nm in names}
+
+    def work(nm):
+        for i, s in enumerate(b.states):
+            got[nm][i] = clients[nm].select_action([s], True)
+
+    srv.start()
+    th = [threading.Thread(target=work, args=(nm,)) for nm in names]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    srv.stop()
+    assert group.cur_subgroup_name == start, 'the server must leave the policy on its own subgroup'
+    cad = ag.policy_net.control_action_dim
+    for nm in names:
+        fw = want[nm]
+        act = np.concatenate([a for a, _ in got[nm]])
+        starts = np.concatenate([[0], np.cumsum(fw['num_nodes'])])
+        rows_of = lambda sid: np.concatenate([np.arange(starts[t], starts[t + 1]) for t in range(len(b.states)) if fw['stage_of'][t] == sid]).astype(int)
+        assert fw['control'] is not None and fw['attr'] is not None
+        assert_close(act[rows_of(2), :cad], fw['control']['mean'].numpy(), rtol=1e-4, atol=2e-5, what=f'{nm}: control mean vs oracle')
+        assert_close(act[rows_of(1), cad + 2:cad + 5], fw['attr']['mean'].clamp(-1, 1).numpy()[:, 2:5], rtol=1e-4, atol=2e-5,
+                     what=f'{nm}: tied attribute means vs oracle')
+    # the subgroups really differ on the design stage (different embedding and tie), so a mixed-up key would show
+    a0 = np.concatenate([a for a, _ in got[names[0]]])
+    a1 = np.concatenate([a for a, _ in got[names[1]]])
+    assert np.abs(a0 - a1).max() > 1e-4
