@@ -51,3 +51,21 @@ def test_cpu_device_is_refused():
         PackedRollout(roll, 'cpu')
     with pytest.raises(_lib.SardError):
         estimate_advantages(torch.zeros(4), torch.ones(4), torch.zeros(4, 1), 0.99, 0.95)
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every prototype of include/sard_b200.h has as many parameters as its ctypes binding (sard_b200/_lib.py): a call
+    through a stale binding would pass garbage in the missing registers instead of failing."""
+    from sard_b200 import _lib
+    src = open(os.path.join(ROOT, 'include', 'sard_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = re.findall(r'\b(sard_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;', src, flags=re.S)
+    assert len(protos) >= 28
+    seen = set()
+    for name, params in protos:
+        params = ' '.join(params.split())
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        res, args = _lib._PROTOS[name]
+        assert len(args) == n, f'{name}: header has {n} parameters, the binding {len(args)}'
+        seen.add(name)
+    assert seen == set(_lib.EXPORTS)
