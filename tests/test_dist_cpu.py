@@ -75,6 +75,15 @@ def _worker(rank, world, port, out):
     c2 = torch.from_numpy(np.concatenate([plan2.stage_graphs, plan2.stage_nodes], axis=1))
     comm.allreduce(c2)                                      # same shape on every rank: no hang, no corruption
     assert np.all(c2[:, :3].sum(1).numpy() == 64 * world)
+    # 5. host metadata over the host group (the agent's per-epoch stage counts, the union of live body indices): the input
+    #    array is left untouched, every rank gets the same result
+    mine = np.concatenate([plan2.stage_graphs, plan2.stage_nodes], axis=1)
+    keep = mine.copy()
+    tot = comm.sum_array(mine)
+    assert np.array_equal(mine, keep) and np.array_equal(tot, c2.numpy())
+    mask = np.zeros((3, 16), dtype=np.int64)
+    mask[rank, [rank, 5 + rank]] = 1
+    assert [np.flatnonzero(m).tolist() for m in comm.max_array(mask)] == [[0, 5], [1, 6], []]
     out.put((rank, perm[:8].tolist(), counts.numpy().tolist()))
     dist.barrier()
     dist.destroy_process_group()
